@@ -1,0 +1,263 @@
+"""ctypes binding of libb200rans.so (include/b200rans.h).
+
+The function names and argument meaning mirror the reference's C interface
+(htscodecs/rANS_static4x16.h:41-64), so the parity tests read like calls to the
+reference.  There is no Python or CPU implementation behind these calls: if the
+CUDA library is missing or no GPU is usable they raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200rans.so")
+
+RANS_ORDER_PACK = 0x80
+RANS_ORDER_RLE = 0x40
+RANS_ORDER_CAT = 0x20
+RANS_ORDER_NOSZ = 0x10
+RANS_ORDER_STRIPE = 0x08
+RANS_ORDER_X32 = 0x04
+RANS_ORDER_STRIPE_NO0 = 1 << 16
+RANS_ORDER_SIMD_AUTO = 1 << 17
+
+EXPORTS = [
+    "rans_compress_bound_4x16", "rans_compress_to_4x16", "rans_compress_4x16",
+    "rans_uncompress_to_4x16", "rans_uncompress_4x16", "rans_set_cpu",
+    "b200rans_set_device", "b200rans_device_count", "b200rans_host_alloc", "b200rans_host_free",
+    "b200rans_compress_batch", "b200rans_uncompress_batch", "b200rans_uncompressed_size",
+    "b200rans_compress_batch_dev_bound", "b200rans_compress_batch_dev",
+    "b200rans_uncompress_batch_dev", "b200rans_compress_batch_multi",
+    "b200rans_uncompress_batch_multi", "b200rans_launch_count", "b200rans_version",
+]
+
+_lib = None
+_libc = C.CDLL(None)
+_libc.free.argtypes = [C.c_void_p]
+_libc.free.restype = None
+
+
+class B200RansError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the CUDA library.  Raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200RansError(
+                "libb200rans.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                "fqzcomp5_b200 has no CPU path")
+        L = C.CDLL(LIB_PATH)
+        vp, u32, i32, sz = C.c_void_p, C.c_uint, C.c_int, C.c_size_t
+        pu32, pi32 = C.POINTER(C.c_uint), C.POINTER(C.c_int)
+        L.rans_compress_bound_4x16.argtypes = [u32, i32]
+        L.rans_compress_bound_4x16.restype = u32
+        L.rans_compress_to_4x16.argtypes = [vp, u32, vp, pu32, i32]
+        L.rans_compress_to_4x16.restype = vp
+        L.rans_compress_4x16.argtypes = [vp, u32, pu32, i32]
+        L.rans_compress_4x16.restype = vp
+        L.rans_uncompress_to_4x16.argtypes = [vp, u32, vp, pu32]
+        L.rans_uncompress_to_4x16.restype = vp
+        L.rans_uncompress_4x16.argtypes = [vp, u32, pu32]
+        L.rans_uncompress_4x16.restype = vp
+        L.rans_set_cpu.argtypes = [i32]
+        L.b200rans_set_device.argtypes = [i32]
+        L.b200rans_host_alloc.argtypes = [sz]
+        L.b200rans_host_alloc.restype = vp
+        L.b200rans_host_free.argtypes = [vp]
+        L.b200rans_compress_batch.argtypes = [i32, vp, vp, vp, vp, sz, vp, vp]
+        L.b200rans_uncompress_batch.argtypes = [i32, vp, vp, vp, vp, vp]
+        L.b200rans_uncompressed_size.argtypes = [vp, u32]
+        L.b200rans_uncompressed_size.restype = C.c_int64
+        L.b200rans_compress_batch_dev_bound.argtypes = [i32, vp, vp]
+        L.b200rans_compress_batch_dev_bound.restype = sz
+        L.b200rans_compress_batch_dev.argtypes = [vp, i32, vp, vp, vp, vp, vp, sz, vp, vp]
+        L.b200rans_uncompress_batch_dev.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.b200rans_compress_batch_multi.argtypes = [i32, i32, vp, vp, vp, vp, vp, sz, vp, vp]
+        L.b200rans_uncompress_batch_multi.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
+        L.b200rans_launch_count.restype = C.c_uint64
+        L.b200rans_version.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _check(rc, what):
+    if rc:
+        raise B200RansError("%s failed with status %d (see stderr)" % (what, rc))
+
+
+# ---------------------------------------------------------------- reference-shaped calls
+def rans_compress_bound_4x16(size, order):
+    return int(lib().rans_compress_bound_4x16(size, order))
+
+
+def rans_compress_to_4x16(data, order, cap=None):
+    """Compress one buffer.  Returns bytes, or None where the C call returns NULL."""
+    L = lib()
+    data = bytes(data)
+    n = len(data)
+    src = C.create_string_buffer(data, max(n, 1))
+    if cap is None:
+        cap = rans_compress_bound_4x16(n, order)
+    dst = C.create_string_buffer(cap + 8)
+    sz = C.c_uint(cap)
+    r = L.rans_compress_to_4x16(C.addressof(src), n, C.addressof(dst), C.byref(sz), order)
+    return dst.raw[:sz.value] if r else None
+
+
+def rans_compress_4x16(data, order):
+    """out == NULL form: the library malloc()s, we free()."""
+    L = lib()
+    data = bytes(data)
+    src = C.create_string_buffer(data, max(len(data), 1))
+    sz = C.c_uint(0)
+    r = L.rans_compress_4x16(C.addressof(src), len(data), C.byref(sz), order)
+    if not r:
+        return None
+    out = C.string_at(r, sz.value)
+    _libc.free(r)
+    return out
+
+
+def rans_uncompress_to_4x16(comp, ulen):
+    L = lib()
+    comp = bytes(comp)
+    src = C.create_string_buffer(comp, max(len(comp), 1))
+    dst = C.create_string_buffer(max(ulen, 1))
+    sz = C.c_uint(ulen)
+    r = L.rans_uncompress_to_4x16(C.addressof(src), len(comp), C.addressof(dst), C.byref(sz))
+    return dst.raw[:sz.value] if r else None
+
+
+def rans_uncompress_4x16(comp):
+    L = lib()
+    comp = bytes(comp)
+    src = C.create_string_buffer(comp, max(len(comp), 1))
+    sz = C.c_uint(0)
+    r = L.rans_uncompress_4x16(C.addressof(src), len(comp), C.byref(sz))
+    if not r:
+        return None
+    out = C.string_at(r, sz.value)
+    _libc.free(r)
+    return out
+
+
+# ---------------------------------------------------------------- batched host API
+class PinnedBuffer:
+    """Page-locked host memory from the library, viewed as a numpy uint8 array."""
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        self.ptr = lib().b200rans_host_alloc(max(self.nbytes, 1))
+        if not self.ptr:
+            raise B200RansError("pinned allocation of %d bytes failed" % nbytes)
+        self.array = np.ctypeslib.as_array((C.c_ubyte * max(self.nbytes, 1)).from_address(self.ptr))[:self.nbytes]
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().b200rans_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _addr(a):
+    return a.ctypes.data
+
+
+def compress_batch(buf, offsets, sizes, orders, out=None, ngpu=1, block_of=None):
+    """Compress n slices of one host array.
+
+    buf: uint8 numpy array (pinned for full PCIe speed); offsets/sizes/orders: per stream.
+    Returns (out_array, out_off, out_size); stream k is out_array[out_off[k]:out_off[k]+out_size[k]].
+    """
+    L = lib()
+    n = len(sizes)
+    base = _addr(buf)
+    ptrs = (np.asarray(offsets, np.uint64) + np.uint64(base)).astype(np.uint64)
+    sizes = np.ascontiguousarray(sizes, np.uint32)
+    orders = np.ascontiguousarray(orders, np.int32)
+    if out is None:
+        cap = int(L.b200rans_compress_batch_dev_bound(n, _addr(sizes), _addr(orders))) + 256 * max(ngpu, 1)
+        out = np.empty(cap, np.uint8)
+    out_off = np.zeros(n, np.uint64)
+    out_size = np.zeros(n, np.uint32)
+    if ngpu == 1:
+        rc = L.b200rans_compress_batch(n, _addr(ptrs), _addr(sizes), _addr(orders), _addr(out), out.size,
+                                       _addr(out_off), _addr(out_size))
+    else:
+        bo = None if block_of is None else np.ascontiguousarray(block_of, np.int32)
+        rc = L.b200rans_compress_batch_multi(ngpu, n, _addr(ptrs), _addr(sizes), _addr(orders),
+                                             _addr(bo) if bo is not None else None, _addr(out), out.size,
+                                             _addr(out_off), _addr(out_size))
+    _check(rc, "b200rans_compress_batch")
+    return out, out_off, out_size
+
+
+def uncompress_batch(comp, comp_off, comp_size, out, out_off, out_size, ngpu=1, block_of=None):
+    """Decompress n streams held in one host array into slices of `out`.
+
+    out_size[k] is the capacity (exact length for NOSZ streams).  Returns (sizes, status)."""
+    L = lib()
+    n = len(comp_size)
+    iptr = (np.asarray(comp_off, np.uint64) + np.uint64(_addr(comp))).astype(np.uint64)
+    optr = (np.asarray(out_off, np.uint64) + np.uint64(_addr(out))).astype(np.uint64)
+    isz = np.ascontiguousarray(comp_size, np.uint32)
+    osz = np.array(out_size, np.uint32)
+    status = np.zeros(n, np.int32)
+    if ngpu == 1:
+        rc = L.b200rans_uncompress_batch(n, _addr(iptr), _addr(isz), _addr(optr), _addr(osz), _addr(status))
+    else:
+        bo = None if block_of is None else np.ascontiguousarray(block_of, np.int32)
+        rc = L.b200rans_uncompress_batch_multi(ngpu, n, _addr(iptr), _addr(isz),
+                                               _addr(bo) if bo is not None else None, _addr(optr), _addr(osz),
+                                               _addr(status))
+    _check(rc, "b200rans_uncompress_batch")
+    return osz, status
+
+
+def uncompressed_size(comp):
+    comp = bytes(comp)
+    return int(lib().b200rans_uncompressed_size(comp, len(comp)))
+
+
+# ---------------------------------------------------------------- device-resident API
+def compress_batch_dev(stream, d_in_ptr, in_off, in_size, orders, d_out_ptr, out_cap, d_out_off_ptr,
+                       d_out_size_ptr):
+    """Pointers are raw device addresses (e.g. torch.Tensor.data_ptr()); descriptor arrays are numpy."""
+    in_off = np.ascontiguousarray(in_off, np.uint64)
+    in_size = np.ascontiguousarray(in_size, np.uint32)
+    orders = np.ascontiguousarray(orders, np.int32)
+    rc = lib().b200rans_compress_batch_dev(stream, len(in_size), d_in_ptr, _addr(in_off), _addr(in_size),
+                                           _addr(orders), d_out_ptr, out_cap, d_out_off_ptr, d_out_size_ptr)
+    _check(rc, "b200rans_compress_batch_dev")
+
+
+def uncompress_batch_dev(stream, d_in_ptr, in_off, in_size, d_out_ptr, out_off, out_size, d_out_size_ptr,
+                         d_status_ptr):
+    in_off = np.ascontiguousarray(in_off, np.uint64)
+    in_size = np.ascontiguousarray(in_size, np.uint32)
+    out_off = np.ascontiguousarray(out_off, np.uint64)
+    out_size = np.ascontiguousarray(out_size, np.uint32)
+    rc = lib().b200rans_uncompress_batch_dev(stream, len(in_size), d_in_ptr, _addr(in_off), _addr(in_size),
+                                             d_out_ptr, _addr(out_off), _addr(out_size), d_out_size_ptr,
+                                             d_status_ptr)
+    _check(rc, "b200rans_uncompress_batch_dev")
+
+
+def compress_bound_batch(in_size, orders):
+    in_size = np.ascontiguousarray(in_size, np.uint32)
+    orders = np.ascontiguousarray(orders, np.int32)
+    return int(lib().b200rans_compress_batch_dev_bound(len(in_size), _addr(in_size), _addr(orders)))
+
+
+def launch_count():
+    return int(lib().b200rans_launch_count())

@@ -1,0 +1,729 @@
+// api.cu -- the C ABI of libb200rans.so (include/b200rans.h): per-thread CUDA
+// contexts, batch planning, host<->device staging, and the reference's seven
+// entry points expressed as one-stream batches.  No codec arithmetic happens on
+// the host: every byte of every stream is produced or consumed by the kernels.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <limits.h>
+#include <vector>
+#include <thread>
+#include <mutex>
+#include <atomic>
+
+#include "../../include/b200rans.h"
+#include "kernels.h"
+#include "stripe.h"
+
+using namespace b200;
+
+#define API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+bool cuda_ok(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return true;
+    fprintf(stderr, "libb200rans: %s failed: %s\n", what, cudaGetErrorString(e));
+    return false;
+}
+#define CK(call) do { if (!cuda_ok((call), #call)) return B200RANS_ECUDA; } while (0)
+
+inline size_t al(size_t v, size_t a = 256) { return (v + a - 1) & ~(a - 1); }
+
+struct Arena {
+    uint8_t *p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+    int ensure(size_t need) {
+        if (need <= cap) return 0;
+        size_t want = need + need / 4 + (1 << 20);
+        if (p) { if (pinned) cudaFreeHost(p); else cudaFree(p); p = nullptr; cap = 0; }
+        cudaError_t e = pinned ? cudaHostAlloc((void **)&p, want, cudaHostAllocDefault)
+                               : cudaMalloc((void **)&p, want);
+        if (e != cudaSuccess) {
+            fprintf(stderr, "libb200rans: %s of %zu bytes failed: %s\n",
+                    pinned ? "cudaHostAlloc" : "cudaMalloc", want, cudaGetErrorString(e));
+            p = nullptr;
+            return B200RANS_ENOMEM;
+        }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) { if (pinned) cudaFreeHost(p); else cudaFree(p); } p = nullptr; cap = 0; }
+};
+
+// bump sub-allocator over an arena laid out before allocation (two passes: size, place)
+struct Layout {
+    size_t off = 0;
+    size_t take(size_t bytes, size_t a = 256) { off = al(off, a); size_t o = off; off += bytes; return o; }
+};
+
+constexpr int NSTAGE = 4;
+struct Stage { Arena h; cudaEvent_t ev = nullptr; bool busy = false; };
+
+struct Ctx {
+    int dev = 0;
+    bool ok = false;
+    cudaStream_t st = nullptr;
+    Arena work;                 // device: jobs, slots, scratch, pool
+    Arena io;                   // device: staged inputs / outputs of the host-buffer API
+    Arena hio;                  // pinned: results read back
+    Stage stage[NSTAGE];        // pinned: job descriptors in flight
+    int next_stage = 0;
+    uint64_t launches = 0;
+
+    int init(int device) {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) {
+            fprintf(stderr, "libb200rans: no usable CUDA device (%s); this library has no CPU path\n",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+            return B200RANS_ENODEV;
+        }
+        if (device < 0 || device >= n) return B200RANS_EINVAL;
+        dev = device;
+        CK(cudaSetDevice(dev));
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        hio.pinned = true;
+        for (auto &s : stage) { s.h.pinned = true; CK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming)); }
+        ok = true;
+        return 0;
+    }
+    // pinned staging block for descriptors; waits until its previous use has been consumed
+    int get_stage(size_t bytes, Stage **out) {
+        Stage &s = stage[next_stage];
+        next_stage = (next_stage + 1) % NSTAGE;
+        if (s.busy) { CK(cudaEventSynchronize(s.ev)); s.busy = false; }
+        int r = s.h.ensure(bytes);
+        if (r) return r;
+        *out = &s;
+        return 0;
+    }
+    ~Ctx() {
+        if (!ok) return;
+        cudaSetDevice(dev);
+        cudaStreamSynchronize(st);
+        work.release(); io.release(); hio.release();
+        for (auto &s : stage) { s.h.release(); if (s.ev) cudaEventDestroy(s.ev); }
+        cudaStreamDestroy(st);
+    }
+};
+
+thread_local Ctx *tls_ctx = nullptr;
+thread_local int tls_device = -1;
+struct CtxOwner { ~CtxOwner() { delete tls_ctx; tls_ctx = nullptr; } };
+thread_local CtxOwner tls_owner;
+
+Ctx *get_ctx(int *err) {
+    (void)&tls_owner;
+    int want = tls_device;
+    if (want < 0) {
+        const char *e = getenv("B200RANS_DEVICE");
+        want = e ? atoi(e) : 0;
+    }
+    if (tls_ctx && tls_ctx->dev != want) { delete tls_ctx; tls_ctx = nullptr; }
+    if (!tls_ctx) {
+        Ctx *c = new Ctx();
+        int r = c->init(want);
+        if (r) { delete c; if (err) *err = r; return nullptr; }
+        tls_ctx = c;
+    }
+    cudaSetDevice(tls_ctx->dev);
+    return tls_ctx;
+}
+
+// ---------------------------------------------------------------- planning
+// Effective order after the size-dependent fix-ups the reference applies first
+// (rANS_static4x16pr.c:1256-1265).  Only used to route streams to kernels and to
+// size scratch; the kernels redo the fix-ups themselves.
+inline int effective_order(uint32_t in_size, int order) {
+    if ((order & ORDER_SIMD_AUTO) && in_size >= 50000 && !(order & X_STRIPE)) order |= X_32;
+    if (in_size <= 20) order &= ~X_STRIPE;
+    if (in_size <= 1000) order &= ~X_32;
+    return order;
+}
+
+// Build and run the encode of a batch whose inputs are already on the device.
+// On return (asynchronously on st): d_out holds the packed streams, d_out_off /
+// d_out_size / d_total describe them.
+int enc_core(Ctx &C, cudaStream_t st, int n, const uint8_t *d_in, const uint64_t *in_off,
+             const uint32_t *in_size, const int *order, const uint32_t *caps,
+             uint8_t *d_out, size_t out_cap, uint64_t *d_out_off, uint32_t *d_out_size,
+             uint64_t *d_total) {
+    if (n <= 0) return 0;
+    // ---- pass 1: count jobs and size scratch
+    std::vector<StripePlan> stripes;
+    size_t njobs = 0;
+    Layout L;
+    std::vector<uint32_t> first(n);
+    for (int k = 0; k < n; k++) {
+        int eo = effective_order(in_size[k], order[k]);
+        first[k] = (uint32_t)njobs;
+        if (eo & X_STRIPE) {
+            StripePlan sp;
+            stripe_plan_encode(sp, k, in_size[k], order[k], caps ? caps[k] : compress_bound(in_size[k], order[k]));
+            sp.first_job = (uint32_t)njobs;
+            njobs += 1 + sp.nsub;             // parent (assembly record) + sub-streams
+            stripes.push_back(sp);
+        } else njobs++;
+    }
+    std::vector<EncJob> jobs(njobs);
+    size_t o_jobs = L.take(njobs * sizeof(EncJob));
+    size_t o_ctr = L.take(256);
+    bool any_o1 = false;
+    size_t pool_bytes = 0;
+    // ---- pass 2: place slots / work buffers
+    auto place = [&](EncJob &J, const uint8_t *in, uint32_t isz, int ord, uint32_t cap, uint32_t item) {
+        memset(&J, 0, sizeof(J));
+        J.in = in; J.in_size = isz; J.order = ord; J.cap = cap; J.item = item;
+        uint32_t slot_cap = (uint32_t)al(compress_bound(isz, ord) + 16, 16);
+        J.slot_cap = slot_cap;
+        J.slot = (uint8_t *)L.take(slot_cap, 256);
+        if (ord & (X_PACK | X_RLE)) J.work = (uint8_t *)L.take((size_t)isz * 4 + isz / 4 + 8192, 256);
+        if ((ord & 1) && isz >= 8) {
+            any_o1 = true;
+            // symbol table (16 B/pair), pair counts (4 B/pair), coded table scratch
+            pool_bytes += 256 * 256 * 20 + 300 * 1024;
+        }
+    };
+    size_t si = 0;
+    for (int k = 0; k < n; k++) {
+        uint32_t j = first[k];
+        uint32_t cap = caps ? caps[k] : compress_bound(in_size[k], order[k]);
+        if (si < stripes.size() && stripes[si].item == k) {
+            StripePlan &sp = stripes[si++];
+            sp.o_transposed = L.take(in_size[k], 256);
+            place(jobs[j], d_in + in_off[k], in_size[k], order[k], cap, (uint32_t)k);
+            jobs[j].stripe_n = sp.N;
+            for (uint32_t s = 0; s < sp.nsub; s++) {
+                const StripeSub &ss = sp.sub[s];
+                // sub-streams get generous private slots; the capacity rule of the
+                // reference is re-applied at selection time (need_cap)
+                place(jobs[j + 1 + s], (const uint8_t *)(sp.o_transposed + ss.off), ss.len, ss.order,
+                      0x7ffffff0u, 0xffffffffu);
+            }
+        } else {
+            place(jobs[j], d_in + in_off[k], in_size[k], order[k], cap, (uint32_t)k);
+        }
+    }
+    // the reference's worst case is one table per stream; real tables are tiny.
+    pool_bytes = std::min<size_t>(pool_bytes, (size_t)2 << 30);
+    pool_bytes = std::max<size_t>(pool_bytes, (size_t)8 << 20);
+    size_t o_pool = L.take(pool_bytes, 256);
+    size_t o_soff = L.take(njobs * 8), o_ssz = L.take(njobs * 4);
+    int r = C.work.ensure(L.off + 256);
+    if (r) return r;
+    uint8_t *W = C.work.p;
+    // relocate offsets into pointers
+    for (auto &J : jobs) {
+        J.slot = W + (size_t)J.slot;
+        if (J.work) J.work = W + (size_t)J.work;
+    }
+    for (auto &sp : stripes)
+        for (uint32_t s = 0; s < sp.nsub; s++) {
+            EncJob &J = jobs[sp.first_job + 1 + s];
+            J.in = W + (size_t)J.in;
+        }
+    Stage *S;
+    size_t stage_bytes = njobs * sizeof(EncJob) + 256;
+    if ((r = C.get_stage(stage_bytes, &S))) return r;
+    memcpy(S->h.p, jobs.data(), njobs * sizeof(EncJob));
+    EncJob *d_jobs = (EncJob *)(W + o_jobs);
+    CK(cudaMemcpyAsync(d_jobs, S->h.p, njobs * sizeof(EncJob), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(W + o_ctr, 0, 256, st));
+    Pool pool{W + o_pool, pool_bytes, (unsigned long long *)(W + o_ctr)};
+
+    // ---- STRIPE: transpose parents into their sub-stream inputs
+    for (auto &sp : stripes) {
+        CK(launch_stripe_split(d_in + in_off[sp.item], W + sp.o_transposed, sp.in_size, sp.N, st));
+        C.launches++;
+    }
+    // ---- encode.  Streams that are purely order-0 go to the lean kernel.
+    CK(launch_enc(d_jobs, (uint32_t)njobs, any_o1, pool, st));
+    C.launches++;
+    CK(cudaEventRecord(S->ev, st)); S->busy = true;
+    // ---- STRIPE: choose the smallest method per sub-stream and assemble the parent
+    if (!stripes.empty()) {
+        for (auto &sp : stripes) {
+            CK(launch_stripe_select(d_jobs, sp.first_job, sp.N, sp.nmeth, st));
+            C.launches++;
+        }
+    }
+    // ---- pack the finished streams of the caller's items (sub-streams carry no item)
+    uint64_t *d_off = d_out_off ? d_out_off : (uint64_t *)(W + o_soff);
+    uint32_t *d_sz = d_out_size ? d_out_size : (uint32_t *)(W + o_ssz);
+    CK(launch_pack(d_jobs, (uint32_t)njobs, d_off, d_sz, d_total, d_out, out_cap, st));
+    C.launches += 2;
+    return 0;
+}
+
+// Decode core: inputs and outputs on the device.  d_status/d_osz are device arrays.
+int dec_core(Ctx &C, cudaStream_t st, int n, const uint8_t *d_in, const uint64_t *in_off,
+             const uint32_t *in_size, const uint8_t *flags /* first byte of each stream, or null */,
+             uint8_t *d_out, const uint64_t *out_off, const uint32_t *out_cap,
+             uint32_t *d_osz, int *d_status) {
+    if (n <= 0) return 0;
+    Layout L;
+    size_t o_jobs = L.take((size_t)n * sizeof(DecJob));
+    size_t o_ctr = L.take(256);
+    std::vector<DecJob> jobs(n);
+    bool any_o1 = false;
+    size_t pool_bytes = 0;
+    for (int k = 0; k < n; k++) {
+        DecJob &J = jobs[k];
+        memset(&J, 0, sizeof(J));
+        J.in = d_in + in_off[k]; J.in_size = in_size[k];
+        J.out = d_out + out_off[k]; J.out_cap = out_cap[k];
+        int f = flags ? flags[k] : 0xff;                 // unknown: assume everything
+        if (f & (X_PACK | X_RLE)) J.tmp = (uint8_t *)L.take((size_t)out_cap[k] * 2 + 4096, 256);
+        if (f & 1) { any_o1 = true; pool_bytes += 257 * 257 * 3 + 256 * 256 * 4 + 64 * 1024; }
+    }
+    pool_bytes = std::min<size_t>(pool_bytes, (size_t)2 << 30);
+    pool_bytes = std::max<size_t>(pool_bytes, (size_t)8 << 20);
+    size_t o_pool = L.take(pool_bytes, 256);
+    size_t o_res = L.take((size_t)n * 8);
+    int r = C.work.ensure(L.off + 256);
+    if (r) return r;
+    uint8_t *W = C.work.p;
+    for (auto &J : jobs) if (J.tmp) J.tmp = W + (size_t)J.tmp;
+    Stage *S;
+    if ((r = C.get_stage((size_t)n * sizeof(DecJob), &S))) return r;
+    memcpy(S->h.p, jobs.data(), (size_t)n * sizeof(DecJob));
+    DecJob *d_jobs = (DecJob *)(W + o_jobs);
+    CK(cudaMemcpyAsync(d_jobs, S->h.p, (size_t)n * sizeof(DecJob), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(W + o_ctr, 0, 256, st));
+    Pool pool{W + o_pool, pool_bytes, (unsigned long long *)(W + o_ctr)};
+    CK(launch_dec(d_jobs, (uint32_t)n, any_o1, pool, st));
+    C.launches++;
+    CK(cudaEventRecord(S->ev, st)); S->busy = true;
+    CK(launch_dec_results(d_jobs, (uint32_t)n, d_osz, d_status, st));
+    C.launches++;
+    (void)o_res;
+    return 0;
+}
+
+// copy a list of host ranges to/from consecutive device offsets, merging
+// neighbours that are contiguous on both sides into one cudaMemcpyAsync
+struct Span { const uint8_t *h; size_t d; size_t len; };
+int copy_spans(std::vector<Span> &sp, uint8_t *dbase, bool to_device, cudaStream_t st) {
+    size_t i = 0;
+    while (i < sp.size()) {
+        size_t j = i + 1, len = sp[i].len;
+        while (j < sp.size() && sp[j].h == sp[i].h + len && sp[j].d == sp[i].d + len) { len += sp[j].len; j++; }
+        if (len) {
+            if (to_device) CK(cudaMemcpyAsync(dbase + sp[i].d, sp[i].h, len, cudaMemcpyHostToDevice, st));
+            else CK(cudaMemcpyAsync((void *)sp[i].h, dbase + sp[i].d, len, cudaMemcpyDeviceToHost, st));
+        }
+        i = j;
+    }
+    return 0;
+}
+
+// device placement of host buffers: keep host contiguity where it exists so that
+// copies merge; otherwise align each stream to 16 bytes
+void place_spans(int n, const unsigned char *const *ptr, const uint32_t *len, std::vector<uint64_t> &off,
+                 size_t *total) {
+    size_t o = 0;
+    off.resize(n);
+    for (int k = 0; k < n; k++) {
+        if (k && ptr[k] == ptr[k - 1] + len[k - 1]) o = off[k - 1] + len[k - 1];
+        else o = al(o, 256) + ((uintptr_t)ptr[k] & 15);   // same alignment mod 16 as on the host
+        off[k] = o;
+        o += len[k];
+    }
+    *total = o + 256;
+}
+
+int compress_batch_impl(int n, const unsigned char *const *in, const unsigned int *in_size, const int *order,
+                        const uint32_t *caps, unsigned char *out, size_t out_cap, size_t *out_off,
+                        unsigned int *out_size) {
+    int err = 0;
+    Ctx *C = get_ctx(&err);
+    if (!C) return err;
+    if (n <= 0) return 0;
+    cudaStream_t st = C->st;
+    std::vector<uint64_t> ioff;
+    size_t in_total;
+    place_spans(n, in, in_size, ioff, &in_total);
+    size_t bound_total = 0;
+    for (int k = 0; k < n; k++) bound_total += al(compress_bound(in_size[k], order[k]), 16) + 16;
+    Layout L;
+    size_t o_in = L.take(in_total), o_out = L.take(bound_total);
+    size_t o_off = L.take((size_t)n * 8), o_sz = L.take((size_t)n * 4), o_tot = L.take(8);
+    int r = C->io.ensure(L.off + 256);
+    if (r) return r;
+    uint8_t *D = C->io.p;
+    std::vector<Span> sp(n);
+    for (int k = 0; k < n; k++) sp[k] = Span{in[k], o_in + ioff[k], in_size[k]};
+    if ((r = copy_spans(sp, D, true, st))) return r;
+    r = enc_core(*C, st, n, D + o_in, ioff.data(), in_size, order, caps, D + o_out, bound_total,
+                 (uint64_t *)(D + o_off), (uint32_t *)(D + o_sz), (uint64_t *)(D + o_tot));
+    if (r) return r;
+    // read back sizes, then exactly the bytes produced
+    size_t res_bytes = (size_t)n * 12 + 8;
+    if ((r = C->hio.ensure(res_bytes))) return r;
+    uint64_t *h_off = (uint64_t *)C->hio.p;
+    uint32_t *h_sz = (uint32_t *)(C->hio.p + (size_t)n * 8);
+    uint64_t *h_tot = (uint64_t *)(C->hio.p + (size_t)n * 12 + (8 - ((size_t)n * 12) % 8) % 8);
+    CK(cudaMemcpyAsync(h_off, D + o_off, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_sz, D + o_sz, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_tot, D + o_tot, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    uint64_t total = *h_tot;
+    if (total > out_cap) return B200RANS_ESPACE;
+    if (total) CK(cudaMemcpyAsync(out, D + o_out, total, cudaMemcpyDeviceToHost, st));
+    for (int k = 0; k < n; k++) { out_off[k] = (size_t)h_off[k]; out_size[k] = h_sz[k]; }
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// host-side peek at a stream header: flag, stored length
+bool peek_header(const unsigned char *in, unsigned int in_size, int *flag, uint32_t *ulen, int *hdr) {
+    if (in_size == 0) return false;
+    *flag = in[0];
+    *hdr = 1;
+    *ulen = 0;
+    if (in[0] & X_NOSZ) return true;
+    uint32_t v = 0;
+    unsigned i = 1, cnt = 0;
+    uint8_t c = 0x80;
+    while ((c & 0x80) && i < in_size && cnt < 6) { c = in[i++]; v = (v << 7) | (c & 0x7f); cnt++; }
+    *ulen = v;
+    *hdr = (int)i;
+    return true;
+}
+
+int uncompress_batch_impl(int n, const unsigned char *const *in, const unsigned int *in_size,
+                          unsigned char *const *out, unsigned int *out_size, int *status) {
+    int err = 0;
+    Ctx *C = get_ctx(&err);
+    if (!C) return err;
+    if (n <= 0) return 0;
+    cudaStream_t st = C->st;
+    // ---- expand STRIPE streams into their sub-streams (host reads only headers)
+    std::vector<DecItem> items(n);
+    std::vector<const unsigned char *> jin;
+    std::vector<uint32_t> jin_size, jcap;
+    std::vector<uint8_t> jflag;
+    std::vector<uint64_t> jout;         // device offset of each job's output
+    std::vector<uint32_t> ocap(n);
+    std::vector<uint64_t> ooff(n);
+    size_t o = 0, scratch = 0;
+    for (int k = 0; k < n; k++) {
+        DecItem &it = items[k];
+        it = DecItem();
+        int flag = 0, hdr = 0;
+        uint32_t ulen = 0;
+        it.first_job = (uint32_t)jin.size();
+        if (!in[k] || !out[k] || !peek_header(in[k], in_size[k], &flag, &ulen, &hdr)) { it.fail = true; continue; }
+        if (flag & X_NOSZ) ulen = out_size[k];
+        o = al(o, 256) + ((uintptr_t)out[k] & 15);
+        if (k && !items[k - 1].fail && out[k] == out[k - 1] + ocap[k - 1] && !(flag & X_STRIPE))
+            o = ooff[k - 1] + ocap[k - 1];
+        ooff[k] = o;
+        if (flag & X_STRIPE) {
+            if (!stripe_plan_decode(it, in[k], in_size[k], out_size[k])) { it.fail = true; continue; }
+            ocap[k] = it.ulen;
+            o += it.ulen;
+            it.o_tmp = scratch; scratch = al(scratch + it.ulen, 256);
+            for (uint32_t s = 0; s < it.N; s++) {
+                jin.push_back(in[k] + it.sub_off[s]);
+                jin_size.push_back(it.sub_clen[s]);
+                jcap.push_back(it.sub_ulen[s]);
+                jflag.push_back(in[k][it.sub_off[s]]);
+                jout.push_back(~0ull);          // placed in scratch below
+            }
+        } else {
+            if (out_size[k] < ulen) { it.fail = true; continue; }
+            ocap[k] = (flag & X_NOSZ) ? out_size[k] : ulen;
+            it.ulen = ocap[k];
+            o += ocap[k];
+            jin.push_back(in[k]); jin_size.push_back(in_size[k]); jcap.push_back(ocap[k]);
+            jflag.push_back((uint8_t)flag); jout.push_back(ooff[k]);
+        }
+        it.njobs = (uint32_t)jin.size() - it.first_job;
+    }
+    size_t out_total = o + 256;
+    int nj = (int)jin.size();
+    std::vector<uint64_t> cioff;
+    size_t in_total = 0;
+    if (nj) place_spans(nj, jin.data(), jin_size.data(), cioff, &in_total);
+    Layout L;
+    size_t o_in = L.take(in_total + 256), o_out = L.take(out_total), o_scr = L.take(scratch + 256);
+    size_t o_osz = L.take((size_t)nj * 4 + 4), o_st = L.take((size_t)nj * 4 + 4);
+    int r = C->io.ensure(L.off + 256);
+    if (r) return r;
+    uint8_t *D = C->io.p;
+    // stripe sub-jobs decode into the scratch area (relative to d_out base = D + o_out)
+    for (int k = 0; k < n; k++) {
+        DecItem &it = items[k];
+        if (it.fail || !it.stripe) continue;
+        for (uint32_t s = 0; s < it.N; s++)
+            jout[it.first_job + s] = (o_scr + it.o_tmp + it.sub_idx[s]) - o_out;
+    }
+    if (nj) {
+        std::vector<Span> sp(nj);
+        for (int j = 0; j < nj; j++) sp[j] = Span{jin[j], o_in + cioff[j], jin_size[j]};
+        if ((r = copy_spans(sp, D, true, st))) return r;
+        r = dec_core(*C, st, nj, D + o_in, cioff.data(), jin_size.data(), jflag.data(), D + o_out,
+                     jout.data(), jcap.data(), (uint32_t *)(D + o_osz), (int *)(D + o_st));
+        if (r) return r;
+        for (int k = 0; k < n; k++) {
+            DecItem &it = items[k];
+            if (it.fail || !it.stripe) continue;
+            CK(launch_stripe_join(D + o_scr + it.o_tmp, D + o_out + ooff[k], it.ulen, it.N, st));
+            C->launches++;
+        }
+    }
+    if ((r = C->hio.ensure((size_t)nj * 8 + 16))) return r;
+    uint32_t *h_osz = (uint32_t *)C->hio.p;
+    int *h_st = (int *)(C->hio.p + (size_t)nj * 4 + 8);
+    if (nj) {
+        CK(cudaMemcpyAsync(h_osz, D + o_osz, (size_t)nj * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_st, D + o_st, (size_t)nj * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    // ---- verdict per item, then copy the good ones out
+    std::vector<Span> sp;
+    for (int k = 0; k < n; k++) {
+        DecItem &it = items[k];
+        int s = it.fail ? ST_FAIL : ST_OK;
+        uint32_t got = 0;
+        if (!it.fail) {
+            for (uint32_t j = 0; j < it.njobs; j++) {
+                uint32_t q = it.first_job + j;
+                if (h_st[q] != ST_OK) s = h_st[q];
+                else if (it.stripe && h_osz[q] != it.sub_ulen[j]) s = ST_FAIL;
+                else if (!it.stripe) got = h_osz[q];
+            }
+            if (it.stripe) got = it.ulen;
+        }
+        if (status) status[k] = s;
+        if (s == ST_OK) { out_size[k] = got; sp.push_back(Span{out[k], o_out + ooff[k], got}); }
+        else out_size[k] = 0;
+    }
+    if ((r = copy_spans(sp, D, false, st))) return r;
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // namespace
+
+// ============================================================ C ABI: part 1
+API unsigned int rans_compress_bound_4x16(unsigned int size, int order) {
+    return compress_bound(size, order);
+}
+
+API void rans_set_cpu(int) {}
+
+API unsigned char *rans_compress_to_4x16(unsigned char *in, unsigned int in_size, unsigned char *out,
+                                         unsigned int *out_size, int order) {
+    if (in_size > INT_MAX || (out && *out_size == 0)) { *out_size = 0; return NULL; }
+    unsigned char *out_free = NULL;
+    uint32_t cap;
+    if (!out) {
+        cap = compress_bound(in_size, order);
+        if (!(out_free = out = (unsigned char *)malloc(cap))) { *out_size = 0; return NULL; }
+    } else cap = *out_size;
+    const unsigned char *ins[1] = {in ? in : (const unsigned char *)""};
+    unsigned int isz[1] = {in_size}, osz[1] = {0};
+    int ord[1] = {order};
+    size_t ooff[1] = {0};
+    // stage through a bound-sized arena, then hand back exactly the stream
+    std::vector<unsigned char> arena;
+    size_t acap = (size_t)std::max(cap, compress_bound(in_size, order)) + 64;
+    unsigned char *tmp = out;
+    bool direct = acap <= cap;
+    if (!direct) { arena.resize(acap); tmp = arena.data(); }
+    int r = compress_batch_impl(1, ins, isz, ord, &cap, tmp, direct ? cap : acap, ooff, osz);
+    if (r || osz[0] == 0 || osz[0] > cap) { free(out_free); *out_size = 0; return NULL; }
+    if (tmp != out || ooff[0]) memmove(out, tmp + ooff[0], osz[0]);
+    *out_size = osz[0];
+    return out;
+}
+
+API unsigned char *rans_compress_4x16(unsigned char *in, unsigned int in_size, unsigned int *out_size,
+                                      int order) {
+    return rans_compress_to_4x16(in, in_size, NULL, out_size, order);
+}
+
+API unsigned char *rans_uncompress_to_4x16(unsigned char *in, unsigned int in_size, unsigned char *out,
+                                           unsigned int *out_size) {
+    int flag, hdr;
+    uint32_t ulen;
+    if (!in || !peek_header(in, in_size, &flag, &ulen, &hdr)) return NULL;
+    unsigned char *out_free = NULL;
+    if (flag & X_NOSZ) {
+        if (!out) return NULL;
+        ulen = *out_size;
+    }
+    if (!out) {
+        if (ulen >= INT_MAX) return NULL;
+        if (!(out_free = out = (unsigned char *)malloc(ulen ? ulen : 1))) return NULL;
+        *out_size = ulen;
+    } else if (*out_size < ulen) return NULL;
+    const unsigned char *ins[1] = {in};
+    unsigned char *outs[1] = {out};
+    unsigned int isz[1] = {in_size}, osz[1] = {(flag & X_STRIPE) ? *out_size : ((flag & X_NOSZ) ? *out_size : ulen)};
+    int st[1] = {0};
+    int r = uncompress_batch_impl(1, ins, isz, outs, osz, st);
+    if (r || st[0] != ST_OK) { free(out_free); return NULL; }
+    *out_size = osz[0];
+    return out;
+}
+
+API unsigned char *rans_uncompress_4x16(unsigned char *in, unsigned int in_size, unsigned int *out_size) {
+    return rans_uncompress_to_4x16(in, in_size, NULL, out_size);
+}
+
+// ============================================================ C ABI: part 2
+API int b200rans_set_device(int device) { tls_device = device; int e = 0; return get_ctx(&e) ? 0 : e; }
+
+API int b200rans_device_count(void) {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
+API void *b200rans_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        fprintf(stderr, "libb200rans: cudaHostAlloc(%zu) failed\n", bytes);
+        return nullptr;
+    }
+    return p;
+}
+API void b200rans_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+API int b200rans_compress_batch(int n, const unsigned char *const *in, const unsigned int *in_size,
+                                const int *order, unsigned char *out, size_t out_cap, size_t *out_off,
+                                unsigned int *out_size) {
+    if (n < 0 || (n && (!in || !in_size || !order || !out || !out_off || !out_size))) return B200RANS_EINVAL;
+    return compress_batch_impl(n, in, in_size, order, nullptr, out, out_cap, out_off, out_size);
+}
+
+API int b200rans_uncompress_batch(int n, const unsigned char *const *in, const unsigned int *in_size,
+                                  unsigned char *const *out, unsigned int *out_size, int *status) {
+    if (n < 0 || (n && (!in || !in_size || !out || !out_size))) return B200RANS_EINVAL;
+    return uncompress_batch_impl(n, in, in_size, out, out_size, status);
+}
+
+API int64_t b200rans_uncompressed_size(const unsigned char *in, unsigned int in_size) {
+    int flag, hdr;
+    uint32_t ulen;
+    if (!in || !peek_header(in, in_size, &flag, &ulen, &hdr) || (flag & X_NOSZ)) return -1;
+    return ulen;
+}
+
+API size_t b200rans_compress_batch_dev_bound(int n, const unsigned int *in_size, const int *order) {
+    size_t t = 0;
+    for (int k = 0; k < n; k++) t += al(compress_bound(in_size[k], order[k]), 16) + 16;
+    return t + 256;
+}
+
+API int b200rans_compress_batch_dev(void *stream, int n, const unsigned char *d_in, const uint64_t *in_off,
+                                    const unsigned int *in_size, const int *order, unsigned char *d_out,
+                                    size_t out_cap, uint64_t *d_out_off, unsigned int *d_out_size) {
+    int err = 0;
+    Ctx *C = get_ctx(&err);
+    if (!C) return err;
+    if (n < 0 || (n && (!d_in || !in_off || !in_size || !order || !d_out))) return B200RANS_EINVAL;
+    cudaStream_t st = stream ? (cudaStream_t)stream : C->st;
+    Layout L;
+    size_t o_tot = L.take(8);
+    // the total lives at the head of the io arena for this call
+    int r = C->io.ensure(256);
+    if (r) return r;
+    return enc_core(*C, st, n, d_in, in_off, in_size, order, nullptr, d_out, out_cap, d_out_off, d_out_size,
+                    (uint64_t *)(C->io.p + o_tot));
+}
+
+API int b200rans_uncompress_batch_dev(void *stream, int n, const unsigned char *d_in, const uint64_t *in_off,
+                                      const unsigned int *in_size, unsigned char *d_out,
+                                      const uint64_t *out_off, const unsigned int *out_size,
+                                      unsigned int *d_out_size, int *d_status) {
+    int err = 0;
+    Ctx *C = get_ctx(&err);
+    if (!C) return err;
+    if (n < 0 || (n && (!d_in || !in_off || !in_size || !d_out || !out_off || !out_size || !d_out_size || !d_status)))
+        return B200RANS_EINVAL;
+    cudaStream_t st = stream ? (cudaStream_t)stream : C->st;
+    return dec_core(*C, st, n, d_in, in_off, in_size, nullptr, d_out, out_off, out_size, d_out_size, d_status);
+}
+
+API uint64_t b200rans_launch_count(void) { return tls_ctx ? tls_ctx->launches : 0; }
+API const char *b200rans_version(void) { return "b200rans 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------- multi-GPU
+// Independent blocks, dealt round-robin over devices; one worker thread (and
+// therefore one context and stream) per device; results gathered in call order.
+namespace {
+template <typename F> int run_on_devices(int ngpu, F &&fn) {
+    int have = b200rans_device_count();
+    if (have <= 0) { fprintf(stderr, "libb200rans: no CUDA device; there is no CPU path\n"); return B200RANS_ENODEV; }
+    if (ngpu <= 0 || ngpu > have) return B200RANS_EINVAL;
+    std::vector<int> rc(ngpu, 0);
+    std::vector<std::thread> th;
+    for (int g = 0; g < ngpu; g++)
+        th.emplace_back([&, g] { tls_device = g; rc[g] = fn(g); });
+    for (auto &t : th) t.join();
+    for (int g = 0; g < ngpu; g++) if (rc[g]) return rc[g];
+    return 0;
+}
+}  // namespace
+
+API int b200rans_compress_batch_multi(int ngpu, int n, const unsigned char *const *in,
+                                      const unsigned int *in_size, const int *order, const int *block_of,
+                                      unsigned char *out, size_t out_cap, size_t *out_off,
+                                      unsigned int *out_size) {
+    if (n < 0 || (n && (!in || !in_size || !order || !out || !out_off || !out_size))) return B200RANS_EINVAL;
+    if (ngpu == 1) return b200rans_compress_batch(n, in, in_size, order, out, out_cap, out_off, out_size);
+    // every device gets a private slice of the arena sized by its streams' bounds
+    std::vector<std::vector<int>> idx(ngpu > 0 ? ngpu : 1);
+    if (ngpu <= 0) return B200RANS_EINVAL;
+    for (int k = 0; k < n; k++) idx[(block_of ? block_of[k] : k) % ngpu].push_back(k);
+    std::vector<size_t> base(ngpu + 1, 0);
+    for (int g = 0; g < ngpu; g++) {
+        size_t t = 0;
+        for (int k : idx[g]) t += al(compress_bound(in_size[k], order[k]), 16) + 16;
+        base[g + 1] = base[g] + al(t + 256, 256);
+    }
+    if (base[ngpu] > out_cap) return B200RANS_ESPACE;
+    return run_on_devices(ngpu, [&](int g) {
+        int m = (int)idx[g].size();
+        if (!m) return 0;
+        std::vector<const unsigned char *> i2(m);
+        std::vector<unsigned int> s2(m), z2(m);
+        std::vector<int> o2(m);
+        std::vector<size_t> f2(m);
+        for (int j = 0; j < m; j++) { int k = idx[g][j]; i2[j] = in[k]; s2[j] = in_size[k]; o2[j] = order[k]; }
+        int r = compress_batch_impl(m, i2.data(), s2.data(), o2.data(), nullptr, out + base[g],
+                                    base[g + 1] - base[g], f2.data(), z2.data());
+        if (r) return r;
+        for (int j = 0; j < m; j++) { int k = idx[g][j]; out_off[k] = base[g] + f2[j]; out_size[k] = z2[j]; }
+        return 0;
+    });
+}
+
+API int b200rans_uncompress_batch_multi(int ngpu, int n, const unsigned char *const *in,
+                                        const unsigned int *in_size, const int *block_of,
+                                        unsigned char *const *out, unsigned int *out_size, int *status) {
+    if (n < 0 || (n && (!in || !in_size || !out || !out_size))) return B200RANS_EINVAL;
+    if (ngpu == 1) return b200rans_uncompress_batch(n, in, in_size, out, out_size, status);
+    if (ngpu <= 0) return B200RANS_EINVAL;
+    std::vector<std::vector<int>> idx(ngpu);
+    for (int k = 0; k < n; k++) idx[(block_of ? block_of[k] : k) % ngpu].push_back(k);
+    return run_on_devices(ngpu, [&](int g) {
+        int m = (int)idx[g].size();
+        if (!m) return 0;
+        std::vector<const unsigned char *> i2(m);
+        std::vector<unsigned char *> o2(m);
+        std::vector<unsigned int> s2(m), z2(m);
+        std::vector<int> st2(m);
+        for (int j = 0; j < m; j++) { int k = idx[g][j]; i2[j] = in[k]; s2[j] = in_size[k]; o2[j] = out[k]; z2[j] = out_size[k]; }
+        int r = uncompress_batch_impl(m, i2.data(), s2.data(), o2.data(), z2.data(), st2.data());
+        if (r) return r;
+        for (int j = 0; j < m; j++) { int k = idx[g][j]; out_size[k] = z2[j]; if (status) status[k] = st2[j]; }
+        return 0;
+    });
+}

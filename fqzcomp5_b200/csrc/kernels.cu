@@ -1,0 +1,427 @@
+// kernels.cu -- the __global__ entry points: container logic of
+// rans_compress_to_4x16 / rans_uncompress_to_4x16 (rANS_static4x16pr.c:1224-1894)
+// around the coders in rans_encode.cuh / rans_decode.cuh, plus the size scan and
+// the gather that packs finished streams back to back.
+#include "kernels.h"
+#include "rans_decode.cuh"
+#include "rans_encode.cuh"
+#include "transforms.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------
+// Encode one stream (everything except STRIPE, which the host expands into
+// NOSZ sub-streams).  Mirrors the decisions of rANS_static4x16pr.c:1256-1579.
+// Capacity checks of the reference are evaluated against J.cap; need_cap
+// records the smallest capacity for which this call succeeds.
+// ------------------------------------------------------------------------
+struct CapCheck {
+    uint32_t cap, need;
+    bool ok;
+    __device__ void require(uint64_t v) {
+        if (v > 0xfffffff0ull) v = 0xfffffff0ull;
+        if (v > need) need = (uint32_t)v;
+        if (v > cap) ok = false;
+    }
+};
+
+template <bool O1>
+__device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const Pool &pool, int lane) {
+    int order = J.order;
+    const uint8_t *in = J.in;
+    uint32_t in_size = J.in_size;
+    uint8_t *out = J.slot;
+    CapCheck cc{J.cap, 1, J.cap != 0};            // (out && *out_size == 0) -> NULL (:1227)
+    uint32_t status = ST_OK;
+    uint32_t head_len = 0, tail_len = 0;
+    const uint8_t *tail = nullptr;
+
+    if ((order & ORDER_SIMD_AUTO) && in_size >= 50000 && !(order & X_STRIPE)) order |= X_32;
+    if (in_size <= 20) order &= ~X_STRIPE;
+    if (in_size <= 1000) order &= ~X_32;
+
+    if (in_size > 0x7fffffffu || (order & X_STRIPE)) {
+        status = (order & X_STRIPE) ? ST_UNSUPPORTED : ST_FAIL;
+    } else if (order & X_CAT) {                                           // :1395-1409
+        uint32_t m = 1;
+        if (lane == 0) { out[0] = X_CAT; m += var_put_u32(out + 1, in_size); }
+        m = __shfl_sync(FULL, m, 0);
+        cc.require((uint64_t)m + in_size);
+        head_len = m; tail = in; tail_len = in_size;
+    } else {
+        const int do_pack = order & X_PACK, no_size = order & X_NOSZ;
+        int do_rle = order & X_RLE, do_simd = order & X_32;
+        uint32_t flag = order & 0xff;
+        uint32_t meta = 1, szq = 0;                 // szq: "*out_size -= sz" at :1453
+        if (!no_size) {
+            if (lane == 0) meta += var_put_u32(out + 1, in_size);
+            meta = __shfl_sync(FULL, meta, 0);
+        }
+        int o1 = order & 1;
+        uint8_t *work = J.work;
+
+        if ((do_pack || do_rle) && in_size && !work) status = ST_UNSUPPORTED;   // host sizes work for these
+        if (status != ST_OK) {
+        } else if (do_pack && in_size) {                                  // :1429-1459
+            cc.require((uint64_t)meta + 256);
+            uint32_t pmeta = 0, plen = 0;
+            bool packed = work && warp_pack(in, in_size, out + meta, &pmeta, work, &plen, smem, lane);
+            if (!packed) flag &= ~X_PACK;
+            else {
+                in = work; work += (plen + 15) & ~15u;
+                in_size = plen;
+                meta += pmeta;
+                uint32_t sz = 0;
+                if (lane == 0) sz = var_put_u32(out + meta, in_size);
+                sz = __shfl_sync(FULL, sz, 0);
+                meta += sz; szq = sz;
+                if (do_simd && in_size < 32) { do_simd = 0; flag &= ~X_32; }
+            }
+        } else if (do_pack) flag &= ~X_PACK;
+
+        if (status != ST_OK) {
+        } else if (do_rle && in_size) {                                   // :1464-1533
+            // work: [literals in_size][meta in_size+257+16]
+            uint8_t *lits = work, *rmeta = work + ((in_size + 15) & ~15u);
+            uint32_t rle_len = 0, rmeta_len = 0;
+            warp_rle_encode(in, in_size, lits, &rle_len, rmeta, &rmeta_len, smem, lane);
+            if ((double)((uint64_t)rle_len + rmeta_len) >= .99 * (double)in_size) {
+                flag &= ~X_RLE; do_rle = 0;
+            } else {
+                uint32_t sz = 0;
+                if (lane == 0) {
+                    sz = var_put_u32(out + meta, rmeta_len * 2);
+                    sz += var_put_u32(out + meta + sz, rle_len);
+                }
+                sz = __shfl_sync(FULL, sz, 0);
+                cc.require((uint64_t)meta + sz + 5 + szq);
+                if (do_simd && (rmeta_len < 32 || rle_len < 32)) { do_simd = 0; flag &= ~X_32; }
+                // the run-length bytes go through the order-0 coder (same lane count)
+                cc.require((uint64_t)compress_bound(rmeta_len, 0) - 20 + meta + sz + 5 + szq);
+                uint8_t *tmp = rmeta + ((rmeta_len + 15) & ~15u);        // scratch for the coded meta
+                uint32_t cb = (compress_bound(rmeta_len, 0) - 20) & ~1u, ctab = 0;
+                uint8_t *cptr = nullptr;
+                int e = do_simd ? enc_o0<32>(rmeta, rmeta_len, tmp, tmp + cb, &ctab, &cptr, *(EncO0Smem *)smem, lane)
+                                : enc_o0<4>(rmeta, rmeta_len, tmp, tmp + cb, &ctab, &cptr, *(EncO0Smem *)smem, lane);
+                if (e) status = ST_FAIL;
+                uint32_t pay = (uint32_t)(tmp + cb - cptr), c_rmeta = ctab + pay, sz2 = 0;
+                if (!e && c_rmeta < rmeta_len) {
+                    if (lane == 0) sz2 = var_put_u32(out + meta + sz, c_rmeta);
+                    sz2 = __shfl_sync(FULL, sz2, 0);
+                    __syncwarp();
+                    warp_copy(out + meta + sz + sz2, tmp, ctab, lane);
+                    warp_copy(out + meta + sz + sz2 + ctab, cptr, pay, lane);
+                } else if (!e) {                                          // raw: too small to pay off
+                    if (lane == 0) {
+                        sz = var_put_u32(out + meta, rmeta_len * 2 + 1);
+                        sz2 = var_put_u32(out + meta + sz, rle_len);
+                    }
+                    sz = __shfl_sync(FULL, sz, 0); sz2 = __shfl_sync(FULL, sz2, 0);
+                    __syncwarp();
+                    warp_copy(out + meta + sz + sz2, rmeta, rmeta_len, lane);
+                    c_rmeta = rmeta_len;
+                }
+                meta += sz + sz2 + c_rmeta;
+                in = lits; in_size = rle_len;
+            }
+        } else if (do_rle) flag &= ~X_RLE;
+
+        cc.require((uint64_t)meta + szq);                                 // :1538
+        if (o1 && in_size < 8) { flag &= ~1u; o1 = 0; }                   // :1547
+        cc.require((uint64_t)compress_bound(in_size, o1) - 20 + meta + szq);   // bound > *out_size in the coder
+
+        uint32_t tab = 0;
+        uint8_t *ptr = nullptr, *oend = out + (J.slot_cap & ~1u);
+        int e = 0;
+        if (status == ST_OK) {
+            __syncwarp();
+            if (O1 && o1) {
+                EncO1Smem &S = *(EncO1Smem *)smem;
+                uint8_t *dyn = smem + sizeof(EncO1Smem);
+                uint32_t hw = (smem_bytes - (uint32_t)sizeof(EncO1Smem)) / 4;
+                EncO0Smem *o0s = (EncO0Smem *)dyn;      // pair counts are dead by the time the table is coded
+                e = do_simd ? enc_o1<32>(in, in_size, out + meta, oend, &tab, &ptr, S, (uint32_t *)dyn, hw, o0s, pool, lane)
+                            : enc_o1<4>(in, in_size, out + meta, oend, &tab, &ptr, S, (uint32_t *)dyn, hw, o0s, pool, lane);
+            } else if (o1) {
+                e = 3;      // order-1 stream routed to the order-0-only kernel: host bug
+            } else {
+                EncO0Smem &S = *(EncO0Smem *)smem;
+                e = do_simd ? enc_o0<32>(in, in_size, out + meta, oend, &tab, &ptr, S, lane)
+                            : enc_o0<4>(in, in_size, out + meta, oend, &tab, &ptr, S, lane);
+            }
+            if (e) status = (e == 2 || e == 3) ? ST_UNSUPPORTED : ST_FAIL;
+        }
+        if (status == ST_OK) {
+            uint32_t pay = (uint32_t)(oend - ptr);
+            if (tab + pay >= in_size) {                                   // :1560-1574 store raw instead
+                flag &= ~3u;
+                flag |= X_CAT | no_size;
+                cc.require((uint64_t)meta + in_size);
+                head_len = meta; tail = in; tail_len = in_size;
+            } else {
+                head_len = meta + tab; tail = ptr; tail_len = pay;
+            }
+            if (lane == 0) out[0] = (uint8_t)flag;
+        }
+    }
+    if (!cc.ok && status == ST_OK) status = ST_FAIL;
+    if (lane == 0) {
+        J.tail = tail; J.head_len = head_len; J.tail_len = tail_len;
+        J.status = status; J.need_cap = cc.need;
+    }
+    __syncwarp();
+}
+
+template <bool O1>
+__global__ void __launch_bounds__(ENC_WARPS * 32)
+enc_kernel(EncJob *jobs, uint32_t njobs, uint32_t warp_smem, Pool pool) {
+    extern __shared__ __align__(16) uint8_t smem_all[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t j = blockIdx.x * ENC_WARPS + wid;
+    if (j >= njobs || jobs[j].stripe_n) return;      // STRIPE parents are assembled by stripe_select
+    enc_stream<O1>(jobs[j], smem_all + (size_t)wid * warp_smem, warp_smem, pool, lane);
+}
+
+// ------------------------------------------------------------------------
+// Decode one stream (everything except STRIPE: the host splits those into
+// their NOSZ sub-streams and un-stripes afterwards).  rANS_static4x16pr.c:1696-1887.
+// ------------------------------------------------------------------------
+template <bool O1>
+__device__ void dec_stream(DecJob &J, uint8_t *smem, uint32_t smem_bytes, const Pool &pool, int lane) {
+    const uint8_t *in = J.in, *in_end = J.in + J.in_size;
+    uint32_t in_size = J.in_size;
+    int status = ST_OK;
+    uint32_t out_size = 0;
+    do {
+        if (in_size == 0) { status = ST_FAIL; break; }
+        const int flag = *in++; in_size--;
+        if (flag & X_STRIPE) { status = ST_UNSUPPORTED; break; }
+        const int do_pack = flag & X_PACK, do_rle = flag & X_RLE, do_cat = flag & X_CAT,
+                  no_size = flag & X_NOSZ, do_simd = flag & X_32, o1 = flag & 1;
+        uint32_t osz = J.out_cap;
+        if (!no_size) { int sz = var_get_u32(in, in_end, &osz); in += sz; in_size -= sz; }
+        if (J.out_cap < osz) { status = ST_FAIL; break; }
+        out_size = osz;
+        uint8_t *out = J.out, *tmp = J.tmp;
+        if ((do_pack || do_rle) && !tmp) { status = ST_UNSUPPORTED; break; }
+        uint8_t *t1, *t2, *t3;                                          // :1760-1782
+        if (do_pack && do_rle) { t1 = out; t2 = tmp; t3 = out; }
+        else if (do_pack)      { t1 = tmp; t2 = tmp; t3 = out; }
+        else if (do_rle)       { t1 = tmp; t2 = out; t3 = out; }
+        else                   { t1 = t2 = t3 = out; }
+        uint32_t t1_size = out_size;
+
+        PackMap pm;                                                      // :1788-1806
+        uint32_t unpacked_sz = 0;
+        if (do_pack) {
+            int c = unpack_meta(in, in_size, pm);
+            if (!c) { status = ST_FAIL; break; }
+            unpacked_sz = osz;
+            in += c; in_size -= c;
+            uint32_t psz;
+            int sz = var_get_u32(in, in_end, &psz);
+            in += sz; in_size -= sz;
+            if (psz > t1_size) { status = ST_FAIL; break; }
+            t1_size = psz;
+        }
+        const uint8_t *meta = nullptr;
+        uint32_t u_meta = 0;
+        if (do_rle) {                                                    // :1810-1834
+            uint32_t c_meta, rle_len;
+            uint32_t sz = var_get_u32(in, in_end, &u_meta);
+            sz += var_get_u32(in + sz, in_end, &rle_len);
+            if (rle_len > t1_size) { status = ST_FAIL; break; }
+            if (u_meta & 1) {
+                meta = in + sz;
+                uint32_t left = (uint32_t)(in_end - meta);
+                u_meta = u_meta / 2 > left ? left : u_meta / 2;
+                c_meta = u_meta;
+            } else {
+                sz += var_get_u32(in + sz, in_end, &c_meta);
+                u_meta /= 2;
+                // run lengths never outgrow the data they describe
+                if (u_meta > J.out_cap + 1024 || in_size < sz) { status = ST_FAIL; break; }
+                uint8_t *mbuf = tmp + ((J.out_cap + 15) & ~15u);
+                int e = do_simd ? dec_o0<32>(in + sz, in_size - sz, mbuf, u_meta, *(DecO0Smem *)smem, lane)
+                                : dec_o0<4>(in + sz, in_size - sz, mbuf, u_meta, *(DecO0Smem *)smem, lane);
+                if (e) { status = ST_FAIL; break; }
+                __syncwarp();
+                meta = mbuf;
+            }
+            if ((uint64_t)c_meta + sz > in_size) { status = ST_FAIL; break; }
+            in += c_meta + sz; in_size -= c_meta + sz;
+            t1_size = rle_len;
+        }
+        if (in_size) {                                                   // :1838-1853
+            if (do_cat) {
+                if (t1_size > in_size || t1_size > out_size) { status = ST_FAIL; break; }
+                warp_copy(t1, in, t1_size, lane);
+            } else {
+                int e;
+                if (O1 && o1) {
+                    DecO1Smem &S = *(DecO1Smem *)smem;
+                    uint8_t *dyn = smem + sizeof(DecO1Smem);
+                    uint32_t tb = smem_bytes - (uint32_t)sizeof(DecO1Smem);
+                    e = do_simd ? dec_o1<32>(in, in_size, t1, t1_size, S, dyn, tb, (DecO0Smem *)smem, pool, lane)
+                                : dec_o1<4>(in, in_size, t1, t1_size, S, dyn, tb, (DecO0Smem *)smem, pool, lane);
+                } else if (o1) {
+                    e = 2;
+                } else {
+                    DecO0Smem &S = *(DecO0Smem *)smem;
+                    e = do_simd ? dec_o0<32>(in, in_size, t1, t1_size, S, lane)
+                                : dec_o0<4>(in, in_size, t1, t1_size, S, lane);
+                }
+                if (e) { status = e == 2 ? ST_UNSUPPORTED : ST_FAIL; break; }
+            }
+        } else t1_size = 0;
+        __syncwarp();
+        uint32_t t2_size = t1_size, t3_size = t1_size;
+        if (do_rle) {                                                    // :1856-1871
+            if (u_meta == 0) { status = ST_FAIL; break; }
+            uint32_t nsyms = *meta ? *meta : 256;
+            if (u_meta < 1 + nsyms) { status = ST_FAIL; break; }
+            uint32_t unrle = out_size;
+            if (!warp_rle_decode(t1, t1_size, meta + 1 + nsyms, u_meta - (1 + nsyms), meta + 1, nsyms,
+                                 t2, &unrle, smem, lane)) { status = ST_FAIL; break; }
+            t3_size = t2_size = unrle;
+        }
+        if (do_pack) {                                                   // :1872-1881
+            if (pm.per == 1) unpacked_sz = t2_size;
+            if (!warp_unpack(t2, t2_size, t3, unpacked_sz, pm, smem, lane)) { status = ST_FAIL; break; }
+            t3_size = unpacked_sz;
+        }
+        out_size = t3_size;
+    } while (0);
+    __syncwarp();
+    if (lane == 0) { J.status = status; J.out_size = status == ST_OK ? out_size : 0; }
+}
+
+template <bool O1>
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+dec_kernel(DecJob *jobs, uint32_t njobs, uint32_t warp_smem, Pool pool) {
+    extern __shared__ __align__(16) uint8_t smem_all[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t j = blockIdx.x * DEC_WARPS + wid;
+    if (j >= njobs) return;
+    dec_stream<O1>(jobs[j], smem_all + (size_t)wid * warp_smem, warp_smem, pool, lane);
+}
+
+// ------------------------------------------------------------------------
+// Packing: exclusive scan of the finished stream sizes (one CTA), then one CTA
+// per stream copies head and tail to their final place.
+// ------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+scan_kernel(const EncJob *jobs, uint32_t njobs, uint64_t *out_off, uint32_t *out_size, uint64_t *total) {
+    __shared__ uint64_t wsum[32];
+    __shared__ uint64_t carry;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < njobs; base += 1024) {
+        uint32_t k = base + threadIdx.x;
+        uint32_t sz = 0;
+        const bool item = k < njobs && jobs[k].item != 0xffffffffu;
+        if (item && jobs[k].status == ST_OK) sz = jobs[k].head_len + jobs[k].tail_len;
+        uint64_t v = (sz + 15u) & ~15ull;                  // streams start 16-byte aligned
+        uint64_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint64_t t = __shfl_up_sync(FULL, x, o);
+            if (lane >= o) x += t;
+        }
+        if (lane == 31) wsum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint64_t y = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint64_t t = __shfl_up_sync(FULL, y, o);
+                if (lane >= o) y += t;
+            }
+            wsum[lane] = y;
+        }
+        __syncthreads();
+        uint64_t excl = carry + (wid ? wsum[wid - 1] : 0) + x - v;
+        if (item) { out_off[jobs[k].item] = excl; out_size[jobs[k].item] = sz; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(256)
+gather_kernel(const EncJob *jobs, uint32_t njobs, const uint64_t *out_off, uint32_t *out_size,
+              uint8_t *out, uint64_t out_cap) {
+    const uint32_t k = blockIdx.x;
+    if (k >= njobs) return;
+    const EncJob &J = jobs[k];
+    if (J.status != ST_OK || J.item == 0xffffffffu) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint64_t off = out_off[J.item];
+    const uint32_t hl = J.head_len, tl = J.tail_len;
+    if (off + hl + tl > out_cap) { if (threadIdx.x == 0) out_size[J.item] = 0; return; }
+    uint8_t *dst = out + off;
+    if (wid == 0) warp_copy(dst, J.slot, hl, lane);
+    if (J.stripe_n) {
+        // STRIPE parent: the tail is the chosen sub-streams, back to back
+        const uint32_t *list = (const uint32_t *)(J.slot + STRIPE_LIST_OFF);
+        uint64_t o = hl;
+        for (uint32_t i = 0; i < J.stripe_n; i++) {
+            const EncJob &S = jobs[list[i]];
+            if (wid == (int)(i % nw)) {
+                warp_copy(dst + o, S.slot, S.head_len, lane);
+                warp_copy(dst + o + S.head_len, S.tail, S.tail_len, lane);
+            }
+            o += S.head_len + S.tail_len;
+        }
+        return;
+    }
+    // tail in 16 KiB pieces spread over the warps; piece boundaries keep dst+hl alignment mod 16
+    const uint32_t P = 16384;
+    for (uint32_t p = wid * P; p < tl; p += nw * P) {
+        uint32_t len = tl - p < P ? tl - p : P;
+        warp_copy(dst + hl + p, J.tail + p, len, lane);
+    }
+}
+
+// ------------------------------------------------------------------------ launchers
+static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    uint32_t ws = o1 ? ENC_SMEM_O1 : ENC_SMEM_O0;
+    size_t sm = (size_t)ws * ENC_WARPS;
+    if (o1) {
+        cudaFuncSetAttribute(enc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        enc_kernel<true><<<cdiv(n, ENC_WARPS), ENC_WARPS * 32, sm, st>>>(d_jobs, n, ws, pool);
+    } else {
+        cudaFuncSetAttribute(enc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        enc_kernel<false><<<cdiv(n, ENC_WARPS), ENC_WARPS * 32, sm, st>>>(d_jobs, n, ws, pool);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dec(DecJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    uint32_t ws = o1 ? DEC_SMEM_O1 : DEC_SMEM_O0;
+    size_t sm = (size_t)ws * DEC_WARPS;
+    if (o1) {
+        cudaFuncSetAttribute(dec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        dec_kernel<true><<<cdiv(n, DEC_WARPS), DEC_WARPS * 32, sm, st>>>(d_jobs, n, ws, pool);
+    } else {
+        cudaFuncSetAttribute(dec_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        dec_kernel<false><<<cdiv(n, DEC_WARPS), DEC_WARPS * 32, sm, st>>>(d_jobs, n, ws, pool);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack(const EncJob *d_jobs, uint32_t n, uint64_t *d_off, uint32_t *d_size,
+                        uint64_t *d_total, uint8_t *d_out, uint64_t out_cap, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    scan_kernel<<<1, 1024, 0, st>>>(d_jobs, n, d_off, d_size, d_total);
+    gather_kernel<<<n, 256, 0, st>>>(d_jobs, n, d_off, d_size, d_out, out_cap);
+    return cudaGetLastError();
+}
+
+}  // namespace b200

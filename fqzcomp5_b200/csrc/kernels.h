@@ -1,0 +1,22 @@
+// kernels.h -- host-visible launchers for the kernels in kernels.cu.
+#pragma once
+#include "common.cuh"
+#include "rans_decode.cuh"
+
+namespace b200 {
+
+// one warp per stream, several streams per CTA
+constexpr int ENC_WARPS = 4;
+constexpr int DEC_WARPS = 4;
+// shared memory per warp (bytes)
+constexpr uint32_t ENC_SMEM_O0 = 5120;     // EncO0Smem
+constexpr uint32_t ENC_SMEM_O1 = 12288;    // EncO1Smem header + pair counts for <= 48 symbols
+constexpr uint32_t DEC_SMEM_O0 = 6144;     // DecO0Smem
+constexpr uint32_t DEC_SMEM_O1 = 14336;    // DecO1Smem header + tables for <= ~48 symbols
+
+cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStream_t st);
+cudaError_t launch_dec(DecJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStream_t st);
+cudaError_t launch_pack(const EncJob *d_jobs, uint32_t n, uint64_t *d_off, uint32_t *d_size,
+                        uint64_t *d_total, uint8_t *d_out, uint64_t out_cap, cudaStream_t st);
+
+}  // namespace b200

@@ -1,0 +1,442 @@
+// rans_decode.cuh -- device side of rans_uncompress_to_4x16: order-0 and order-1
+// rANS decode with N = 4 or 32 interleaved states.  One warp per stream.
+//
+// Reference behaviour restated here (never its code):
+//   o0: rANS_static4x16pr.c:234-349, rANS_static32x16pr.c:256-410
+//   o1: rANS_static4x16pr.c:524-821, rANS_static32x16pr.c:531-758
+//   tables: rANS_static16_int.h:191-272 (alphabet, order-0), :425-536 (order-1)
+#pragma once
+#include "common.cuh"
+#ifdef B200_DEBUG
+#include <stdio.h>
+#endif
+
+namespace b200 {
+
+// Bump allocator over a scratch pool shared by the jobs of one launch.
+struct Pool {
+    uint8_t *base;
+    unsigned long long cap;
+    unsigned long long *used;   // device counter
+};
+__device__ inline uint8_t *pool_alloc(const Pool &p, uint32_t bytes, int lane) {
+    unsigned long long off = 0;
+    bytes = (bytes + 255u) & ~255u;
+    if (lane == 0) off = atomicAdd(p.used, (unsigned long long)bytes);
+    off = __shfl_sync(FULL, off, 0);
+    if (off + bytes > p.cap) return nullptr;
+    return p.base + off;
+}
+
+// ------------------------------------------------------------------------
+// Compressed-word staging: the 16-bit renormalisation words of one stream are
+// consumed strictly in order by the whole warp.  They are staged through a
+// 1 KiB shared-memory ring filled by 16-byte cp.async copies (four 256-byte
+// chunks), indexed by the low bits of the global address so that alignment is
+// preserved; bytes past the end of the stream are zero-filled, never read.
+// ------------------------------------------------------------------------
+constexpr uint32_t RING = 1024, CHUNK = 256;
+
+struct WordRing {
+    const uint8_t *a0;   // 256-byte aligned global base
+    uint8_t *ring;       // shared memory, RING bytes, 16-byte aligned
+    uint32_t pos;        // next unread byte, offset from a0
+    uint32_t end;        // end of stream, offset from a0
+    uint32_t fe;         // ring holds [fe-RING, fe)
+
+    __device__ __forceinline__ void fill_chunk(uint32_t c, int lane) const {
+        if (lane < 16) {
+            uint32_t p = c + lane * 16;
+            uint32_t nb = p + 16 <= end ? 16u : (p < end ? end - p : 0u);
+            cp_async16_zfill(ring + (p & (RING - 1)), a0 + p, nb);
+        }
+    }
+    __device__ __forceinline__ void init(const uint8_t *in, uint32_t start, uint32_t in_size,
+                                         uint8_t *ring_, int lane) {
+        uintptr_t A = (uintptr_t)in;
+        a0 = (const uint8_t *)(A & ~(uintptr_t)(CHUNK - 1));
+        uint32_t d = (uint32_t)(A - (uintptr_t)a0);
+        ring = ring_;
+        pos = d + start;
+        end = d + in_size;
+        uint32_t c0 = pos & ~(CHUNK - 1);
+        __syncwarp();
+        for (uint32_t c = 0; c < RING; c += CHUNK) fill_chunk(c0 + c, lane);
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncwarp();
+        fe = c0 + RING;
+    }
+    // Called once per step (a step consumes at most 64 bytes).
+    __device__ __forceinline__ void advance(int lane) {
+        if (pos + (RING - CHUNK) >= fe) {
+            cp_async_wait_all();       // the chunk issued one refill ago
+            __syncwarp();
+            fill_chunk(fe, lane);
+            cp_async_commit();
+            fe += CHUNK;
+        }
+    }
+    __device__ __forceinline__ uint32_t word_at(uint32_t p) const {
+        // p may be odd when the stream sits at an odd address
+        uint32_t o = p & (RING - 1);
+        if (p & 1) return ring[o] | ((uint32_t)ring[(o + 1) & (RING - 1)] << 8);
+        return *(const uint16_t *)(ring + o);
+    }
+    __device__ __forceinline__ void drain() const { cp_async_wait_all(); __syncwarp(); }
+};
+
+// One renormalisation round for the warp (rANS_word.h:414-476): lanes whose
+// state fell below 2^15 take the next words in lane order.  A lane refills only
+// if two more bytes exist, exactly like RansDecRenormSafe.
+__device__ __forceinline__ uint32_t renorm_step(uint32_t R, bool act, WordRing &w, int lane,
+                                                uint32_t lt) {
+    bool need = act && R < RANS_L;
+    uint32_t mask = __ballot_sync(FULL, need);
+    uint32_t k = __popc(mask & lt);
+    uint32_t cnt = __popc(mask);
+    if (w.pos + 64 > w.end) {            // near the end of the stream: count what is left
+        uint32_t avail = w.end > w.pos ? (w.end - w.pos) >> 1 : 0;
+        need = need && k < avail;
+        cnt = min(cnt, avail);
+    }
+    if (need) R = (R << 16) | w.word_at(w.pos + 2 * k);
+    w.pos += 2 * cnt;
+    w.advance(lane);
+    return R;
+}
+
+// ------------------------------------------------------------------------
+// Alphabet list (rANS_static16_int.h:191-238).  Single-thread, bounds checked.
+// Marks F[sym]=1; returns bytes consumed, 0 on failure.
+// ------------------------------------------------------------------------
+__device__ inline int get_alphabet(const uint8_t *cp, const uint8_t *end, uint32_t *F) {
+    const uint8_t *op = cp;
+    if (cp >= end) return 0;
+    int run = 0, j = *cp++;
+    do {
+        F[j] = 1;
+        if (cp >= end) return 0;
+        if (!run && j + 1 == *cp) {
+            if (cp + 1 >= end) return 0;
+            j = *cp++;
+            run = *cp++;
+        } else if (run) {
+            run--;
+            if (++j > 255) return 0;
+        } else {
+            j = *cp++;
+        }
+    } while (j && cp < end);
+    return (int)(cp - op);
+}
+
+// ======================================================================== o0
+struct __align__(16) DecO0Smem {
+    uint8_t  ring[RING];
+    uint32_t tab[256];     // freq | start<<16 (freq may be 4096: no 12-bit wrap)
+    uint8_t  lut[4096];    // slot -> symbol
+};
+
+// Returns 0 on success.  `out` receives out_sz bytes.
+template <int N>
+__device__ int dec_o0(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_t out_sz,
+                      DecO0Smem &S, int lane) {
+    if (in_size < 16 || out_sz >= 0x7fffffffu) return 1;
+    const uint8_t *end = in + in_size;
+    for (int j = lane; j < 256; j += 32) S.tab[j] = 0;
+    __syncwarp();
+
+    // --- frequency table: alphabet + one varint per listed symbol (lane 0)
+    int hdr = 0;
+    if (lane == 0) {
+        const uint8_t *tend = (N == 4) ? end - 8 : end;     // rANS_static4x16pr.c:249
+        const uint8_t *cp = in;
+        int n = get_alphabet(cp, tend, S.tab);
+        if (n) {
+            cp += n;
+            for (int j = 0; j < 256; j++) {
+                if (!S.tab[j]) continue;
+                uint32_t f;
+                cp += var_get_u32(cp, tend, &f);
+                S.tab[j] = f;
+            }
+            hdr = (int)(cp - in);
+        }
+    }
+    hdr = __shfl_sync(FULL, hdr, 0);
+    if (!hdr) return 1;
+    __syncwarp();
+
+    // --- scale to 4096 (rANS_static16_int.h:151-162) and accumulate starts
+    uint32_t f[8], loc = 0;
+    bool bad = false;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        f[t] = S.tab[lane * 8 + t];
+        bad |= f[t] > 4096;
+        loc += f[t];
+    }
+    if (__any_sync(FULL, bad)) return 1;
+    uint32_t incl = warp_incl_scan(loc, lane);
+    uint32_t fsum = __shfl_sync(FULL, incl, 31);
+    if (fsum == 0 || fsum > 4096 || (fsum & (fsum - 1))) return 1;
+    int sh = __clz(fsum) - __clz(4096u);
+    uint32_t x = (incl - loc) << sh;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        uint32_t ff = f[t] << sh;
+        S.tab[lane * 8 + t] = ff | (x << 16);
+        x += ff;
+    }
+    __syncwarp();
+    for (int j = 0; j < 256; j++) {
+        uint32_t fb = S.tab[j], ff = fb & 0xffff, b = fb >> 16;
+        for (uint32_t y = lane; y < ff; y += 32) S.lut[b + y] = (uint8_t)j;
+    }
+
+    // --- N initial states, little endian, lane 0 first (rANS_word.h:121-134)
+    if ((uint32_t)(end - (in + hdr)) < (uint32_t)N * 4) return 1;
+    const bool act = lane < N;
+    uint32_t R = RANS_L;
+    if (act) {
+        const uint8_t *p = in + hdr + 4 * lane;
+        R = p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24);
+    }
+    if (__any_sync(FULL, R < RANS_L)) return 1;
+
+    WordRing w;
+    w.init(in, hdr + 4 * N, in_size, S.ring, lane);     // ends with __syncwarp: lut visible
+    const uint32_t lt = lanemask_lt();
+    const uint32_t full = out_sz - out_sz % N;
+    for (uint32_t i = 0; i < full; i += N) {
+        uint32_t m = R & 4095;
+        uint32_t s = S.lut[m];
+        uint32_t fb = S.tab[s];
+        R = (fb & 0xffff) * (R >> 12) + m - (fb >> 16);
+        if (act) out[i + lane] = (uint8_t)s;
+        R = renorm_step(R, act, w, lane, lt);
+    }
+    // the last out_sz % N symbols: table look-up only (rANS_static32x16pr.c:400-401)
+    if ((uint32_t)lane < out_sz - full) out[full + lane] = S.lut[R & 4095];
+    w.drain();
+    return 0;
+}
+
+// ======================================================================== o1
+// Tables live in rank space: only symbols of the alphabet get rows/columns.
+//   fs[ctx][r]   = start | freq<<16 of the r-th listed symbol in context ctx
+//   blut[ctx][b] = rank of the symbol owning slot b<<(shift-6)
+// A look-up is blut -> fs[r], stepping r forward while slot >= start+freq.
+struct DecO1Tabs {
+    uint32_t *fs;       // [nsym][nsym]
+    uint8_t  *blut;     // [nsym][64]
+    uint8_t  *sym;      // [nsym] rank -> symbol
+    uint32_t  nsym;
+};
+constexpr int O1_BUCKET_BITS = 6;
+
+__host__ __device__ inline uint32_t dec_o1_tab_bytes(uint32_t nsym) {
+    return nsym * nsym * 4 + nsym * 64 + ((nsym + 15) & ~15u);
+}
+
+// one order-1 row (rANS_static16_int.h:425-456), single thread.  A[] lists the
+// alphabet (rank -> symbol); writes F[rank].  Returns bytes consumed, 0 = error.
+__device__ inline int get_freq_row(const uint8_t *cp, const uint8_t *end, uint32_t nsym,
+                                   uint32_t *F, uint32_t *tot) {
+    const uint8_t *op = cp;
+    if (cp >= end) return 0;
+    uint32_t zrun = 0, t = 0;
+    for (uint32_t r = 0; r < nsym; r++) {
+        uint32_t f = 0;
+        if (cp >= end) { F[r] = 0; continue; }    // the reference's loop stops here; rest stay 0
+        if (zrun) { zrun--; }
+        else {
+            cp += var_get_u32(cp, end, &f);
+            if (f == 0) {
+                if (cp >= end) return 0;
+                zrun = *cp++;
+            }
+        }
+        F[r] = f;
+        t += f;
+    }
+    *tot = t;
+    return (int)(cp - op);
+}
+
+struct __align__(16) DecO1Smem {
+    uint8_t  ring[RING];
+    uint32_t F0[256];           // alphabet marks / scratch
+    uint8_t  rank[256];
+};                              // followed by dynamic table storage (DecO1Tabs) when it fits
+
+template <int N>
+__device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_t out_sz,
+                      DecO1Smem &S, uint8_t *smem_tabs, uint32_t smem_tab_bytes, DecO0Smem *o0s,
+                      const Pool &pool, int lane) {
+    if (in_size < (uint32_t)(N == 4 ? 16 : N * 4) || out_sz >= 0x7fffffffu) return 1;
+    const uint8_t *end = in + in_size;
+    const uint8_t *cp = in, *tend = end, *after = nullptr;
+    const uint32_t shift = *cp >> 4;
+    if (shift != 10 && shift != 12) return 1;       // the encoder writes nothing else
+    const uint32_t tot = 1u << shift;
+    const bool comp = *cp++ & 1;
+    if (comp) {                                     // table itself rANS-coded (o0, 4 lanes)
+        uint32_t usz = 0, csz = 0;
+        cp += var_get_u32(cp, end, &usz);
+        cp += var_get_u32(cp, end, &csz);
+        if (csz > (uint32_t)(end - cp) || usz > 257 * 257 * 3) return 1;
+        after = cp + csz;
+        uint8_t *tb = pool_alloc(pool, usz + 16, lane);
+        if (!tb) return 2;
+        if (dec_o0<4>(cp, csz, tb, usz, *o0s, lane)) return 1;
+        __threadfence_block();
+        __syncwarp();
+        cp = tb;
+        tend = tb + usz;
+    }
+
+    // --- alphabet (single thread), then ranks
+    for (int j = lane; j < 256; j += 32) S.F0[j] = 0;
+    __syncwarp();
+    int n = 0;
+    if (lane == 0) n = get_alphabet(cp, tend, S.F0);
+    n = __shfl_sync(FULL, n, 0);
+    if (!n) return 1;
+    cp += n;
+    if (cp >= tend) return 1;
+    __syncwarp();
+    uint32_t nsym = 0;
+    {
+        uint32_t loc = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) loc += S.F0[lane * 8 + t] ? 1 : 0;
+        uint32_t incl = warp_incl_scan(loc, lane);
+        nsym = __shfl_sync(FULL, incl, 31);
+        uint32_t r = incl - loc;
+        for (int t = 0; t < 8; t++) {
+            int j = lane * 8 + t;
+            S.rank[j] = S.F0[j] ? (uint8_t)r++ : 0xff;
+        }
+    }
+    __syncwarp();
+
+    // --- table storage: shared memory when it fits, else the scratch pool
+    DecO1Tabs T;
+    T.nsym = nsym;
+    uint32_t need = dec_o1_tab_bytes(nsym);
+    uint8_t *tb;
+    const bool in_smem = need <= smem_tab_bytes;
+    if (in_smem) tb = smem_tabs;
+    else { tb = pool_alloc(pool, need, lane); if (!tb) return 2; }
+    T.fs = (uint32_t *)tb;
+    T.blut = tb + nsym * nsym * 4;
+    T.sym = T.blut + nsym * 64;
+    for (int j = lane; j < 256; j += 32)
+        if (S.rank[j] != 0xff) T.sym[S.rank[j]] = (uint8_t)j;
+
+    // --- rows, in alphabet order (rANS_static16_int.h:488-530); serial varint parse
+    int err = 0;
+    if (lane == 0) {
+        for (uint32_t i = 0; i < nsym && !err; i++) {
+            uint32_t *row = T.fs + i * nsym, tsum = 0;
+            int c = get_freq_row(cp, tend, nsym, row, &tsum);
+            if (!c) { err = 1; break; }
+            cp += c;
+            if (!tsum) { for (uint32_t r = 0; r < nsym; r++) row[r] = 0; continue; }
+            int sh = 0;
+            { uint32_t z = tsum; while (z < tot) { z *= 2; sh++; } }   // normalise_freq_shift
+            uint32_t x = 0;
+            for (uint32_t r = 0; r < nsym; r++) {
+                uint32_t f = row[r] << sh;
+                if (row[r] > tot || f > tot - x) { err = 1; break; }
+                row[r] = x | (f << 16);
+                x += f;
+            }
+            if (!err && x != tot) err = 1;
+        }
+    }
+    err = __shfl_sync(FULL, err, 0);
+    if (err) return 1;
+    {   // only lane 0 walked the table: share where it ended
+        const uint8_t *tbase = comp ? tend : in;     // any pointer all lanes agree on
+        long long d = __shfl_sync(FULL, (long long)(cp - tbase), 0);
+        cp = tbase + d;
+    }
+    __threadfence_block();
+    __syncwarp();
+    // --- bucket look-up: lane per row
+    const uint32_t bw = shift - O1_BUCKET_BITS;
+    for (uint32_t i = lane; i < nsym; i += 32) {
+        const uint32_t *row = T.fs + i * nsym;
+        uint8_t *bl = T.blut + i * 64;
+        uint32_t r = 0, e = row[0];
+        bool empty = true;
+        for (uint32_t q = 0; q < nsym; q++) empty &= (row[q] >> 16) == 0;
+        for (uint32_t b = 0; b < 64; b++) {
+            uint32_t m = b << bw;
+            if (!empty)
+                while (r + 1 < nsym && m >= (e & 0xffff) + (e >> 16)) e = row[++r];
+            bl[b] = (uint8_t)r;
+        }
+    }
+    if (after) cp = after;
+    if ((uint32_t)(end - cp) < (uint32_t)N * 4) return 1;
+    const bool act = lane < N;
+    uint32_t R = RANS_L;
+    if (act) {
+        const uint8_t *p = cp + 4 * lane;
+        R = p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24);
+    }
+    if (__any_sync(FULL, R < RANS_L)) return 1;
+
+#ifdef B200_DEBUG
+    if (lane == 0) {
+        printf("dec_o1<%d> in_size=%u out_sz=%u shift=%u comp=%d nsym=%u in_smem=%d cpoff=%ld R0=%x\n", N, in_size, out_sz, shift, (int)comp, nsym, (int)in_smem, (long)(cp - in), R);
+        for (uint32_t i = 0; i < nsym && i < 4; i++) { printf(" row%u:", i); for (uint32_t r = 0; r < nsym && r < 8; r++) printf(" %u+%u", T.fs[i*nsym+r] & 0xffff, T.fs[i*nsym+r] >> 16); printf(" | blut"); for (int b = 0; b < 8; b++) printf(" %u", T.blut[i*64+b*8]); printf(" sym %u\n", T.sym[i]); }
+    }
+#endif
+    WordRing w;
+    w.init(in, (uint32_t)(cp - in) + 4 * N, in_size, S.ring, lane);
+    __threadfence_block();
+    __syncwarp();
+    const uint32_t lt = lanemask_lt();
+    const uint32_t seg = out_sz / N, mask = tot - 1;
+    uint8_t *o = out + (size_t)lane * seg;
+    uint32_t ctx = S.rank[0];               // every lane starts in context 0 (symbol 0 is always listed)
+    if (ctx == 0xff) return 1;
+    const uint32_t *fs = T.fs;
+    const uint8_t *blut = T.blut, *symtab = T.sym;
+    const uint32_t ns = nsym;
+
+    auto step = [&](bool on) {
+        uint32_t m = R & mask;
+        uint32_t r = blut[ctx * 64 + (m >> bw)];
+        const uint32_t *row = fs + ctx * ns;
+        uint32_t e = row[r];
+        while (m - (e & 0xffff) >= (e >> 16) && r + 1 < ns) e = row[++r];   // unsigned: m >= start always
+        if (on) {
+            R = (e >> 16) * (R >> shift) + m - (e & 0xffff);
+            ctx = r;
+        }
+        return (uint8_t)symtab[r];
+    };
+
+    for (uint32_t k = 0; k < seg; k++) {
+        uint8_t s = step(act);
+        if (act) o[k] = s;
+        R = renorm_step(R, act, w, lane, lt);
+    }
+    // remainder: the last lane alone (rANS_static32x16pr.c:676-684)
+    const bool last = lane == N - 1;
+    for (uint32_t k = seg * N; k < out_sz; k++) {
+        uint8_t s = step(last);
+        if (last) out[k] = s;
+        R = renorm_step(R, last, w, lane, lt);
+    }
+    w.drain();
+    return 0;
+}
+
+}  // namespace b200

@@ -1,0 +1,537 @@
+// rans_encode.cuh -- device side of rans_compress_to_4x16: histograms, the
+// reference's exact frequency normalisation and table serialisation, and the
+// backward N-lane rANS encode with warp-ballot compaction of the 16-bit words.
+// One warp per stream.
+//
+// Reference behaviour restated here (never its code):
+//   o0: rANS_static4x16pr.c:112-232, rANS_static32x16pr.c:67-254
+//   o1: rANS_static4x16pr.c:422-518, rANS_static32x16pr.c:414-525
+//   model: rANS_static16_int.h:97-146 (normalise_freq), :165-189, :240-252,
+//          :278-306, :312-421 (encode_freq1); rANS_static4x16pr.c:357-420 (shift)
+//   symbol: rANS_word.h:201-272 (RansEncSymbolInit), :287-336 (RansEncPutSymbol)
+#pragma once
+#include "common.cuh"
+#include "rans_decode.cuh"   // Pool
+
+namespace b200 {
+
+// ------------------------------------------------------------------------
+// Order-0 histogram of a byte range by one warp into shared memory.
+// 16-byte loads; equal neighbours inside a lane's 16 bytes are merged into one
+// shared-memory atomic (quality strings are sticky).
+// ------------------------------------------------------------------------
+__device__ inline void warp_hist8(const uint8_t *in, uint32_t n, uint32_t *F, int lane) {
+    for (int j = lane; j < 256; j += 32) F[j] = 0;
+    __syncwarp();
+    uint32_t head = (uint32_t)((16 - ((uintptr_t)in & 15)) & 15);
+    if (head > n) head = n;
+    if ((uint32_t)lane < head) atomicAdd(&F[in[lane]], 1u);
+    const uint8_t *p = in + head;
+    uint32_t rest = n - head, nv = rest >> 4;
+    const uint4 *v = (const uint4 *)p;
+    for (uint32_t i = lane; i < nv; i += 32) {
+        uint4 q = v[i];
+        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        uint32_t prev = w[0] & 0xff, cnt = 0;
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                uint32_t c = (w[a] >> (8 * b)) & 0xff;
+                if (c == prev) cnt++;
+                else { atomicAdd(&F[prev], cnt); prev = c; cnt = 1; }
+            }
+        atomicAdd(&F[prev], cnt);
+    }
+    for (uint32_t i = (nv << 4) + lane; i < rest; i += 32) atomicAdd(&F[p[i]], 1u);
+    __syncwarp();
+}
+
+__device__ __forceinline__ uint32_t round2(uint32_t v) {      // rANS_static16_int.h:86-95
+    v--;
+    v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v >> 8; v |= v >> 16;
+    return v + 1;
+}
+
+// ------------------------------------------------------------------------
+// normalise_freq (rANS_static16_int.h:97-146), warp version over 256 entries
+// in shared memory (lane owns entries 8*lane..8*lane+7).
+// 31-bit fixed-point scale; zero stays zero, non-zero stays >= 1; the FIRST most
+// frequent symbol absorbs the error; one rescale from the scaled counts if that
+// would more than halve it; greedy shave as the last resort.
+// ------------------------------------------------------------------------
+__device__ inline int normalise_freq_warp(uint32_t *F, uint32_t size_in, uint32_t tot, int lane) {
+    if (!size_in) return 0;
+    int size = (int)size_in;
+    int big = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        uint64_t tr = ((uint64_t)tot << 31) / (uint32_t)size + (uint32_t)((1 << 30) / size);
+        uint32_t top = 0, sum = 0;
+        int arg = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            int j = lane * 8 + t;
+            uint32_t f = F[j];
+            if (!f) continue;
+            if (top < f) { top = f; arg = j; }
+            f = (uint32_t)((f * tr) >> 31);
+            if (!f) f = 1;
+            F[j] = f;
+            sum += f;
+        }
+        sum = warp_sum(sum);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {          // max, ties -> lowest index
+            uint32_t t2 = __shfl_xor_sync(FULL, top, o);
+            int a2 = __shfl_xor_sync(FULL, arg, o);
+            if (t2 > top || (t2 == top && a2 < arg)) { top = t2; arg = a2; }
+        }
+        big = top ? arg : 0;
+        __syncwarp();
+        int adjust = (int)tot - (int)sum;
+        uint32_t fb = F[big];
+        if (adjust >= 0) { if (lane == 0) F[big] = fb + adjust; break; }
+        if (fb > (uint32_t)-adjust && (pass == 1 || fb / 2 >= (uint32_t)-adjust)) {
+            if (lane == 0) F[big] = fb + adjust;
+            break;
+        }
+        if (pass == 0) { size = (int)sum; continue; }
+        if (lane == 0) {
+            adjust += fb - 1;
+            F[big] = 1;
+            for (int j = 0; adjust && j < 256; j++) {
+                if (F[j] < 2) continue;
+                int d = (F[j] > (uint32_t)-adjust) ? adjust : 1 - (int)F[j];
+                F[j] += d;
+                adjust -= d;
+            }
+        }
+    }
+    __syncwarp();
+    return F[big] > 0 ? 0 : -1;
+}
+
+// Same algorithm, one thread, over the n entries of one order-1 row.
+__device__ inline int normalise_freq_row(uint32_t *F, uint32_t n, uint32_t size_in, uint32_t tot) {
+    if (!size_in) return 0;
+    int size = (int)size_in;
+    uint32_t big = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        uint64_t tr = ((uint64_t)tot << 31) / (uint32_t)size + (uint32_t)((1 << 30) / size);
+        uint32_t top = 0, sum = 0;
+        big = 0;
+        for (uint32_t j = 0; j < n; j++) {
+            uint32_t f = F[j];
+            if (!f) continue;
+            if (top < f) { top = f; big = j; }
+            f = (uint32_t)((f * tr) >> 31);
+            if (!f) f = 1;
+            F[j] = f;
+            sum += f;
+        }
+        int adjust = (int)tot - (int)sum;
+        if (adjust >= 0) { F[big] += adjust; break; }
+        if (F[big] > (uint32_t)-adjust && (pass == 1 || F[big] / 2 >= (uint32_t)-adjust)) {
+            F[big] += adjust;
+            break;
+        }
+        if (pass == 0) { size = (int)sum; continue; }
+        adjust += F[big] - 1;
+        F[big] = 1;
+        for (uint32_t j = 0; adjust && j < n; j++) {
+            if (F[j] < 2) continue;
+            int d = (F[j] > (uint32_t)-adjust) ? adjust : 1 - (int)F[j];
+            F[j] += d;
+            adjust -= d;
+        }
+    }
+    return F[big] > 0 ? 0 : -1;
+}
+
+// Alphabet list (rANS_static16_int.h:165-189), single thread.
+__device__ inline int put_alphabet(uint8_t *cp, const uint32_t *F) {
+    uint8_t *op = cp;
+    int j = 0;
+    while (j < 256) {
+        if (!F[j]) { j++; continue; }
+        *cp++ = (uint8_t)j;
+        if (j && F[j - 1]) {
+            int k = j + 1;
+            while (k < 256 && F[k]) k++;
+            *cp++ = (uint8_t)(k - (j + 1));
+            j = k;
+        } else j++;
+    }
+    *cp++ = 0;
+    return (int)(cp - op);
+}
+
+// Encoder symbol (rANS_word.h:171-179,201-272) packed into 16 bytes:
+//   x = x_max, y = rcp_freq, z = bias, w = cmpl_freq | (rcp_shift-32)<<16
+__device__ __forceinline__ uint4 enc_sym_init(uint32_t start, uint32_t freq, uint32_t bits) {
+    uint4 s;
+    s.x = ((RANS_L >> bits) << 16) * freq - 1;
+    uint32_t cmpl = ((1u << bits) - freq) & 0xffff;
+    if (freq < 2) {
+        s.y = ~0u;
+        s.z = start + (1u << bits) - 1;
+        s.w = cmpl;
+    } else {
+        uint32_t sh = 32 - __clz(freq - 1);                 // smallest sh with freq <= 1<<sh
+        s.y = (uint32_t)(((1ull << (sh + 31)) + freq - 1) / freq);
+        s.z = start;
+        s.w = cmpl | ((sh - 1) << 16);
+    }
+    return s;
+}
+
+// One encode step for the warp (rANS_word.h:287-336 + the lane order of
+// rANS_static32x16pr.c:187-231): lanes whose state exceeds x_max emit their low
+// 16 bits; lane 31's word lands at the highest address.  ptr moves down.
+__device__ __forceinline__ uint32_t enc_step(uint32_t R, bool on, uint4 e, uint8_t *&ptr, int lane) {
+    bool emit = on && R > e.x;
+    uint32_t mask = __ballot_sync(FULL, emit);
+    if (emit) {
+        uint32_t k = __popc(mask >> lane);
+        *(uint16_t *)(ptr - 2 * k) = (uint16_t)R;
+        R >>= 16;
+    }
+    ptr -= 2 * __popc(mask);
+    if (on) {
+        uint32_t q = __umulhi(R, e.y) >> (e.w >> 16);
+        R = R + e.z + q * (e.w & 0xffff);
+    }
+    return R;
+}
+
+__device__ __forceinline__ void enc_flush(uint32_t R, bool act, int N, uint8_t *&ptr, int lane) {
+    ptr -= 4 * N;
+    if (act) {
+        uint16_t *p = (uint16_t *)(ptr + 4 * lane);       // ptr is 2-byte aligned only
+        p[0] = (uint16_t)R;
+        p[1] = (uint16_t)(R >> 16);
+    }
+}
+
+// ======================================================================== o0
+struct __align__(16) EncO0Smem {
+    uint4    sym[256];
+    uint32_t F[256];
+};
+
+// Writes the frequency table at `out` (forwards) and the payload below
+// `out_end` (backwards).  Returns 0 ok; *tab_len, *ptr_out give the two pieces.
+template <int N>
+__device__ int enc_o0(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_end,
+                      uint32_t *tab_len, uint8_t **ptr_out, EncO0Smem &S, int lane) {
+    uint8_t *ptr = out_end;
+    *tab_len = 0;
+    *ptr_out = ptr;
+    if (n == 0) return 0;
+    warp_hist8(in, n, S.F, lane);
+
+    uint32_t fsum = round2(n);
+    if (fsum > 4096) fsum = 4096;
+    if (normalise_freq_warp(S.F, n, fsum, lane) < 0) return 1;
+    uint32_t tl = 0;
+    if (lane == 0) {                                        // rANS_static16_int.h:240-252
+        uint8_t *cp = out;
+        cp += put_alphabet(cp, S.F);
+        for (int j = 0; j < 256; j++)
+            if (S.F[j]) cp += var_put_u32(cp, S.F[j]);
+        tl = (uint32_t)(cp - out);
+    }
+    tl = __shfl_sync(FULL, tl, 0);
+    *tab_len = tl;
+    if (normalise_freq_warp(S.F, fsum, 4096, lane) < 0) return 1;
+
+    {   // cumulative starts and encoder symbols
+        uint32_t f[8], loc = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) { f[t] = S.F[lane * 8 + t]; loc += f[t]; }
+        uint32_t x = warp_incl_scan(loc, lane) - loc;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            if (f[t]) S.sym[lane * 8 + t] = enc_sym_init(x, f[t], 12);
+            x += f[t];
+        }
+    }
+    __syncwarp();
+
+    // NB every lane runs the same ballots: lanes >= N (N == 4) are predicated off.
+    const bool act = (N == 32) ? true : lane < N;
+    uint32_t R = RANS_L;
+    const uint32_t rem = n % N;
+    uint32_t i = n - rem;
+    if (rem) {                                               // symbols i..n-1 on lanes 0..rem-1
+        bool on = (uint32_t)lane < rem;
+        uint4 e = S.sym[on ? in[i + lane] : 0];
+        R = enc_step(R, on, e, ptr, lane);
+    }
+    const uint8_t *q = in + (act ? lane : 0);
+    for (; i >= 4 * N; i -= 4 * N) {
+        uint32_t s0 = q[i - N], s1 = q[i - 2 * N], s2 = q[i - 3 * N], s3 = q[i - 4 * N];
+        uint4 e0 = S.sym[s0], e1 = S.sym[s1], e2 = S.sym[s2], e3 = S.sym[s3];
+        R = enc_step(R, act, e0, ptr, lane);
+        R = enc_step(R, act, e1, ptr, lane);
+        R = enc_step(R, act, e2, ptr, lane);
+        R = enc_step(R, act, e3, ptr, lane);
+    }
+    for (; i > 0; i -= N) R = enc_step(R, act, S.sym[q[i - N]], ptr, lane);
+    enc_flush(R, act, N, ptr, lane);
+    *ptr_out = ptr;
+    __syncwarp();
+    return 0;
+}
+
+// ======================================================================== o1
+// rans_compute_shift (rANS_static4x16pr.c:357-420) helpers
+__device__ __forceinline__ double fast_log(double a) {                    // utils.h:69-72
+    return (double)(__double_as_longlong(a) - 4606921278410026770LL) * 1.539095918623324e-16;
+}
+
+struct __align__(16) EncO1Smem {
+    uint32_t T[256];        // o0 counts, then order-1 row totals (symbol space)
+    uint8_t  rank[256];
+    uint8_t  sym[256];      // rank -> symbol
+    uint16_t S[256];        // per-row stored total (rank space)
+    uint32_t rowlen[256];   // serialised row lengths / offsets (rank space)
+};                          // followed by dynamic storage: nsym*nsym pair counts when they fit
+
+// serialise one row against the alphabet (rANS_static16_int.h:278-306): every
+// listed symbol gets a varint, a run of z zeros becomes 0,(z-1).  With cp==null
+// only the length is computed.
+__device__ inline uint32_t put_freq_row(uint8_t *cp, const uint32_t *F, uint32_t n) {
+    uint32_t len = 0, j = 0;
+    while (j < n) {
+        if (F[j]) {
+            if (cp) len += var_put_u32(cp + len, F[j]); else len += var_size_u32(F[j]);
+            j++;
+            continue;
+        }
+        uint32_t z = 0;
+        while (j < n && !F[j]) { z++; j++; }
+        if (cp) { cp[len] = 0; cp[len + 1] = (uint8_t)(z - 1); }
+        len += 2;
+    }
+    return len;
+}
+
+template <int N>
+__device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_end,
+                      uint32_t *tab_len, uint8_t **ptr_out, EncO1Smem &S, uint32_t *smem_hist,
+                      uint32_t smem_hist_words, EncO0Smem *o0s, const Pool &pool, int lane) {
+    *tab_len = 0;
+    *ptr_out = out_end;
+    if (N == 32 && n < 32) return 1;
+    const uint32_t seg = n / N;
+
+    // ---- alphabet = symbols present, plus 0 (rANS_static16_int.h:357-361)
+    warp_hist8(in, n, S.T, lane);
+    uint32_t nsym;
+    {
+        uint32_t loc = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) { int j = lane * 8 + t; loc += (S.T[j] || j == 0) ? 1 : 0; }
+        uint32_t incl = warp_incl_scan(loc, lane);
+        nsym = __shfl_sync(FULL, incl, 31);
+        uint32_t r = incl - loc;
+        for (int t = 0; t < 8; t++) {
+            int j = lane * 8 + t;
+            bool p = S.T[j] || j == 0;
+            S.rank[j] = p ? (uint8_t)r : 0xff;
+            if (p) S.sym[r++] = (uint8_t)j;
+        }
+    }
+    __syncwarp();
+
+    // ---- pair counts H[rank(prev)][rank(cur)], first symbol follows 0 (utils.h:279-357)
+    uint32_t *H;
+    const uint32_t hw = nsym * nsym;
+    if (hw <= smem_hist_words) H = smem_hist;
+    else { H = (uint32_t *)pool_alloc(pool, hw * 4, lane); if (!H) return 2; }
+    for (uint32_t j = lane; j < hw; j += 32) H[j] = 0;
+    __syncwarp();
+    for (uint32_t base = 0; base < n; base += 32) {
+        uint32_t p = base + lane;
+        if (p < n) {
+            uint32_t prev = p ? in[p - 1] : 0, cur = in[p];
+            atomicAdd(&H[S.rank[prev] * nsym + S.rank[cur]], 1u);
+        }
+    }
+    // lanes 1..N-1 start in context 0 (rANS_static16_int.h:325-327)
+    if (lane >= 1 && lane < N) atomicAdd(&H[S.rank[0] * nsym + S.rank[in[lane * seg]]], 1u);
+    __syncwarp();
+    // row totals; the last symbol's total gets one extra (utils.h:311,345)
+    for (uint32_t i = lane; i < nsym; i += 32) {
+        uint32_t t = 0;
+        for (uint32_t j = 0; j < nsym; j++) t += H[i * nsym + j];
+        if (S.sym[i] == in[n - 1]) t++;
+        S.T[i] = t;                     // now rank space
+    }
+    __syncwarp();
+
+    // ---- precision: 10 or 12 bits (rANS_static4x16pr.c:357-420), lane per row
+    double e10 = 0, e12 = 0;
+    uint32_t max_tot = 0;
+    for (uint32_t i = lane; i < nsym; i += 32) {
+        const uint32_t *row = H + i * nsym;
+        uint32_t Ti = S.T[i];
+        if (!Ti) { S.S[i] = 0; continue; }
+        uint32_t max_val = round2(Ti);
+        int ns = 0, sm10 = 0, sm12 = 0;
+        for (uint32_t j = 0; j < nsym; j++) {
+            uint32_t f = row[j];
+            if (f && max_val / f > 1024) sm10++;
+            if (f && max_val / f > 4096) sm12++;
+        }
+        double l10 = log((double)(1024 + sm10)), l12 = log((double)(4096 + sm12));
+        double T_slow = (double)4096 / Ti, T_fast = (double)1024 / Ti;
+        for (uint32_t j = 0; j < nsym; j++) {
+            uint32_t f = row[j];
+            if (!f) continue;
+            ns++;
+            double a = f * T_fast, b = f * T_slow;
+            e10 -= f * (fast_log(a > 1 ? a : 1) - l10);
+            e12 -= f * (fast_log(b > 1 ? b : 1) - l12);
+            e10 += 1.3;
+            e12 += 4.7;
+        }
+        if (ns < 64 && max_val > 128) max_val /= 2;
+        if (max_val > 1024) max_val /= 2;
+        if (max_val > 4096) max_val = 4096;
+        S.S[i] = (uint16_t)max_val;
+        if (max_tot < max_val) max_tot = max_val;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        e10 += __shfl_xor_sync(FULL, e10, o);
+        e12 += __shfl_xor_sync(FULL, e12, o);
+        max_tot = max(max_tot, __shfl_xor_sync(FULL, max_tot, o));
+    }
+    const uint32_t shift = (e10 / e12 < 1.01 || max_tot <= 1024) ? 10 : 12;
+
+    // ---- rows: normalise to the stored total, measure, serialise, scale, symbols
+    uint4 *symtab = (uint4 *)pool_alloc(pool, hw * 16, lane);
+    if (!symtab) return 2;
+    int err = 0;
+    for (uint32_t i = lane; i < nsym; i += 32) {
+        uint32_t *row = H + i * nsym;
+        uint32_t Ti = S.T[i];
+        if (!Ti) { S.rowlen[i] = 0; continue; }
+        uint32_t mv = S.S[i];
+        if (shift == 10 && mv > 1024) mv = 1024;
+        if (normalise_freq_row(row, nsym, Ti, mv) < 0) err = 1;
+        S.S[i] = (uint16_t)mv;
+        S.rowlen[i] = put_freq_row(nullptr, row, nsym);
+    }
+    if (__any_sync(FULL, err)) return 1;
+    __syncwarp();
+    uint32_t hdr = 0;
+    if (lane == 0) {
+        // alphabet of the CONTEXTS that have a row, with 0 forced in (:357-361)
+        uint32_t *A = S.rowlen + 0;            // reuse not possible: build a private mark array
+        (void)A;
+        uint8_t *cp = out;
+        *cp++ = 0;
+        // put_alphabet over symbol space: mark = row total != 0 (or symbol 0)
+        int j = 0;
+        auto present = [&](int s) { uint8_t r = S.rank[s]; return r != 0xff && (S.T[r] != 0 || s == 0); };
+        while (j < 256) {
+            if (!present(j)) { j++; continue; }
+            *cp++ = (uint8_t)j;
+            if (j && present(j - 1)) {
+                int k = j + 1;
+                while (k < 256 && present(k)) k++;
+                *cp++ = (uint8_t)(k - (j + 1));
+                j = k;
+            } else j++;
+        }
+        *cp++ = 0;
+        hdr = (uint32_t)(cp - out);
+        uint32_t off = hdr;                      // exclusive scan of row lengths
+        for (uint32_t i = 0; i < nsym; i++) { uint32_t l = S.rowlen[i]; S.rowlen[i] = off; off += l; }
+        hdr = off;
+    }
+    uint32_t tl = __shfl_sync(FULL, hdr, 0);
+    __syncwarp();
+    for (uint32_t i = lane; i < nsym; i += 32) {
+        uint32_t *row = H + i * nsym;
+        if (!S.T[i]) continue;
+        put_freq_row(out + S.rowlen[i], row, nsym);
+        uint32_t mv = S.S[i];
+        int sh = 0;
+        while ((mv << sh) < (1u << shift)) sh++;
+        uint32_t x = 0;
+        for (uint32_t j = 0; j < nsym; j++) {
+            uint32_t f = row[j] << sh;
+            symtab[i * nsym + j] = enc_sym_init(x, f, shift);
+            x += f;
+        }
+    }
+    __threadfence_block();
+    __syncwarp();
+
+    out[0] = (uint8_t)(shift << 4);
+    if (tl > 1000) {                          // try the 4-lane o0 coder on the table (:396-412)
+        uint32_t usz = tl - 1;
+        uint32_t cb = compress_bound(usz, 0) - 20;
+        uint8_t *tmp = pool_alloc(pool, cb + 16, lane);
+        if (!tmp) return 2;
+        uint32_t ctab = 0;
+        uint8_t *cptr = nullptr;
+        __syncwarp();
+        if (enc_o0<4>(out + 1, usz, tmp, tmp + (cb & ~1u), &ctab, &cptr, *o0s, lane) == 0) {
+            uint32_t pay = (uint32_t)(tmp + (cb & ~1u) - cptr);
+            uint32_t csz = ctab + pay;
+            if (csz + 6 < tl) {
+                uint32_t h = 1;
+                if (lane == 0) {
+                    out[0] |= 1;
+                    h += var_put_u32(out + h, usz);
+                    h += var_put_u32(out + h, csz);
+                }
+                h = __shfl_sync(FULL, h, 0);
+                __syncwarp();
+                warp_copy(out + h, tmp, ctab, lane);
+                warp_copy(out + h + ctab, cptr, pay, lane);
+                tl = h + csz;
+            }
+        }
+        __syncwarp();
+    }
+    *tab_len = tl;
+
+    // ---- encode.  Lane z owns [z*seg,(z+1)*seg); lane N-1 also the tail; every
+    // symbol is coded in the context of its predecessor, lane starts in context 0.
+    const bool act = lane < N;
+    uint8_t *ptr = out_end;
+    uint32_t R = RANS_L;
+    const uint8_t *rank = S.rank;
+    {   // tail on lane N-1, from the end down to N*seg
+        const bool lastl = lane == N - 1;
+        for (uint32_t p = n - 1; p >= N * seg && p > 0; p--) {
+            uint4 e = make_uint4(0, 0, 0, 0);
+            if (lastl) e = symtab[rank[in[p - 1]] * nsym + rank[in[p]]];
+            R = enc_step(R, lastl, e, ptr, lane);
+        }
+    }
+    const uint8_t *q = in + (size_t)(act ? lane : 0) * seg;
+    uint32_t rs = act && seg ? rank[q[seg - 1]] : 0;         // rank of the symbol being coded
+    for (uint32_t k = seg; k-- > 1;) {
+        uint32_t rc = rank[q[k - 1]];
+        uint4 e = symtab[rc * nsym + rs];
+        R = enc_step(R, act, e, ptr, lane);
+        rs = rc;
+    }
+    if (seg) {
+        uint4 e = symtab[rank[0] * nsym + rs];
+        R = enc_step(R, act, e, ptr, lane);
+    }
+    enc_flush(R, act, N, ptr, lane);
+    *ptr_out = ptr;
+    __syncwarp();
+    return 0;
+}
+
+}  // namespace b200

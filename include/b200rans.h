@@ -1,0 +1,165 @@
+/*
+ * b200rans.h -- C ABI of libb200rans.so: the htscodecs rANS Nx16 codec
+ * (order-0/order-1, 4 or 32 interleaved lanes, PACK / RLE / NOSZ / CAT / STRIPE)
+ * computed by hand-written sm_100a CUDA kernels.
+ *
+ * Part 1 re-declares, unchanged, the interface fqzcomp5 binds today
+ * (/root/reference/htscodecs/rANS_static4x16.h:41-64); stock fqzcomp5.o and
+ * tokenise_name3.o link against this library instead of rANS_static4x16pr.o +
+ * rANS_static32x16pr*.o (call sites: fqzcomp5.c:1422,1528,1550,1594,1639,1650,
+ * 1996,2008,2016,2433,2447,2490; tokenise_name3.c:1243,1261).
+ *
+ * Part 2 is the batched extension those callers need to keep a GPU busy
+ * (SURVEY H1/H9): one call carries many independent streams.
+ *
+ * There is no CPU implementation behind any entry point: without a usable
+ * CUDA device every call fails (NULL / negative return) and says so on stderr.
+ */
+#ifndef B200RANS_H
+#define B200RANS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------
+ * Part 1: drop-in symbols.  Semantics, flag byte, ownership (out == NULL =>
+ * the library malloc()s and the caller free()s) and error convention (NULL,
+ * encoder also sets *out_size = 0) are the reference's.
+ * ---------------------------------------------------------------------- */
+
+/* rANS_static4x16.h:41  (rANS_static4x16pr.c:93-106) */
+unsigned int rans_compress_bound_4x16(unsigned int size, int order);
+
+/* rANS_static4x16.h:42-44  (rANS_static4x16pr.c:1224-1600) */
+unsigned char *rans_compress_to_4x16(unsigned char *in, unsigned int in_size,
+                                     unsigned char *out, unsigned int *out_size,
+                                     int order);
+/* rANS_static4x16.h:45-46  (rANS_static4x16pr.c:1602-1605) */
+unsigned char *rans_compress_4x16(unsigned char *in, unsigned int in_size,
+                                  unsigned int *out_size, int order);
+/* rANS_static4x16.h:47-48  (rANS_static4x16pr.c:1607-1894) */
+unsigned char *rans_uncompress_to_4x16(unsigned char *in, unsigned int in_size,
+                                       unsigned char *out, unsigned int *out_size);
+/* rANS_static4x16.h:49-50  (rANS_static4x16pr.c:1896-1899) */
+unsigned char *rans_uncompress_4x16(unsigned char *in, unsigned int in_size,
+                                    unsigned int *out_size);
+/* rANS_static4x16.h:64  (rANS_static4x16pr.c:1212-1217): test hook selecting
+ * x86 ISA variants; accepted and ignored (there is one implementation). */
+void rans_set_cpu(int opts);
+
+/* "order" bits, rANS_static4x16.h:66-103 */
+#define RANS_ORDER_PACK       0x80
+#define RANS_ORDER_RLE        0x40
+#define RANS_ORDER_CAT        0x20
+#define RANS_ORDER_NOSZ       0x10
+#define RANS_ORDER_STRIPE     0x08
+#define RANS_ORDER_X32        0x04
+#define RANS_ORDER_STRIPE_NO0 (1 << 16)
+#define RANS_ORDER_SIMD_AUTO  (1 << 17)
+
+/* ------------------------------------------------------------------------
+ * Part 2: batched extension (not in the reference).
+ *
+ * A batch is n independent calls.  Each produces / consumes exactly the byte
+ * stream the corresponding single call would.  Calls that the reference would
+ * fail (NULL) are reported per stream, the rest of the batch still completes.
+ * All functions return 0 on success and a negative b200rans_status otherwise.
+ * ---------------------------------------------------------------------- */
+
+typedef enum {
+    B200RANS_OK = 0,
+    B200RANS_ENODEV = -1,   /* no CUDA device / driver; there is no CPU fallback */
+    B200RANS_ECUDA = -2,    /* a CUDA call failed; text on stderr */
+    B200RANS_ENOMEM = -3,
+    B200RANS_EINVAL = -4,
+    B200RANS_ESPACE = -5    /* output arena too small */
+} b200rans_status;
+
+/* Select the device used by the calling thread's context (default: device 0,
+ * or $B200RANS_DEVICE).  Each host thread owns a private context (stream,
+ * device + pinned scratch arenas), mirroring the per-thread scratch of
+ * htscodecs/utils.c:119-208, so hts_tpool workers may call concurrently. */
+int b200rans_set_device(int device);
+int b200rans_device_count(void);
+
+/* Pinned host memory helpers: buffers allocated here move at full PCIe rate. */
+void *b200rans_host_alloc(size_t bytes);
+void  b200rans_host_free(void *p);
+
+/* Host buffers in, one host arena out.
+ *   in[k], in_size[k], order[k]   as rans_compress_to_4x16
+ *   out, out_cap                  arena receiving the n streams back to back
+ *   out_off[k], out_size[k]       where stream k landed; out_size[k]==0 => that
+ *                                 call failed as the reference's would
+ * Capacity semantics of each call are those of out == NULL in the reference
+ * (the library provides rans_compress_bound_4x16 bytes). */
+int b200rans_compress_batch(int n,
+                            const unsigned char *const *in, const unsigned int *in_size,
+                            const int *order,
+                            unsigned char *out, size_t out_cap,
+                            size_t *out_off, unsigned int *out_size);
+
+/* Host buffers in, caller-placed outputs.
+ *   out[k]        destination of stream k (must not be NULL)
+ *   out_size[k]   in: capacity (exact length for NOSZ streams); out: bytes
+ *                 written, or 0 with status[k] != 0 on failure
+ *   status        optional per-stream result (0 = ok), may be NULL */
+int b200rans_uncompress_batch(int n,
+                              const unsigned char *const *in, const unsigned int *in_size,
+                              unsigned char *const *out, unsigned int *out_size,
+                              int *status);
+
+/* Peek the uncompressed length stored in a stream header (host memory).
+ * Returns -1 for NOSZ streams (length not stored) or malformed headers. */
+int64_t b200rans_uncompressed_size(const unsigned char *in, unsigned int in_size);
+
+/* ---- device-resident variants (inputs and outputs already in HBM) ---------
+ * Descriptor arrays are host memory; data pointers are device memory.  Work is
+ * enqueued on `stream` (a cudaStream_t; NULL = the thread context's stream)
+ * and is asynchronous: results are valid once the stream has been
+ * synchronised.  d_out_off / d_out_size / d_status are DEVICE arrays. */
+size_t b200rans_compress_batch_dev_bound(int n, const unsigned int *in_size, const int *order);
+
+int b200rans_compress_batch_dev(void *stream, int n,
+                                const unsigned char *d_in,
+                                const uint64_t *in_off, const unsigned int *in_size,
+                                const int *order,
+                                unsigned char *d_out, size_t out_cap,
+                                uint64_t *d_out_off, unsigned int *d_out_size);
+
+/* STRIPE streams are not accepted here (their sub-stream table must be read on
+ * the host); everything else is.  out_size[k] is the expected length. */
+int b200rans_uncompress_batch_dev(void *stream, int n,
+                                  const unsigned char *d_in,
+                                  const uint64_t *in_off, const unsigned int *in_size,
+                                  unsigned char *d_out,
+                                  const uint64_t *out_off, const unsigned int *out_size,
+                                  unsigned int *d_out_size, int *d_status);
+
+/* Multi-GPU block partitioning: streams are dealt round-robin by
+ * `block_of[k]` (or by k when NULL) over the first `ngpu` devices, one worker
+ * thread and stream per device, results gathered in call order.  No
+ * collective is involved. */
+int b200rans_compress_batch_multi(int ngpu, int n,
+                                  const unsigned char *const *in, const unsigned int *in_size,
+                                  const int *order, const int *block_of,
+                                  unsigned char *out, size_t out_cap,
+                                  size_t *out_off, unsigned int *out_size);
+int b200rans_uncompress_batch_multi(int ngpu, int n,
+                                    const unsigned char *const *in, const unsigned int *in_size,
+                                    const int *block_of,
+                                    unsigned char *const *out, unsigned int *out_size,
+                                    int *status);
+
+/* Number of kernel launches issued by this thread's context so far. */
+uint64_t b200rans_launch_count(void);
+const char *b200rans_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RANS_H */
