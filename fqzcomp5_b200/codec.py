@@ -30,6 +30,7 @@ EXPORTS = [
     "b200rans_compress_batch_dev_bound", "b200rans_compress_batch_dev",
     "b200rans_uncompress_batch_dev", "b200rans_compress_batch_multi",
     "b200rans_uncompress_batch_multi", "b200rans_launch_count", "b200rans_version",
+    "b200rans_set_profiling", "b200rans_last_kernel_ms",
 ]
 
 _lib = None
@@ -75,11 +76,14 @@ def lib():
         L.b200rans_compress_batch_dev_bound.argtypes = [i32, vp, vp]
         L.b200rans_compress_batch_dev_bound.restype = sz
         L.b200rans_compress_batch_dev.argtypes = [vp, i32, vp, vp, vp, vp, vp, sz, vp, vp]
-        L.b200rans_uncompress_batch_dev.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.b200rans_uncompress_batch_dev.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.b200rans_compress_batch_multi.argtypes = [i32, i32, vp, vp, vp, vp, vp, sz, vp, vp]
         L.b200rans_uncompress_batch_multi.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
         L.b200rans_launch_count.restype = C.c_uint64
         L.b200rans_version.restype = C.c_char_p
+        L.b200rans_set_profiling.argtypes = [i32]
+        L.b200rans_last_kernel_ms.argtypes = [i32]
+        L.b200rans_last_kernel_ms.restype = C.c_float
         _lib = L
     return _lib
 
@@ -242,12 +246,15 @@ def compress_batch_dev(stream, d_in_ptr, in_off, in_size, orders, d_out_ptr, out
 
 
 def uncompress_batch_dev(stream, d_in_ptr, in_off, in_size, d_out_ptr, out_off, out_size, d_out_size_ptr,
-                         d_status_ptr):
+                         d_status_ptr, flags=None):
     in_off = np.ascontiguousarray(in_off, np.uint64)
     in_size = np.ascontiguousarray(in_size, np.uint32)
     out_off = np.ascontiguousarray(out_off, np.uint64)
     out_size = np.ascontiguousarray(out_size, np.uint32)
+    if flags is not None:
+        flags = np.ascontiguousarray(flags, np.uint8)
     rc = lib().b200rans_uncompress_batch_dev(stream, len(in_size), d_in_ptr, _addr(in_off), _addr(in_size),
+                                             _addr(flags) if flags is not None else None,
                                              d_out_ptr, _addr(out_off), _addr(out_size), d_out_size_ptr,
                                              d_status_ptr)
     _check(rc, "b200rans_uncompress_batch_dev")
@@ -261,3 +268,12 @@ def compress_bound_batch(in_size, orders):
 
 def launch_count():
     return int(lib().b200rans_launch_count())
+
+
+def set_profiling(on):
+    _check(lib().b200rans_set_profiling(1 if on else 0), "b200rans_set_profiling")
+
+
+def last_kernel_ms(which):
+    """which: 0 = encode coder kernel, 1 = decode coder kernel of the last batch call."""
+    return float(lib().b200rans_last_kernel_ms(which))

@@ -72,6 +72,9 @@ struct Ctx {
     Stage stage[NSTAGE];        // pinned: job descriptors in flight
     int next_stage = 0;
     uint64_t launches = 0;
+    bool prof = false;          // bracket the coder kernels with timing events (bench.py roofline)
+    cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};   // enc start/stop, dec start/stop
+    bool pe_valid[2] = {false, false};
 
     int init(int device) {
         int n = 0;
@@ -87,6 +90,7 @@ struct Ctx {
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         hio.pinned = true;
         for (auto &s : stage) { s.h.pinned = true; CK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming)); }
+        for (auto &e : pe) CK(cudaEventCreate(&e));
         ok = true;
         return 0;
     }
@@ -106,6 +110,7 @@ struct Ctx {
         cudaStreamSynchronize(st);
         work.release(); io.release(); hio.release();
         for (auto &s : stage) { s.h.release(); if (s.ev) cudaEventDestroy(s.ev); }
+        for (auto &e : pe) if (e) cudaEventDestroy(e);
         cudaStreamDestroy(st);
     }
 };
@@ -240,7 +245,9 @@ int enc_core(Ctx &C, cudaStream_t st, int n, const uint8_t *d_in, const uint64_t
         C.launches++;
     }
     // ---- encode.  Streams that are purely order-0 go to the lean kernel.
+    if (C.prof) CK(cudaEventRecord(C.pe[0], st));
     CK(launch_enc(d_jobs, (uint32_t)njobs, any_o1, pool, st));
+    if (C.prof) { CK(cudaEventRecord(C.pe[1], st)); C.pe_valid[0] = true; }
     C.launches++;
     CK(cudaEventRecord(S->ev, st)); S->busy = true;
     // ---- STRIPE: choose the smallest method per sub-stream and assemble the parent
@@ -294,7 +301,9 @@ int dec_core(Ctx &C, cudaStream_t st, int n, const uint8_t *d_in, const uint64_t
     CK(cudaMemcpyAsync(d_jobs, S->h.p, (size_t)n * sizeof(DecJob), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(W + o_ctr, 0, 256, st));
     Pool pool{W + o_pool, pool_bytes, (unsigned long long *)(W + o_ctr)};
+    if (C.prof) CK(cudaEventRecord(C.pe[2], st));
     CK(launch_dec(d_jobs, (uint32_t)n, any_o1, pool, st));
+    if (C.prof) { CK(cudaEventRecord(C.pe[3], st)); C.pe_valid[1] = true; }
     C.launches++;
     CK(cudaEventRecord(S->ev, st)); S->busy = true;
     CK(launch_dec_results(d_jobs, (uint32_t)n, d_osz, d_status, st));
@@ -639,7 +648,8 @@ API int b200rans_compress_batch_dev(void *stream, int n, const unsigned char *d_
 }
 
 API int b200rans_uncompress_batch_dev(void *stream, int n, const unsigned char *d_in, const uint64_t *in_off,
-                                      const unsigned int *in_size, unsigned char *d_out,
+                                      const unsigned int *in_size, const unsigned char *flags,
+                                      unsigned char *d_out,
                                       const uint64_t *out_off, const unsigned int *out_size,
                                       unsigned int *d_out_size, int *d_status) {
     int err = 0;
@@ -648,10 +658,26 @@ API int b200rans_uncompress_batch_dev(void *stream, int n, const unsigned char *
     if (n < 0 || (n && (!d_in || !in_off || !in_size || !d_out || !out_off || !out_size || !d_out_size || !d_status)))
         return B200RANS_EINVAL;
     cudaStream_t st = stream ? (cudaStream_t)stream : C->st;
-    return dec_core(*C, st, n, d_in, in_off, in_size, nullptr, d_out, out_off, out_size, d_out_size, d_status);
+    return dec_core(*C, st, n, d_in, in_off, in_size, flags, d_out, out_off, out_size, d_out_size, d_status);
 }
 
 API uint64_t b200rans_launch_count(void) { return tls_ctx ? tls_ctx->launches : 0; }
+
+API int b200rans_set_profiling(int on) {
+    int e = 0;
+    Ctx *C = get_ctx(&e);
+    if (!C) return e;
+    C->prof = on != 0;
+    return 0;
+}
+API float b200rans_last_kernel_ms(int which) {
+    Ctx *C = tls_ctx;
+    if (!C || which < 0 || which > 1 || !C->pe_valid[which]) return -1.f;
+    float ms = -1.f;
+    if (cudaEventSynchronize(C->pe[2 * which + 1]) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, C->pe[2 * which], C->pe[2 * which + 1]) != cudaSuccess) return -1.f;
+    return ms;
+}
 API const char *b200rans_version(void) { return "b200rans 0.1 (sm_100a)"; }
 
 // ------------------------------------------------------------- multi-GPU

@@ -77,6 +77,18 @@ struct WordRing {
             fe += CHUNK;
         }
     }
+    // Fast-path maintenance, once per group of 4 steps (<= 256 bytes consumed):
+    // keep at least 768 bytes ahead; the chunk issued here is not read before
+    // the next call, which first waits for it.
+    __device__ __forceinline__ void advance4(int lane) {
+        cp_async_wait_all();
+        __syncwarp();
+        if (pos + (RING - CHUNK) >= fe) {
+            fill_chunk(fe, lane);
+            cp_async_commit();
+            fe += CHUNK;
+        }
+    }
     __device__ __forceinline__ uint32_t word_at(uint32_t p) const {
         // p may be odd when the stream sits at an odd address
         uint32_t o = p & (RING - 1);
@@ -85,6 +97,20 @@ struct WordRing {
     }
     __device__ __forceinline__ void drain() const { cp_async_wait_all(); __syncwarp(); }
 };
+
+__device__ __forceinline__ void stg_u8(uint8_t *p, uint32_t v) {
+    asm volatile("st.global.u8 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u8(const uint8_t *base, uint32_t off) {
+    uint32_t v, a = (uint32_t)__cvta_generic_to_shared(base) + off;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(const uint8_t *base, uint32_t off) {
+    uint32_t v, a = (uint32_t)__cvta_generic_to_shared(base) + off;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
 
 // One renormalisation round for the warp (rANS_word.h:414-476): lanes whose
 // state fell below 2^15 take the next words in lane order.  A lane refills only
@@ -137,6 +163,44 @@ struct __align__(16) DecO0Smem {
     uint32_t tab[256];     // freq | start<<16 (freq may be 4096: no 12-bit wrap)
     uint8_t  lut[4096];    // slot -> symbol
 };
+
+template <int N, bool ODD>
+__device__ __forceinline__ void dec_o0_fast(uint32_t &R_, uint32_t &i_, uint32_t full, uint8_t *out,
+                                            WordRing &w, const DecO0Smem &S, int lane, uint32_t lt) {
+    const bool act = (N == 32) ? true : lane < N;
+    uint32_t R = R_, i = i_, pos = w.pos;
+    uint8_t *o = out + i + (act ? lane : 0);
+    const uint8_t *ring = w.ring;
+    while (i + 4 * N <= full && pos + 4 * 64 <= w.end) {
+        w.pos = pos;
+        w.advance4(lane);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            uint32_t m = R & 4095;
+            uint32_t s = S.lut[m];
+            uint32_t fb = S.tab[s];
+            R = (fb & 0xffff) * (R >> 12) + m - (fb >> 16);
+            if (act) stg_u8(o + u * N, s);
+            bool need = act && R < RANS_L;
+            uint32_t mask = __ballot_sync(FULL, need);
+            if (need) {
+                uint32_t p = pos + 2 * __popc(mask & lt);
+                uint32_t wv = ODD ? (lds_u8(ring, p & (RING - 1)) | (lds_u8(ring, (p + 1) & (RING - 1)) << 8))
+                                  : lds_u16(ring, p & (RING - 1));
+                R = (R << 16) | wv;
+            }
+            pos += 2 * __popc(mask);
+        }
+        o += 4 * N;
+        i += 4 * N;
+    }
+    w.pos = pos;
+    // hand over to the careful loop with the ring in its per-step regime
+    cp_async_wait_all();
+    __syncwarp();
+    R_ = R;
+    i_ = i;
+}
 
 // Returns 0 on success.  `out` receives out_sz bytes.
 template <int N>
@@ -209,7 +273,12 @@ __device__ int dec_o0(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
     w.init(in, hdr + 4 * N, in_size, S.ring, lane);     // ends with __syncwarp: lut visible
     const uint32_t lt = lanemask_lt();
     const uint32_t full = out_sz - out_sz % N;
-    for (uint32_t i = 0; i < full; i += N) {
+    uint32_t i = 0;
+    // Hot loop: groups of 4 steps while 4*64 bytes of words are certainly left,
+    // so no end-of-stream bookkeeping and one ring check per group.
+    if (w.pos & 1) dec_o0_fast<N, true>(R, i, full, out, w, S, lane, lt);
+    else dec_o0_fast<N, false>(R, i, full, out, w, S, lane, lt);
+    for (; i < full; i += N) {
         uint32_t m = R & 4095;
         uint32_t s = S.lut[m];
         uint32_t fb = S.tab[s];
@@ -333,8 +402,8 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
     T.fs = (uint32_t *)tb;
     T.blut = tb + nsym * nsym * 4;
     T.sym = T.blut + nsym * 64;
-    for (int j = lane; j < 256; j += 32)
-        if (S.rank[j] != 0xff) T.sym[S.rank[j]] = (uint8_t)j;
+    for (int j = lane; j < 256; j += 32)          // presence from F0: rank 255 is a valid rank
+        if (S.F0[j]) T.sym[S.rank[j]] = (uint8_t)j;
 
     // --- rows, in alphabet order (rANS_static16_int.h:488-530); serial varint parse
     int err = 0;
@@ -404,8 +473,8 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
     const uint32_t lt = lanemask_lt();
     const uint32_t seg = out_sz / N, mask = tot - 1;
     uint8_t *o = out + (size_t)lane * seg;
-    uint32_t ctx = S.rank[0];               // every lane starts in context 0 (symbol 0 is always listed)
-    if (ctx == 0xff) return 1;
+    uint32_t ctx = S.rank[0];               // every lane starts in context 0
+    if (!S.F0[0]) return 1;                 // symbol 0 is always listed by the encoder
     const uint32_t *fs = T.fs;
     const uint8_t *blut = T.blut, *symtab = T.sym;
     const uint32_t ns = nsym;

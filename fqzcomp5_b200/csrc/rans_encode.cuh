@@ -296,6 +296,8 @@ struct __align__(16) EncO1Smem {
     uint8_t  sym[256];      // rank -> symbol
     uint16_t S[256];        // per-row stored total (rank space)
     uint32_t rowlen[256];   // serialised row lengths / offsets (rank space)
+    uint32_t pres[8];       // alphabet membership bitmap (symbol space)
+    uint32_t pad_[4];
 };                          // followed by dynamic storage: nsym*nsym pair counts when they fit
 
 // serialise one row against the alphabet (rANS_static16_int.h:278-306): every
@@ -336,12 +338,18 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
         uint32_t incl = warp_incl_scan(loc, lane);
         nsym = __shfl_sync(FULL, incl, 31);
         uint32_t r = incl - loc;
+        uint32_t bits = 0;
         for (int t = 0; t < 8; t++) {
             int j = lane * 8 + t;
             bool p = S.T[j] || j == 0;
             S.rank[j] = p ? (uint8_t)r : 0xff;
-            if (p) S.sym[r++] = (uint8_t)j;
+            if (p) { S.sym[r++] = (uint8_t)j; bits |= 1u << t; }
         }
+        // lane l holds symbols 8l..8l+7: four lanes make one 32-bit word
+        uint32_t w = bits << (8 * (lane & 3));
+        w |= __shfl_xor_sync(FULL, w, 1);
+        w |= __shfl_xor_sync(FULL, w, 2);
+        if ((lane & 3) == 0) S.pres[lane >> 2] = w;
     }
     __syncwarp();
 
@@ -436,7 +444,9 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
         *cp++ = 0;
         // put_alphabet over symbol space: mark = row total != 0 (or symbol 0)
         int j = 0;
-        auto present = [&](int s) { uint8_t r = S.rank[s]; return r != 0xff && (S.T[r] != 0 || s == 0); };
+        // listed = occurs in the data (or is 0); every such symbol has a non-zero row total.
+        // (rank 255 is a valid rank, so presence is kept separately from rank[])
+        auto present = [&](int s) { return (S.pres[s >> 5] >> (s & 31)) & 1; };
         while (j < 256) {
             if (!present(j)) { j++; continue; }
             *cp++ = (uint8_t)j;

@@ -132,10 +132,14 @@ int b200rans_compress_batch_dev(void *stream, int n,
                                 uint64_t *d_out_off, unsigned int *d_out_size);
 
 /* STRIPE streams are not accepted here (their sub-stream table must be read on
- * the host); everything else is.  out_size[k] is the expected length. */
+ * the host); everything else is.  out_size[k] is the expected length.
+ * flags: optional HOST array holding the first byte of each stream (the format's
+ * flag byte); it lets the library pick the lean order-0 kernel and skip
+ * transform scratch.  NULL = unknown, the general kernel is used. */
 int b200rans_uncompress_batch_dev(void *stream, int n,
                                   const unsigned char *d_in,
                                   const uint64_t *in_off, const unsigned int *in_size,
+                                  const unsigned char *flags,
                                   unsigned char *d_out,
                                   const uint64_t *out_off, const unsigned int *out_size,
                                   unsigned int *d_out_size, int *d_status);
@@ -157,6 +161,14 @@ int b200rans_uncompress_batch_multi(int ngpu, int n,
 
 /* Number of kernel launches issued by this thread's context so far. */
 uint64_t b200rans_launch_count(void);
+
+/* Measurement hooks: with profiling on, the encode / decode coder kernel of each
+ * batch call is bracketed by CUDA events on the launching stream;
+ * b200rans_last_kernel_ms(0|1) returns the duration of the last encode (0) or
+ * decode (1) coder kernel in milliseconds (synchronises on its stop event),
+ * or a negative value if none was recorded. */
+int   b200rans_set_profiling(int on);
+float b200rans_last_kernel_ms(int which);
 const char *b200rans_version(void);
 
 #ifdef __cplusplus

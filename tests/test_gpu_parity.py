@@ -1,0 +1,202 @@
+"""Parity of the CUDA path with the CPU checkers, through the C ABI.
+
+Bit-exact both ways: the GPU's compressed bytes equal the CPU
+codec's, and the GPU decodes CPU-encoded streams back to the input.  The
+checker is the unmodified reference build when oracle/_ref is present, else
+the oracle; the committed golden vectors pin both.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+import corpus
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_decode(g, comp, n):
+    return g.rans_uncompress_to_4x16(comp, n) if comp[0] & 0x10 else g.rans_uncompress_4x16(comp)
+
+
+def _cpu_decode(c, comp, n):
+    return c.uncompress(comp, n) if comp[0] & 0x10 else c.uncompress(comp)
+
+
+@pytest.mark.parametrize("gen", corpus.GENS)
+def test_single_call_parity(gpu_codec, checker, gen):
+    """Every order flag x edge sizes, one rans_compress_to_4x16 call each."""
+    bad = []
+    for g, n, seed, order in corpus.parity_cases(corpus.SIZES_EDGE + [50000], gens=[gen]):
+        data = corpus.make(g, n, seed)
+        want = checker.compress(data, order)
+        got = gpu_codec.rans_compress_to_4x16(data, order)
+        if want != got:
+            bad.append(("enc", g, n, hex(order), want and len(want), got and len(got)))
+            continue
+        if want is not None and _gpu_decode(gpu_codec, want, n) != data:
+            bad.append(("dec", g, n, hex(order)))
+    assert not bad, bad[:10]
+
+
+def test_golden_vectors(gpu_codec, golden):
+    """The reference's own outputs, committed under tests/golden/."""
+    bad = []
+    for v in golden["vectors"]:
+        data = corpus.make(v["gen"], v["n"], v["seed"])
+        out = gpu_codec.rans_compress_to_4x16(data, v["order"])
+        if v.get("null"):
+            ok = out is None
+        else:
+            ok = (out is not None and len(out) == v["len"]
+                  and hashlib.sha256(out).hexdigest() == v["sha256"]
+                  and _gpu_decode(gpu_codec, out, len(data)) == data)
+        if not ok:
+            bad.append((v["gen"], v["n"], hex(v["order"])))
+    assert not bad, bad[:10]
+
+
+def test_malloc_forms(gpu_codec, checker):
+    data = corpus.make("ont_qual", 70000, 4)
+    for order in (0, 5, 0xc5, (4 << 8) | 9):
+        want = checker.compress_malloc(data, order)
+        assert gpu_codec.rans_compress_4x16(data, order) == want
+        assert gpu_codec.rans_uncompress_4x16(want) == data
+
+
+def test_capacity_semantics(gpu_codec, checker):
+    """out != NULL: *out_size is the capacity; too small => NULL, like the reference."""
+    data = corpus.make("illumina_qual", 20000, 2)
+    for order in (0, 5, 0x45):
+        full = checker.bound(len(data), order)
+        for cap in (1, 10, 1000, full - 100, full):
+            assert gpu_codec.rans_compress_to_4x16(data, order, cap=cap) == checker.compress(data, order, cap=cap), \
+                (hex(order), cap)
+
+
+def test_mid_sizes_and_self_compressed_tables(gpu_codec, checker):
+    cases = [("wide", 300000, 5), ("wide", 300000, 1), ("text", 300000, 5), ("text", 49999, 1),
+             ("illumina_qual", 500001, 5), ("illumina_qual", 500001, 4), ("ont_qual", 1 << 20, 5),
+             ("illumina_seq", 1 << 20, 0xc5), ("binned_qual", 1 << 20, 0x84), ("runs", 300000, 0x45),
+             ("illumina_qual", 600000, (150 << 8) | 9), ("stripe32", 400000, (4 << 8) | 9),
+             ("nsym17", 300000, 0xc5), ("nsym16", 300000, 0xc1)]
+    for g, n, order in cases:
+        data = corpus.make(g, n, 1)
+        want = checker.compress(data, order)
+        assert gpu_codec.rans_compress_to_4x16(data, order) == want, (g, n, hex(order))
+        assert _gpu_decode(gpu_codec, want, n) == data, (g, n, hex(order))
+
+
+def test_corrupt_streams_fail_cleanly(gpu_codec, checker):
+    """Truncated / damaged input: NULL or garbage of the right length, never a fault."""
+    data = corpus.make("illumina_qual", 6000, 2)
+    for order in (0, 1, 4, 5, 0xc5, 0x408):
+        c = checker.compress(data, order)
+        assert gpu_codec.rans_uncompress_4x16(c[:10]) is None or order == 0x408
+        assert gpu_codec.rans_uncompress_4x16(b"") is None
+        rng = np.random.default_rng(5)
+        for _ in range(8):
+            d = bytearray(c)
+            pos = int(rng.integers(1, len(d)))
+            d[pos] ^= 1 << int(rng.integers(0, 8))
+            r = gpu_codec.rans_uncompress_4x16(bytes(d))
+            assert r is None or isinstance(r, bytes)
+        # the library is still healthy afterwards
+        assert gpu_codec.rans_uncompress_4x16(c) == data
+
+
+def test_batch_host_api(gpu_codec, checker):
+    """Many streams per call, mixed orders and sizes, one arena out."""
+    parts, orders = [], []
+    for g, n, o in [("illumina_qual", 262144, 4), ("illumina_qual", 262144, 5), ("ont_qual", 100000, 5),
+                    ("illumina_seq", 200000, 0xc5), ("random", 5000, 4), ("const", 70000, 0x84),
+                    ("text", 30000, 1), ("illumina_qual", 0, 0), ("runs", 90000, 0x44),
+                    ("illumina_qual", 60000, (150 << 8) | 9), ("nsym4", 777, 0xc1)] * 3:
+        parts.append(np.frombuffer(corpus.make(g, n, 3), np.uint8))
+        orders.append(o)
+    sizes = [p.size for p in parts]
+    offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64)
+    buf = np.concatenate(parts) if sum(sizes) else np.zeros(0, np.uint8)
+    out, ooff, osz = gpu_codec.compress_batch(buf, offs, sizes, orders)
+    for k, (p, o) in enumerate(zip(parts, orders)):
+        want = checker.compress(p.tobytes(), o)
+        got = out[int(ooff[k]):int(ooff[k]) + int(osz[k])].tobytes()
+        assert got == want, (k, hex(o), len(got), len(want))
+    back = np.empty(buf.size + 16, np.uint8)
+    rsz, status = gpu_codec.uncompress_batch(out, ooff, osz, back, offs, sizes)
+    assert (status == 0).all() and (rsz == np.array(sizes, np.uint32)).all()
+    assert np.array_equal(back[:buf.size], buf)
+
+
+def test_batch_device_api_roundtrip(gpu_codec, checker):
+    """Device-resident path (what bench.py's `value` times): parity per slice."""
+    import torch
+    data = np.frombuffer(corpus.make("illumina_qual", 4 << 20, 2), np.uint8)
+    for order in (4, 5):
+        S = 262144
+        sl = [(o, min(S, data.size - o)) for o in range(0, data.size, S)]
+        in_off = np.array([o for o, _ in sl], np.uint64)
+        in_size = np.array([s for _, s in sl], np.uint32)
+        orders = np.full(len(sl), order, np.int32)
+        d_in = torch.from_numpy(data.copy()).cuda()
+        cap = gpu_codec.compress_bound_batch(in_size, orders)
+        d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+        d_off = torch.zeros(len(sl), dtype=torch.int64, device="cuda")
+        d_sz = torch.zeros(len(sl), dtype=torch.int32, device="cuda")
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            gpu_codec.compress_batch_dev(st.cuda_stream, d_in.data_ptr(), in_off, in_size, orders,
+                                         d_out.data_ptr(), cap, d_off.data_ptr(), d_sz.data_ptr())
+        st.synchronize()
+        off, sz, comp = d_off.cpu().numpy(), d_sz.cpu().numpy(), d_out.cpu().numpy()
+        for k, (o, s) in enumerate(sl):
+            assert comp[off[k]:off[k] + sz[k]].tobytes() == checker.compress(data[o:o + s].tobytes(), order), k
+        d_back = torch.zeros(data.size, dtype=torch.uint8, device="cuda")
+        d_osz = torch.zeros(len(sl), dtype=torch.int32, device="cuda")
+        d_st = torch.ones(len(sl), dtype=torch.int32, device="cuda")
+        flags = comp[off]
+        with torch.cuda.stream(st):
+            gpu_codec.uncompress_batch_dev(st.cuda_stream, d_out.data_ptr(), off.astype(np.uint64),
+                                           sz.astype(np.uint32), d_back.data_ptr(), in_off, in_size,
+                                           d_osz.data_ptr(), d_st.data_ptr(), flags=flags)
+        st.synchronize()
+        assert int(d_st.abs().sum()) == 0
+        assert torch.equal(d_back, d_in)
+
+
+def test_large_block_roundtrip_property(gpu_codec):
+    """Size-independent property at a block the oracle would take minutes on:
+    encode -> decode is the identity, and the total compressed size matches the
+    sum over a sample of slices checked individually elsewhere."""
+    n = 256 << 20
+    from fqzcomp5_b200 import synth
+    buf = synth.illumina_qual(n)
+    S = 262144
+    sl = synth.slices(buf, S)
+    offs = [o for o, _ in sl]
+    sizes = [s for _, s in sl]
+    for order in (4, 5):
+        out, ooff, osz = gpu_codec.compress_batch(buf, offs, sizes, [order] * len(sl))
+        assert (osz > 0).all()
+        back = np.empty(n, np.uint8)
+        rsz, status = gpu_codec.uncompress_batch(out, ooff, osz, back, offs, sizes)
+        assert (status == 0).all()
+        assert hashlib.sha256(back).digest() == hashlib.sha256(buf).digest()
+        assert 0.05 < float(osz.sum()) / n < 0.8
+
+
+def test_concurrent_callers(gpu_codec, checker):
+    """hts_tpool calls the codec from several worker threads at once (SURVEY 8b threading)."""
+    import threading
+    data = [corpus.make("illumina_qual", 50000 + 1000 * i, i) for i in range(8)]
+    want = [checker.compress(d, 5) for d in data]
+    res = [None] * 8
+
+    def work(i):
+        for _ in range(3):
+            res[i] = gpu_codec.rans_compress_to_4x16(data[i], 5)
+            assert gpu_codec.rans_uncompress_4x16(res[i]) == data[i]
+    th = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert res == want

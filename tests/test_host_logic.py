@@ -1,0 +1,70 @@
+"""Host-side logic that needs no GPU: generators, slicing, and the N>1 block
+partition exercised with two real processes over gloo."""
+import os
+
+import numpy as np
+import pytest
+
+from fqzcomp5_b200 import partition, synth
+
+
+def test_generators_are_deterministic_and_shaped():
+    a, b = synth.illumina_qual(100000), synth.illumina_qual(100000)
+    assert np.array_equal(a, b) and a.min() >= 2 and a.max() <= 40
+    s = synth.illumina_seq(30000)
+    assert set(np.unique(s).tolist()) <= set(b"ACGT")
+    o = synth.ont_qual(100000)
+    assert o.min() >= 1 and o.max() <= 40 and o.size == 100000
+    bq = synth.binned_qual(5000)
+    assert set(np.unique(bq).tolist()) <= {2, 12, 23, 37}
+    big = synth.illumina_qual((1 << 25) + 12345)          # crosses a chunk boundary
+    assert big.size == (1 << 25) + 12345
+
+
+def test_slices_cover_the_buffer():
+    buf = np.zeros(1000003, np.uint8)
+    sl = synth.slices(buf, 262144)
+    assert sl[0] == (0, 262144) and sum(s for _, s in sl) == buf.size
+    assert all(o2 == o1 + s1 for (o1, s1), (o2, _) in zip(sl, sl[1:]))
+
+
+def test_partition_round_robin():
+    for world in (1, 2, 4, 8):
+        owned = [partition.blocks_of_rank(64, r, world) for r in range(world)]
+        assert sorted(sum(owned, [])) == list(range(64))
+        per_rank = [[("blk", b) for b in owned[r]] for r in range(world)]
+        assert partition.gather_in_order(per_rank, 64, world) == [("blk", b) for b in range(64)]
+
+
+def _worker(rank, world, port, nblocks, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = partition.blocks_of_rank(nblocks, rank, world)
+    # stand-in for the per-block compressed size each rank would produce
+    sizes = torch.tensor([1000 + 7 * b for b in mine] + [0] * (nblocks - len(mine)), dtype=torch.int64)
+    gathered = [torch.zeros(nblocks, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(gathered, sizes)                       # index/size exchange only: no data-path collective
+    t = torch.tensor([float(rank + 1)])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)               # the max-over-ranks timing reduction bench.py uses
+    if rank == 0:
+        per_rank = [gathered[r][:len(partition.blocks_of_rank(nblocks, r, world))].tolist() for r in range(world)]
+        q.put((partition.gather_in_order(per_rank, nblocks, world), float(t)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_partition_over_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world, nblocks, port = 2, 7, 29500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_worker, args=(r, world, port, nblocks, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res, tmax = q.get(timeout=120)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [1000 + 7 * b for b in range(nblocks)] and tmax == 2.0
