@@ -60,17 +60,50 @@ struct Layout {
 };
 
 constexpr int NSTAGE = 4;
+constexpr int NPIPE = 3;                  // chunks in flight in the host-buffer API
+constexpr size_t CHUNK_BYTES = 48u << 20; // uncompressed bytes per pipeline chunk
 struct Stage { Arena h; cudaEvent_t ev = nullptr; bool busy = false; };
 
-struct Ctx {
-    int dev = 0;
-    bool ok = false;
+// One pipeline lane: a stream plus the arenas a chunk of work needs.  Chunks of a
+// large host-buffer batch rotate over NPIPE lanes so that the H2D copy of one
+// chunk, the kernels of the previous and the D2H copy of the one before overlap.
+struct Lane {
     cudaStream_t st = nullptr;
     Arena work;                 // device: jobs, slots, scratch, pool
     Arena io;                   // device: staged inputs / outputs of the host-buffer API
     Arena hio;                  // pinned: results read back
     Stage stage[NSTAGE];        // pinned: job descriptors in flight
     int next_stage = 0;
+
+    int init() {
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        hio.pinned = true;
+        for (auto &s : stage) { s.h.pinned = true; CK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming)); }
+        return 0;
+    }
+    // pinned staging block for descriptors; waits until its previous use has been consumed
+    int get_stage(size_t bytes, Stage **out) {
+        Stage &s = stage[next_stage];
+        next_stage = (next_stage + 1) % NSTAGE;
+        if (s.busy) { CK(cudaEventSynchronize(s.ev)); s.busy = false; }
+        int r = s.h.ensure(bytes);
+        if (r) return r;
+        *out = &s;
+        return 0;
+    }
+    void destroy() {
+        if (st) cudaStreamSynchronize(st);
+        work.release(); io.release(); hio.release();
+        for (auto &s : stage) { s.h.release(); if (s.ev) cudaEventDestroy(s.ev); }
+        if (st) cudaStreamDestroy(st);
+        st = nullptr;
+    }
+};
+
+struct Ctx {
+    int dev = 0;
+    bool ok = false;
+    Lane lane[NPIPE];
     uint64_t launches = 0;
     bool prof = false;          // bracket the coder kernels with timing events (bench.py roofline)
     cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};   // enc start/stop, dec start/stop
@@ -87,31 +120,16 @@ struct Ctx {
         if (device < 0 || device >= n) return B200RANS_EINVAL;
         dev = device;
         CK(cudaSetDevice(dev));
-        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        hio.pinned = true;
-        for (auto &s : stage) { s.h.pinned = true; CK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming)); }
-        for (auto &e : pe) CK(cudaEventCreate(&e));
+        for (auto &l : lane) { int r = l.init(); if (r) return r; }
+        for (auto &e2 : pe) CK(cudaEventCreate(&e2));
         ok = true;
-        return 0;
-    }
-    // pinned staging block for descriptors; waits until its previous use has been consumed
-    int get_stage(size_t bytes, Stage **out) {
-        Stage &s = stage[next_stage];
-        next_stage = (next_stage + 1) % NSTAGE;
-        if (s.busy) { CK(cudaEventSynchronize(s.ev)); s.busy = false; }
-        int r = s.h.ensure(bytes);
-        if (r) return r;
-        *out = &s;
         return 0;
     }
     ~Ctx() {
         if (!ok) return;
         cudaSetDevice(dev);
-        cudaStreamSynchronize(st);
-        work.release(); io.release(); hio.release();
-        for (auto &s : stage) { s.h.release(); if (s.ev) cudaEventDestroy(s.ev); }
+        for (auto &l : lane) l.destroy();
         for (auto &e : pe) if (e) cudaEventDestroy(e);
-        cudaStreamDestroy(st);
     }
 };
 
@@ -152,7 +170,7 @@ inline int effective_order(uint32_t in_size, int order) {
 // Build and run the encode of a batch whose inputs are already on the device.
 // On return (asynchronously on st): d_out holds the packed streams, d_out_off /
 // d_out_size / d_total describe them.
-int enc_core(Ctx &C, cudaStream_t st, int n, const uint8_t *d_in, const uint64_t *in_off,
+int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, const uint64_t *in_off,
              const uint32_t *in_size, const int *order, const uint32_t *caps,
              uint8_t *d_out, size_t out_cap, uint64_t *d_out_off, uint32_t *d_out_size,
              uint64_t *d_total) {
@@ -176,7 +194,7 @@ int enc_core(Ctx &C, cudaStream_t st, int n, const uint8_t *d_in, const uint64_t
     std::vector<EncJob> jobs(njobs);
     size_t o_jobs = L.take(njobs * sizeof(EncJob));
     size_t o_ctr = L.take(256);
-    bool any_o1 = false;
+    uint32_t n_o0 = 0, n_o1 = 0;
     size_t pool_bytes = 0;
     // ---- pass 2: place slots / work buffers
     auto place = [&](EncJob &J, const uint8_t *in, uint32_t isz, int ord, uint32_t cap, uint32_t item) {
@@ -187,10 +205,11 @@ int enc_core(Ctx &C, cudaStream_t st, int n, const uint8_t *d_in, const uint64_t
         J.slot = (uint8_t *)L.take(slot_cap, 256);
         if (ord & (X_PACK | X_RLE)) J.work = (uint8_t *)L.take((size_t)isz * 4 + isz / 4 + 8192, 256);
         if ((ord & 1) && isz >= 8) {
-            any_o1 = true;
+            J.route = 1;                     // the order-1 kernel (larger shared memory per warp)
+            n_o1++;
             // symbol table (16 B/pair), pair counts (4 B/pair), coded table scratch
             pool_bytes += 256 * 256 * 20 + 300 * 1024;
-        }
+        } else n_o0++;
     };
     size_t si = 0;
     for (int k = 0; k < n; k++) {
@@ -200,6 +219,8 @@ int enc_core(Ctx &C, cudaStream_t st, int n, const uint8_t *d_in, const uint64_t
             StripePlan &sp = stripes[si++];
             sp.o_transposed = L.take(in_size[k], 256);
             place(jobs[j], d_in + in_off[k], in_size[k], order[k], cap, (uint32_t)k);
+            if (jobs[j].route) { n_o1--; pool_bytes -= 256 * 256 * 20 + 300 * 1024; } else n_o0--;
+            jobs[j].route = 2;               // assembled by stripe_select, not coded
             jobs[j].stripe_n = sp.N;
             for (uint32_t s = 0; s < sp.nsub; s++) {
                 const StripeSub &ss = sp.sub[s];
@@ -217,9 +238,9 @@ int enc_core(Ctx &C, cudaStream_t st, int n, const uint8_t *d_in, const uint64_t
     pool_bytes = std::max<size_t>(pool_bytes, (size_t)8 << 20);
     size_t o_pool = L.take(pool_bytes, 256);
     size_t o_soff = L.take(njobs * 8), o_ssz = L.take(njobs * 4);
-    int r = C.work.ensure(L.off + 256);
+    int r = Ln.work.ensure(L.off + 256);
     if (r) return r;
-    uint8_t *W = C.work.p;
+    uint8_t *W = Ln.work.p;
     // relocate offsets into pointers
     for (auto &J : jobs) {
         J.slot = W + (size_t)J.slot;
@@ -232,7 +253,7 @@ int enc_core(Ctx &C, cudaStream_t st, int n, const uint8_t *d_in, const uint64_t
         }
     Stage *S;
     size_t stage_bytes = njobs * sizeof(EncJob) + 256;
-    if ((r = C.get_stage(stage_bytes, &S))) return r;
+    if ((r = Ln.get_stage(stage_bytes, &S))) return r;
     memcpy(S->h.p, jobs.data(), njobs * sizeof(EncJob));
     EncJob *d_jobs = (EncJob *)(W + o_jobs);
     CK(cudaMemcpyAsync(d_jobs, S->h.p, njobs * sizeof(EncJob), cudaMemcpyHostToDevice, st));
@@ -244,18 +265,16 @@ int enc_core(Ctx &C, cudaStream_t st, int n, const uint8_t *d_in, const uint64_t
         CK(launch_stripe_split(d_in + in_off[sp.item], W + sp.o_transposed, sp.in_size, sp.N, st));
         C.launches++;
     }
-    // ---- encode.  Streams that are purely order-0 go to the lean kernel.
+    // ---- encode: order-0 streams on the lean kernel, the rest on the order-1 kernel
     if (C.prof) CK(cudaEventRecord(C.pe[0], st));
-    CK(launch_enc(d_jobs, (uint32_t)njobs, any_o1, pool, st));
+    if (n_o0) { CK(launch_enc(d_jobs, (uint32_t)njobs, false, pool, st)); C.launches++; }
+    if (n_o1) { CK(launch_enc(d_jobs, (uint32_t)njobs, true, pool, st)); C.launches++; }
     if (C.prof) { CK(cudaEventRecord(C.pe[1], st)); C.pe_valid[0] = true; }
-    C.launches++;
     CK(cudaEventRecord(S->ev, st)); S->busy = true;
     // ---- STRIPE: choose the smallest method per sub-stream and assemble the parent
-    if (!stripes.empty()) {
-        for (auto &sp : stripes) {
-            CK(launch_stripe_select(d_jobs, sp.first_job, sp.N, sp.nmeth, st));
-            C.launches++;
-        }
+    for (auto &sp : stripes) {
+        CK(launch_stripe_select(d_jobs, sp.first_job, sp.N, sp.nmeth, st));
+        C.launches++;
     }
     // ---- pack the finished streams of the caller's items (sub-streams carry no item)
     uint64_t *d_off = d_out_off ? d_out_off : (uint64_t *)(W + o_soff);
@@ -266,7 +285,7 @@ int enc_core(Ctx &C, cudaStream_t st, int n, const uint8_t *d_in, const uint64_t
 }
 
 // Decode core: inputs and outputs on the device.  d_status/d_osz are device arrays.
-int dec_core(Ctx &C, cudaStream_t st, int n, const uint8_t *d_in, const uint64_t *in_off,
+int dec_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, const uint64_t *in_off,
              const uint32_t *in_size, const uint8_t *flags /* first byte of each stream, or null */,
              uint8_t *d_out, const uint64_t *out_off, const uint32_t *out_cap,
              uint32_t *d_osz, int *d_status) {
@@ -275,7 +294,7 @@ int dec_core(Ctx &C, cudaStream_t st, int n, const uint8_t *d_in, const uint64_t
     size_t o_jobs = L.take((size_t)n * sizeof(DecJob));
     size_t o_ctr = L.take(256);
     std::vector<DecJob> jobs(n);
-    bool any_o1 = false;
+    uint32_t n_o0 = 0, n_o1 = 0;
     size_t pool_bytes = 0;
     for (int k = 0; k < n; k++) {
         DecJob &J = jobs[k];
@@ -284,42 +303,51 @@ int dec_core(Ctx &C, cudaStream_t st, int n, const uint8_t *d_in, const uint64_t
         J.out = d_out + out_off[k]; J.out_cap = out_cap[k];
         int f = flags ? flags[k] : 0xff;                 // unknown: assume everything
         if (f & (X_PACK | X_RLE)) J.tmp = (uint8_t *)L.take((size_t)out_cap[k] * 2 + 4096, 256);
-        if (f & 1) { any_o1 = true; pool_bytes += 257 * 257 * 3 + 256 * 256 * 4 + 64 * 1024; }
+        if ((f & 1) && !(f & X_CAT)) {
+            J.route = 1; n_o1++;
+            pool_bytes += 257 * 257 * 3 + 256 * 256 * 4 + 64 * 1024;
+        } else n_o0++;
     }
     pool_bytes = std::min<size_t>(pool_bytes, (size_t)2 << 30);
     pool_bytes = std::max<size_t>(pool_bytes, (size_t)8 << 20);
     size_t o_pool = L.take(pool_bytes, 256);
-    size_t o_res = L.take((size_t)n * 8);
-    int r = C.work.ensure(L.off + 256);
+    int r = Ln.work.ensure(L.off + 256);
     if (r) return r;
-    uint8_t *W = C.work.p;
+    uint8_t *W = Ln.work.p;
     for (auto &J : jobs) if (J.tmp) J.tmp = W + (size_t)J.tmp;
     Stage *S;
-    if ((r = C.get_stage((size_t)n * sizeof(DecJob), &S))) return r;
+    if ((r = Ln.get_stage((size_t)n * sizeof(DecJob), &S))) return r;
     memcpy(S->h.p, jobs.data(), (size_t)n * sizeof(DecJob));
     DecJob *d_jobs = (DecJob *)(W + o_jobs);
     CK(cudaMemcpyAsync(d_jobs, S->h.p, (size_t)n * sizeof(DecJob), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(W + o_ctr, 0, 256, st));
     Pool pool{W + o_pool, pool_bytes, (unsigned long long *)(W + o_ctr)};
     if (C.prof) CK(cudaEventRecord(C.pe[2], st));
-    CK(launch_dec(d_jobs, (uint32_t)n, any_o1, pool, st));
+    if (n_o0) { CK(launch_dec(d_jobs, (uint32_t)n, false, pool, st)); C.launches++; }
+    if (n_o1) { CK(launch_dec(d_jobs, (uint32_t)n, true, pool, st)); C.launches++; }
     if (C.prof) { CK(cudaEventRecord(C.pe[3], st)); C.pe_valid[1] = true; }
-    C.launches++;
     CK(cudaEventRecord(S->ev, st)); S->busy = true;
     CK(launch_dec_results(d_jobs, (uint32_t)n, d_osz, d_status, st));
     C.launches++;
-    (void)o_res;
     return 0;
 }
 
-// copy a list of host ranges to/from consecutive device offsets, merging
-// neighbours that are contiguous on both sides into one cudaMemcpyAsync
+// copy a list of host ranges to/from device offsets, merging neighbours that are
+// laid out identically on both sides into one cudaMemcpyAsync.  Host-to-device
+// copies may also bridge gaps of up to 64 bytes (alignment padding inside one
+// host arena; fewer than a page, so the bytes between two valid ranges are
+// readable); device-to-host copies only merge exact neighbours.
 struct Span { const uint8_t *h; size_t d; size_t len; };
 int copy_spans(std::vector<Span> &sp, uint8_t *dbase, bool to_device, cudaStream_t st) {
+    const size_t max_gap = to_device ? 64 : 0;
     size_t i = 0;
     while (i < sp.size()) {
         size_t j = i + 1, len = sp[i].len;
-        while (j < sp.size() && sp[j].h == sp[i].h + len && sp[j].d == sp[i].d + len) { len += sp[j].len; j++; }
+        while (j < sp.size() && sp[j].h >= sp[i].h + len && (size_t)(sp[j].h - (sp[i].h + len)) <= max_gap &&
+               sp[j].d - sp[i].d == (size_t)(sp[j].h - sp[i].h)) {
+            len = (size_t)(sp[j].h - sp[i].h) + sp[j].len;
+            j++;
+        }
         if (len) {
             if (to_device) CK(cudaMemcpyAsync(dbase + sp[i].d, sp[i].h, len, cudaMemcpyHostToDevice, st));
             else CK(cudaMemcpyAsync((void *)sp[i].h, dbase + sp[i].d, len, cudaMemcpyDeviceToHost, st));
@@ -329,20 +357,29 @@ int copy_spans(std::vector<Span> &sp, uint8_t *dbase, bool to_device, cudaStream
     return 0;
 }
 
-// device placement of host buffers: keep host contiguity where it exists so that
-// copies merge; otherwise align each stream to 16 bytes
-void place_spans(int n, const unsigned char *const *ptr, const uint32_t *len, std::vector<uint64_t> &off,
+// device placement of host buffers [k0,k1): mirror the host layout where buffers
+// follow each other closely so that copies merge; otherwise start a new
+// 256-byte aligned run with the same alignment mod 16 as on the host
+void place_spans(int k0, int k1, const unsigned char *const *ptr, const uint32_t *len, uint64_t *off,
                  size_t *total) {
     size_t o = 0;
-    off.resize(n);
-    for (int k = 0; k < n; k++) {
-        if (k && ptr[k] == ptr[k - 1] + len[k - 1]) o = off[k - 1] + len[k - 1];
-        else o = al(o, 256) + ((uintptr_t)ptr[k] & 15);   // same alignment mod 16 as on the host
+    for (int k = k0; k < k1; k++) {
+        if (k > k0 && ptr[k] >= ptr[k - 1] + len[k - 1] && (size_t)(ptr[k] - (ptr[k - 1] + len[k - 1])) <= 64)
+            o = off[k - 1] + (size_t)(ptr[k] - ptr[k - 1]);
+        else o = al(o, 256) + ((uintptr_t)ptr[k] & 15);
         off[k] = o;
         o += len[k];
     }
     *total = o + 256;
 }
+
+// ------------------------------------------------------------ host-buffer encode
+struct EncChunk {
+    int k0 = 0, k1 = 0;
+    Lane *L = nullptr;
+    size_t o_in = 0, o_out = 0, o_off = 0, o_sz = 0, o_tot = 0, bound_total = 0;
+    size_t base = 0;            // where this chunk's streams start in the caller's arena
+};
 
 int compress_batch_impl(int n, const unsigned char *const *in, const unsigned int *in_size, const int *order,
                         const uint32_t *caps, unsigned char *out, size_t out_cap, size_t *out_off,
@@ -351,40 +388,78 @@ int compress_batch_impl(int n, const unsigned char *const *in, const unsigned in
     Ctx *C = get_ctx(&err);
     if (!C) return err;
     if (n <= 0) return 0;
-    cudaStream_t st = C->st;
-    std::vector<uint64_t> ioff;
-    size_t in_total;
-    place_spans(n, in, in_size, ioff, &in_total);
-    size_t bound_total = 0;
-    for (int k = 0; k < n; k++) bound_total += al(compress_bound(in_size[k], order[k]), 16) + 16;
-    Layout L;
-    size_t o_in = L.take(in_total), o_out = L.take(bound_total);
-    size_t o_off = L.take((size_t)n * 8), o_sz = L.take((size_t)n * 4), o_tot = L.take(8);
-    int r = C->io.ensure(L.off + 256);
-    if (r) return r;
-    uint8_t *D = C->io.p;
-    std::vector<Span> sp(n);
-    for (int k = 0; k < n; k++) sp[k] = Span{in[k], o_in + ioff[k], in_size[k]};
-    if ((r = copy_spans(sp, D, true, st))) return r;
-    r = enc_core(*C, st, n, D + o_in, ioff.data(), in_size, order, caps, D + o_out, bound_total,
-                 (uint64_t *)(D + o_off), (uint32_t *)(D + o_sz), (uint64_t *)(D + o_tot));
-    if (r) return r;
-    // read back sizes, then exactly the bytes produced
-    size_t res_bytes = (size_t)n * 12 + 8;
-    if ((r = C->hio.ensure(res_bytes))) return r;
-    uint64_t *h_off = (uint64_t *)C->hio.p;
-    uint32_t *h_sz = (uint32_t *)(C->hio.p + (size_t)n * 8);
-    uint64_t *h_tot = (uint64_t *)(C->hio.p + (size_t)n * 12 + (8 - ((size_t)n * 12) % 8) % 8);
-    CK(cudaMemcpyAsync(h_off, D + o_off, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h_sz, D + o_sz, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h_tot, D + o_tot, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    uint64_t total = *h_tot;
-    if (total > out_cap) return B200RANS_ESPACE;
-    if (total) CK(cudaMemcpyAsync(out, D + o_out, total, cudaMemcpyDeviceToHost, st));
-    for (int k = 0; k < n; k++) { out_off[k] = (size_t)h_off[k]; out_size[k] = h_sz[k]; }
-    CK(cudaStreamSynchronize(st));
-    return 0;
+    // ---- split into pipeline chunks of ~CHUNK_BYTES of input
+    std::vector<EncChunk> ch;
+    for (int k = 0; k < n;) {
+        EncChunk c;
+        c.k0 = k;
+        size_t acc = 0;
+        while (k < n && (k == c.k0 || (acc + in_size[k] <= CHUNK_BYTES && k - c.k0 < 16384))) acc += in_size[k++];
+        c.k1 = k;
+        ch.push_back(c);
+    }
+    std::vector<uint64_t> ioff(n);
+    size_t out_base = 0;
+    int rc = 0;
+
+    auto submit = [&](EncChunk &c) -> int {
+        Lane &Ln = *c.L;
+        int m = c.k1 - c.k0;
+        size_t in_total;
+        place_spans(c.k0, c.k1, in, in_size, ioff.data(), &in_total);
+        c.bound_total = 0;
+        for (int k = c.k0; k < c.k1; k++) c.bound_total += al(compress_bound(in_size[k], order[k]), 16) + 16;
+        Layout L;
+        c.o_in = L.take(in_total); c.o_out = L.take(c.bound_total);
+        c.o_off = L.take((size_t)m * 8); c.o_sz = L.take((size_t)m * 4); c.o_tot = L.take(8);
+        int r = Ln.io.ensure(L.off + 256);
+        if (r) return r;
+        uint8_t *D = Ln.io.p;
+        std::vector<Span> sp(m);
+        for (int k = c.k0; k < c.k1; k++) sp[k - c.k0] = Span{in[k], c.o_in + ioff[k], in_size[k]};
+        if ((r = copy_spans(sp, D, true, Ln.st))) return r;
+        r = enc_core(*C, Ln, Ln.st, m, D + c.o_in, ioff.data() + c.k0, in_size + c.k0, order + c.k0,
+                     caps ? caps + c.k0 : nullptr, D + c.o_out, c.bound_total, (uint64_t *)(D + c.o_off),
+                     (uint32_t *)(D + c.o_sz), (uint64_t *)(D + c.o_tot));
+        if (r) return r;
+        if ((r = Ln.hio.ensure((size_t)m * 12 + 32))) return r;
+        uint8_t *H = Ln.hio.p;
+        CK(cudaMemcpyAsync(H, D + c.o_tot, 8, cudaMemcpyDeviceToHost, Ln.st));
+        CK(cudaMemcpyAsync(H + 16, D + c.o_off, (size_t)m * 8, cudaMemcpyDeviceToHost, Ln.st));
+        CK(cudaMemcpyAsync(H + 16 + (size_t)m * 8, D + c.o_sz, (size_t)m * 4, cudaMemcpyDeviceToHost, Ln.st));
+        return 0;
+    };
+    // sizes known: start the copy of exactly the bytes produced
+    auto readback = [&](EncChunk &c) -> int {
+        Lane &Ln = *c.L;
+        int m = c.k1 - c.k0;
+        CK(cudaStreamSynchronize(Ln.st));
+        uint8_t *H = Ln.hio.p;
+        uint64_t total = *(uint64_t *)H;
+        const uint64_t *h_off = (const uint64_t *)(H + 16);
+        const uint32_t *h_sz = (const uint32_t *)(H + 16 + (size_t)m * 8);
+        c.base = out_base;
+        if (out_base + total > out_cap) return B200RANS_ESPACE;
+        if (total) CK(cudaMemcpyAsync(out + out_base, Ln.io.p + c.o_out, total, cudaMemcpyDeviceToHost, Ln.st));
+        for (int k = c.k0; k < c.k1; k++) {
+            out_off[k] = out_base + (size_t)h_off[k - c.k0];
+            out_size[k] = h_sz[k - c.k0];
+        }
+        out_base += total;
+        return 0;
+    };
+    auto finish = [&](EncChunk &c) -> int { CK(cudaStreamSynchronize(c.L->st)); return 0; };
+
+    int nc = (int)ch.size();
+    for (int c = 0; c < nc && !rc; c++) {
+        ch[c].L = &C->lane[c % NPIPE];
+        rc = submit(ch[c]);
+        if (!rc && c >= 1) rc = readback(ch[c - 1]);
+        if (!rc && c >= 2) rc = finish(ch[c - 2]);      // frees the lane chunk c+1 will use
+    }
+    if (!rc) rc = readback(ch[nc - 1]);
+    for (auto &l : C->lane) cudaStreamSynchronize(l.st);
+    return rc;
 }
 
 // host-side peek at a stream header: flag, stored length
@@ -403,118 +478,159 @@ bool peek_header(const unsigned char *in, unsigned int in_size, int *flag, uint3
     return true;
 }
 
+// ------------------------------------------------------------ host-buffer decode
+struct DecChunk {
+    int k0 = 0, k1 = 0;         // items
+    int j0 = 0, j1 = 0;         // jobs
+    Lane *L = nullptr;
+    size_t o_in = 0, o_out = 0, o_scr = 0, o_osz = 0, o_st = 0;
+};
+
 int uncompress_batch_impl(int n, const unsigned char *const *in, const unsigned int *in_size,
                           unsigned char *const *out, unsigned int *out_size, int *status) {
     int err = 0;
     Ctx *C = get_ctx(&err);
     if (!C) return err;
     if (n <= 0) return 0;
-    cudaStream_t st = C->st;
-    // ---- expand STRIPE streams into their sub-streams (host reads only headers)
+    // ---- plan: expand STRIPE streams into their sub-streams (host reads only headers)
     std::vector<DecItem> items(n);
     std::vector<const unsigned char *> jin;
     std::vector<uint32_t> jin_size, jcap;
     std::vector<uint8_t> jflag;
-    std::vector<uint64_t> jout;         // device offset of each job's output
-    std::vector<uint32_t> ocap(n);
-    std::vector<uint64_t> ooff(n);
-    size_t o = 0, scratch = 0;
-    for (int k = 0; k < n; k++) {
-        DecItem &it = items[k];
-        it = DecItem();
-        int flag = 0, hdr = 0;
-        uint32_t ulen = 0;
-        it.first_job = (uint32_t)jin.size();
-        if (!in[k] || !out[k] || !peek_header(in[k], in_size[k], &flag, &ulen, &hdr)) { it.fail = true; continue; }
-        if (flag & X_NOSZ) ulen = out_size[k];
-        o = al(o, 256) + ((uintptr_t)out[k] & 15);
-        if (k && !items[k - 1].fail && out[k] == out[k - 1] + ocap[k - 1] && !(flag & X_STRIPE))
-            o = ooff[k - 1] + ocap[k - 1];
-        ooff[k] = o;
-        if (flag & X_STRIPE) {
-            if (!stripe_plan_decode(it, in[k], in_size[k], out_size[k])) { it.fail = true; continue; }
-            ocap[k] = it.ulen;
-            o += it.ulen;
-            it.o_tmp = scratch; scratch = al(scratch + it.ulen, 256);
-            for (uint32_t s = 0; s < it.N; s++) {
-                jin.push_back(in[k] + it.sub_off[s]);
-                jin_size.push_back(it.sub_clen[s]);
-                jcap.push_back(it.sub_ulen[s]);
-                jflag.push_back(in[k][it.sub_off[s]]);
-                jout.push_back(~0ull);          // placed in scratch below
-            }
-        } else {
-            if (out_size[k] < ulen) { it.fail = true; continue; }
-            ocap[k] = (flag & X_NOSZ) ? out_size[k] : ulen;
-            it.ulen = ocap[k];
-            o += ocap[k];
-            jin.push_back(in[k]); jin_size.push_back(in_size[k]); jcap.push_back(ocap[k]);
-            jflag.push_back((uint8_t)flag); jout.push_back(ooff[k]);
-        }
-        it.njobs = (uint32_t)jin.size() - it.first_job;
-    }
-    size_t out_total = o + 256;
-    int nj = (int)jin.size();
-    std::vector<uint64_t> cioff;
-    size_t in_total = 0;
-    if (nj) place_spans(nj, jin.data(), jin_size.data(), cioff, &in_total);
-    Layout L;
-    size_t o_in = L.take(in_total + 256), o_out = L.take(out_total), o_scr = L.take(scratch + 256);
-    size_t o_osz = L.take((size_t)nj * 4 + 4), o_st = L.take((size_t)nj * 4 + 4);
-    int r = C->io.ensure(L.off + 256);
-    if (r) return r;
-    uint8_t *D = C->io.p;
-    // stripe sub-jobs decode into the scratch area (relative to d_out base = D + o_out)
-    for (int k = 0; k < n; k++) {
-        DecItem &it = items[k];
-        if (it.fail || !it.stripe) continue;
-        for (uint32_t s = 0; s < it.N; s++)
-            jout[it.first_job + s] = (o_scr + it.o_tmp + it.sub_idx[s]) - o_out;
-    }
-    if (nj) {
-        std::vector<Span> sp(nj);
-        for (int j = 0; j < nj; j++) sp[j] = Span{jin[j], o_in + cioff[j], jin_size[j]};
-        if ((r = copy_spans(sp, D, true, st))) return r;
-        r = dec_core(*C, st, nj, D + o_in, cioff.data(), jin_size.data(), jflag.data(), D + o_out,
-                     jout.data(), jcap.data(), (uint32_t *)(D + o_osz), (int *)(D + o_st));
-        if (r) return r;
+    std::vector<uint32_t> ocap(n, 0);
+    std::vector<DecChunk> ch;
+    {
+        DecChunk c;
+        size_t acc = 0;
         for (int k = 0; k < n; k++) {
             DecItem &it = items[k];
+            int flag = 0, hdr = 0;
+            uint32_t ulen = 0;
+            it.first_job = (uint32_t)jin.size();
+            if (!in[k] || !out[k] || !peek_header(in[k], in_size[k], &flag, &ulen, &hdr)) it.fail = true;
+            else if (flag & X_STRIPE) {
+                if (!stripe_plan_decode(it, in[k], in_size[k], out_size[k])) it.fail = true;
+                else {
+                    ocap[k] = it.ulen;
+                    for (uint32_t s = 0; s < it.N; s++) {
+                        jin.push_back(in[k] + it.sub_off[s]);
+                        jin_size.push_back(it.sub_clen[s]);
+                        jcap.push_back(it.sub_ulen[s]);
+                        jflag.push_back(in[k][it.sub_off[s]]);
+                    }
+                }
+            } else {
+                if (flag & X_NOSZ) ulen = out_size[k];
+                if (out_size[k] < ulen) it.fail = true;
+                else {
+                    ocap[k] = it.ulen = ulen;
+                    jin.push_back(in[k]); jin_size.push_back(in_size[k]); jcap.push_back(ulen);
+                    jflag.push_back((uint8_t)flag);
+                }
+            }
+            it.njobs = (uint32_t)jin.size() - it.first_job;
+            acc += ocap[k];
+            if (acc >= CHUNK_BYTES || k - c.k0 + 1 >= 16384 || k == n - 1) {
+                c.k1 = k + 1; c.j1 = (int)jin.size();
+                ch.push_back(c);
+                c = DecChunk(); c.k0 = k + 1; c.j0 = (int)jin.size();
+                acc = 0;
+            }
+        }
+    }
+    int nj = (int)jin.size();
+    std::vector<uint64_t> cioff(nj ? nj : 1), jout(nj ? nj : 1), ooff(n);
+    int rc = 0;
+
+    auto submit = [&](DecChunk &c) -> int {
+        Lane &Ln = *c.L;
+        int mj = c.j1 - c.j0;
+        // outputs: mirror host contiguity so that the copies back merge
+        size_t o = 0, scratch = 0;
+        for (int k = c.k0; k < c.k1; k++) {
+            DecItem &it = items[k];
+            if (it.fail) continue;
+            int p = k - 1;
+            while (p >= c.k0 && items[p].fail) p--;
+            if (p >= c.k0 && out[k] == out[p] + ocap[p]) o = ooff[p] + ocap[p];
+            else o = al(o, 256) + ((uintptr_t)out[k] & 15);
+            ooff[k] = o;
+            o += ocap[k];
+            if (it.stripe) { it.o_tmp = scratch; scratch = al(scratch + it.ulen, 256); }
+        }
+        size_t in_total = 0;
+        if (mj) place_spans(c.j0, c.j1, jin.data(), jin_size.data(), cioff.data(), &in_total);
+        Layout L;
+        c.o_in = L.take(in_total + 256); c.o_out = L.take(o + 256); c.o_scr = L.take(scratch + 256);
+        c.o_osz = L.take((size_t)mj * 4 + 4); c.o_st = L.take((size_t)mj * 4 + 4);
+        int r = Ln.io.ensure(L.off + 256);
+        if (r) return r;
+        uint8_t *D = Ln.io.p;
+        for (int k = c.k0; k < c.k1; k++) {
+            DecItem &it = items[k];
+            if (it.fail) continue;
+            if (it.stripe)      // sub-streams decode into scratch, joined afterwards
+                for (uint32_t s = 0; s < it.N; s++) jout[it.first_job + s] = (c.o_scr + it.o_tmp + it.sub_idx[s]) - c.o_out;
+            else jout[it.first_job] = ooff[k];
+        }
+        if (!mj) return 0;
+        std::vector<Span> sp(mj);
+        for (int j = c.j0; j < c.j1; j++) sp[j - c.j0] = Span{jin[j], c.o_in + cioff[j], jin_size[j]};
+        if ((r = copy_spans(sp, D, true, Ln.st))) return r;
+        r = dec_core(*C, Ln, Ln.st, mj, D + c.o_in, cioff.data() + c.j0, jin_size.data() + c.j0,
+                     jflag.data() + c.j0, D + c.o_out, jout.data() + c.j0, jcap.data() + c.j0,
+                     (uint32_t *)(D + c.o_osz), (int *)(D + c.o_st));
+        if (r) return r;
+        for (int k = c.k0; k < c.k1; k++) {
+            DecItem &it = items[k];
             if (it.fail || !it.stripe) continue;
-            CK(launch_stripe_join(D + o_scr + it.o_tmp, D + o_out + ooff[k], it.ulen, it.N, st));
+            CK(launch_stripe_join(D + c.o_scr + it.o_tmp, D + c.o_out + ooff[k], it.ulen, it.N, Ln.st));
             C->launches++;
         }
-    }
-    if ((r = C->hio.ensure((size_t)nj * 8 + 16))) return r;
-    uint32_t *h_osz = (uint32_t *)C->hio.p;
-    int *h_st = (int *)(C->hio.p + (size_t)nj * 4 + 8);
-    if (nj) {
-        CK(cudaMemcpyAsync(h_osz, D + o_osz, (size_t)nj * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(h_st, D + o_st, (size_t)nj * 4, cudaMemcpyDeviceToHost, st));
-    }
-    CK(cudaStreamSynchronize(st));
-    // ---- verdict per item, then copy the good ones out
-    std::vector<Span> sp;
-    for (int k = 0; k < n; k++) {
-        DecItem &it = items[k];
-        int s = it.fail ? ST_FAIL : ST_OK;
-        uint32_t got = 0;
-        if (!it.fail) {
-            for (uint32_t j = 0; j < it.njobs; j++) {
-                uint32_t q = it.first_job + j;
-                if (h_st[q] != ST_OK) s = h_st[q];
-                else if (it.stripe && h_osz[q] != it.sub_ulen[j]) s = ST_FAIL;
-                else if (!it.stripe) got = h_osz[q];
+        if ((r = Ln.hio.ensure((size_t)mj * 8 + 32))) return r;
+        CK(cudaMemcpyAsync(Ln.hio.p, D + c.o_osz, (size_t)mj * 4, cudaMemcpyDeviceToHost, Ln.st));
+        CK(cudaMemcpyAsync(Ln.hio.p + (size_t)mj * 4 + 8, D + c.o_st, (size_t)mj * 4, cudaMemcpyDeviceToHost, Ln.st));
+        return 0;
+    };
+    // verdict per item, then copy the good ones out
+    auto readback = [&](DecChunk &c) -> int {
+        Lane &Ln = *c.L;
+        int mj = c.j1 - c.j0;
+        CK(cudaStreamSynchronize(Ln.st));
+        const uint32_t *h_osz = (const uint32_t *)Ln.hio.p;
+        const int *h_st = (const int *)(Ln.hio.p + (size_t)mj * 4 + 8);
+        std::vector<Span> sp;
+        for (int k = c.k0; k < c.k1; k++) {
+            DecItem &it = items[k];
+            int s = it.fail ? ST_FAIL : ST_OK;
+            uint32_t got = 0;
+            if (!it.fail) {
+                for (uint32_t j = 0; j < it.njobs; j++) {
+                    uint32_t q = it.first_job + j - c.j0;
+                    if (h_st[q] != ST_OK) s = h_st[q];
+                    else if (it.stripe && h_osz[q] != it.sub_ulen[j]) s = ST_FAIL;
+                    else if (!it.stripe) got = h_osz[q];
+                }
+                if (it.stripe) got = it.ulen;
             }
-            if (it.stripe) got = it.ulen;
+            if (status) status[k] = s;
+            if (s == ST_OK) { out_size[k] = got; sp.push_back(Span{out[k], c.o_out + ooff[k], got}); }
+            else out_size[k] = 0;
         }
-        if (status) status[k] = s;
-        if (s == ST_OK) { out_size[k] = got; sp.push_back(Span{out[k], o_out + ooff[k], got}); }
-        else out_size[k] = 0;
+        return copy_spans(sp, Ln.io.p, false, Ln.st);
+    };
+    auto finish = [&](DecChunk &c) -> int { CK(cudaStreamSynchronize(c.L->st)); return 0; };
+
+    int nc = (int)ch.size();
+    for (int c = 0; c < nc && !rc; c++) {
+        ch[c].L = &C->lane[c % NPIPE];
+        rc = submit(ch[c]);
+        if (!rc && c >= 1) rc = readback(ch[c - 1]);
+        if (!rc && c >= 2) rc = finish(ch[c - 2]);
     }
-    if ((r = copy_spans(sp, D, false, st))) return r;
-    CK(cudaStreamSynchronize(st));
-    return 0;
+    if (!rc && nc) rc = readback(ch[nc - 1]);
+    for (auto &l : C->lane) cudaStreamSynchronize(l.st);
+    return rc;
 }
 
 }  // namespace
@@ -637,14 +753,13 @@ API int b200rans_compress_batch_dev(void *stream, int n, const unsigned char *d_
     Ctx *C = get_ctx(&err);
     if (!C) return err;
     if (n < 0 || (n && (!d_in || !in_off || !in_size || !order || !d_out))) return B200RANS_EINVAL;
-    cudaStream_t st = stream ? (cudaStream_t)stream : C->st;
-    Layout L;
-    size_t o_tot = L.take(8);
-    // the total lives at the head of the io arena for this call
-    int r = C->io.ensure(256);
+    Lane &Ln = C->lane[0];
+    cudaStream_t st = stream ? (cudaStream_t)stream : Ln.st;
+    // the grand total lives at the head of the lane's io arena for this call
+    int r = Ln.io.ensure(256);
     if (r) return r;
-    return enc_core(*C, st, n, d_in, in_off, in_size, order, nullptr, d_out, out_cap, d_out_off, d_out_size,
-                    (uint64_t *)(C->io.p + o_tot));
+    return enc_core(*C, Ln, st, n, d_in, in_off, in_size, order, nullptr, d_out, out_cap, d_out_off, d_out_size,
+                    (uint64_t *)Ln.io.p);
 }
 
 API int b200rans_uncompress_batch_dev(void *stream, int n, const unsigned char *d_in, const uint64_t *in_off,
@@ -657,8 +772,9 @@ API int b200rans_uncompress_batch_dev(void *stream, int n, const unsigned char *
     if (!C) return err;
     if (n < 0 || (n && (!d_in || !in_off || !in_size || !d_out || !out_off || !out_size || !d_out_size || !d_status)))
         return B200RANS_EINVAL;
-    cudaStream_t st = stream ? (cudaStream_t)stream : C->st;
-    return dec_core(*C, st, n, d_in, in_off, in_size, flags, d_out, out_off, out_size, d_out_size, d_status);
+    Lane &Ln = C->lane[0];
+    cudaStream_t st = stream ? (cudaStream_t)stream : Ln.st;
+    return dec_core(*C, Ln, st, n, d_in, in_off, in_size, flags, d_out, out_off, out_size, d_out_size, d_status);
 }
 
 API uint64_t b200rans_launch_count(void) { return tls_ctx ? tls_ctx->launches : 0; }

@@ -35,6 +35,8 @@ struct EncJob {
     uint32_t item;          // index into the caller's arrays; 0xffffffff for STRIPE sub-streams
     uint32_t stripe_n;      // >0: STRIPE parent record; its tail is the chosen sub-streams,
                             //     whose job indices sit at (uint32_t*)(slot + STRIPE_LIST_OFF)
+    uint32_t route;         // 0: order-0 kernel, 1: order-1 kernel, 2: not coded (STRIPE parent)
+    uint32_t pad_;
 };
 constexpr uint32_t STRIPE_LIST_OFF = 2048;   // header is < 7 + 5*255 bytes
 
@@ -46,6 +48,8 @@ struct DecJob {
     uint32_t out_cap;       // capacity; exact length for NOSZ streams
     uint32_t out_size;      // result
     int32_t  status;        // result: 0 ok
+    uint32_t route;         // 0: order-0 kernel, 1: order-1 kernel
+    uint32_t pad_;
 };
 
 enum : int32_t {

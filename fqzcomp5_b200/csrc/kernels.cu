@@ -178,7 +178,7 @@ enc_kernel(EncJob *jobs, uint32_t njobs, uint32_t warp_smem, Pool pool) {
     extern __shared__ __align__(16) uint8_t smem_all[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t j = blockIdx.x * ENC_WARPS + wid;
-    if (j >= njobs || jobs[j].stripe_n) return;      // STRIPE parents are assembled by stripe_select
+    if (j >= njobs || jobs[j].route != (O1 ? 1u : 0u)) return;   // other kernel's stream, or a STRIPE parent
     enc_stream<O1>(jobs[j], smem_all + (size_t)wid * warp_smem, warp_smem, pool, lane);
 }
 
@@ -302,7 +302,7 @@ dec_kernel(DecJob *jobs, uint32_t njobs, uint32_t warp_smem, Pool pool) {
     extern __shared__ __align__(16) uint8_t smem_all[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t j = blockIdx.x * DEC_WARPS + wid;
-    if (j >= njobs) return;
+    if (j >= njobs || jobs[j].route != (O1 ? 1u : 0u)) return;
     dec_stream<O1>(jobs[j], smem_all + (size_t)wid * warp_smem, warp_smem, pool, lane);
 }
 

@@ -20,6 +20,31 @@ namespace b200 {
 // 16-byte loads; equal neighbours inside a lane's 16 bytes are merged into one
 // shared-memory atomic (quality strings are sticky).
 // ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ldg_u8(const uint8_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(__cvta_generic_to_global(p)));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg_u128(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(__cvta_generic_to_global(p)));
+    return v;
+}
+__device__ __forceinline__ void hist16(uint4 q, uint32_t *F) {
+    uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t prev = w[0] & 0xff, cnt = 0;
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            uint32_t c = (w[a] >> (8 * b)) & 0xff;
+            if (c == prev) cnt++;
+            else { atomicAdd(&F[prev], cnt); prev = c; cnt = 1; }
+        }
+    atomicAdd(&F[prev], cnt);
+}
+
 __device__ inline void warp_hist8(const uint8_t *in, uint32_t n, uint32_t *F, int lane) {
     for (int j = lane; j < 256; j += 32) F[j] = 0;
     __syncwarp();
@@ -29,20 +54,12 @@ __device__ inline void warp_hist8(const uint8_t *in, uint32_t n, uint32_t *F, in
     const uint8_t *p = in + head;
     uint32_t rest = n - head, nv = rest >> 4;
     const uint4 *v = (const uint4 *)p;
-    for (uint32_t i = lane; i < nv; i += 32) {
-        uint4 q = v[i];
-        uint32_t w[4] = {q.x, q.y, q.z, q.w};
-        uint32_t prev = w[0] & 0xff, cnt = 0;
-#pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                uint32_t c = (w[a] >> (8 * b)) & 0xff;
-                if (c == prev) cnt++;
-                else { atomicAdd(&F[prev], cnt); prev = c; cnt = 1; }
-            }
-        atomicAdd(&F[prev], cnt);
+    uint32_t i = lane;
+    for (; i + 96 < nv; i += 128) {                  // four 16-byte loads in flight per lane
+        uint4 q0 = ldg_u128(v + i), q1 = ldg_u128(v + i + 32), q2 = ldg_u128(v + i + 64), q3 = ldg_u128(v + i + 96);
+        hist16(q0, F); hist16(q1, F); hist16(q2, F); hist16(q3, F);
     }
+    for (; i < nv; i += 32) hist16(ldg_u128(v + i), F);
     for (uint32_t i = (nv << 4) + lane; i < rest; i += 32) atomicAdd(&F[p[i]], 1u);
     __syncwarp();
 }
@@ -269,13 +286,30 @@ __device__ int enc_o0(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
         R = enc_step(R, on, e, ptr, lane);
     }
     const uint8_t *q = in + (act ? lane : 0);
+    // Symbols are fetched two groups (8 steps) ahead of their use so that the
+    // DRAM latency of a new 128-byte line is off the state chain.
+    uint32_t sA[4] = {0, 0, 0, 0}, sB[4] = {0, 0, 0, 0};
+    if (i >= 4 * N) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) sA[u] = ldg_u8(q + i - (u + 1) * N);
+    }
+    if (i >= 8 * N) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) sB[u] = ldg_u8(q + i - (u + 5) * N);
+    }
     for (; i >= 4 * N; i -= 4 * N) {
-        uint32_t s0 = q[i - N], s1 = q[i - 2 * N], s2 = q[i - 3 * N], s3 = q[i - 4 * N];
-        uint4 e0 = S.sym[s0], e1 = S.sym[s1], e2 = S.sym[s2], e3 = S.sym[s3];
+        uint32_t sC[4] = {0, 0, 0, 0};
+        if (i >= 12 * N) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) sC[u] = ldg_u8(q + i - (u + 9) * N);
+        }
+        uint4 e0 = S.sym[sA[0]], e1 = S.sym[sA[1]], e2 = S.sym[sA[2]], e3 = S.sym[sA[3]];
         R = enc_step(R, act, e0, ptr, lane);
         R = enc_step(R, act, e1, ptr, lane);
         R = enc_step(R, act, e2, ptr, lane);
         R = enc_step(R, act, e3, ptr, lane);
+#pragma unroll
+        for (int u = 0; u < 4; u++) { sA[u] = sB[u]; sB[u] = sC[u]; }
     }
     for (; i > 0; i -= N) R = enc_step(R, act, S.sym[q[i - N]], ptr, lane);
     enc_flush(R, act, N, ptr, lane);
