@@ -234,7 +234,7 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
         }
     }
     // the reference's worst case is one table per stream; real tables are tiny.
-    pool_bytes = std::min<size_t>(pool_bytes, (size_t)2 << 30);
+    pool_bytes = std::min<size_t>(pool_bytes, (size_t)16 << 30);
     pool_bytes = std::max<size_t>(pool_bytes, (size_t)8 << 20);
     size_t o_pool = L.take(pool_bytes, 256);
     size_t o_soff = L.take(njobs * 8), o_ssz = L.take(njobs * 4);

@@ -138,10 +138,9 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
             if (O1 && o1) {
                 EncO1Smem &S = *(EncO1Smem *)smem;
                 uint8_t *dyn = smem + sizeof(EncO1Smem);
-                uint32_t hw = (smem_bytes - (uint32_t)sizeof(EncO1Smem)) / 4;
-                EncO0Smem *o0s = (EncO0Smem *)dyn;      // pair counts are dead by the time the table is coded
-                e = do_simd ? enc_o1<32>(in, in_size, out + meta, oend, &tab, &ptr, S, (uint32_t *)dyn, hw, o0s, pool, lane)
-                            : enc_o1<4>(in, in_size, out + meta, oend, &tab, &ptr, S, (uint32_t *)dyn, hw, o0s, pool, lane);
+                uint32_t dynb = smem_bytes - (uint32_t)sizeof(EncO1Smem);
+                e = do_simd ? enc_o1<32>(in, in_size, out + meta, oend, &tab, &ptr, S, dyn, dynb, pool, lane)
+                            : enc_o1<4>(in, in_size, out + meta, oend, &tab, &ptr, S, dyn, dynb, pool, lane);
             } else if (o1) {
                 e = 3;      // order-1 stream routed to the order-0-only kernel: host bug
             } else {
@@ -173,11 +172,11 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
 }
 
 template <bool O1>
-__global__ void __launch_bounds__(ENC_WARPS * 32)
+__global__ void __launch_bounds__((O1 ? ENC_WARPS_O1 : ENC_WARPS) * 32)
 enc_kernel(EncJob *jobs, uint32_t njobs, uint32_t warp_smem, Pool pool) {
     extern __shared__ __align__(16) uint8_t smem_all[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t j = blockIdx.x * ENC_WARPS + wid;
+    uint32_t j = blockIdx.x * (O1 ? ENC_WARPS_O1 : ENC_WARPS) + wid;
     if (j >= njobs || jobs[j].route != (O1 ? 1u : 0u)) return;   // other kernel's stream, or a STRIPE parent
     enc_stream<O1>(jobs[j], smem_all + (size_t)wid * warp_smem, warp_smem, pool, lane);
 }
@@ -297,11 +296,11 @@ __device__ void dec_stream(DecJob &J, uint8_t *smem, uint32_t smem_bytes, const 
 }
 
 template <bool O1>
-__global__ void __launch_bounds__(DEC_WARPS * 32)
+__global__ void __launch_bounds__((O1 ? DEC_WARPS_O1 : DEC_WARPS) * 32)
 dec_kernel(DecJob *jobs, uint32_t njobs, uint32_t warp_smem, Pool pool) {
     extern __shared__ __align__(16) uint8_t smem_all[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t j = blockIdx.x * DEC_WARPS + wid;
+    uint32_t j = blockIdx.x * (O1 ? DEC_WARPS_O1 : DEC_WARPS) + wid;
     if (j >= njobs || jobs[j].route != (O1 ? 1u : 0u)) return;
     dec_stream<O1>(jobs[j], smem_all + (size_t)wid * warp_smem, warp_smem, pool, lane);
 }
@@ -391,10 +390,10 @@ static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStream_t st) {
     if (!n) return cudaSuccess;
     uint32_t ws = o1 ? ENC_SMEM_O1 : ENC_SMEM_O0;
-    size_t sm = (size_t)ws * ENC_WARPS;
+    size_t sm = (size_t)ws * (o1 ? ENC_WARPS_O1 : ENC_WARPS);
     if (o1) {
         cudaFuncSetAttribute(enc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        enc_kernel<true><<<cdiv(n, ENC_WARPS), ENC_WARPS * 32, sm, st>>>(d_jobs, n, ws, pool);
+        enc_kernel<true><<<cdiv(n, ENC_WARPS_O1), ENC_WARPS_O1 * 32, sm, st>>>(d_jobs, n, ws, pool);
     } else {
         cudaFuncSetAttribute(enc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         enc_kernel<false><<<cdiv(n, ENC_WARPS), ENC_WARPS * 32, sm, st>>>(d_jobs, n, ws, pool);
@@ -405,10 +404,10 @@ cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStrea
 cudaError_t launch_dec(DecJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStream_t st) {
     if (!n) return cudaSuccess;
     uint32_t ws = o1 ? DEC_SMEM_O1 : DEC_SMEM_O0;
-    size_t sm = (size_t)ws * DEC_WARPS;
+    size_t sm = (size_t)ws * (o1 ? DEC_WARPS_O1 : DEC_WARPS);
     if (o1) {
         cudaFuncSetAttribute(dec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        dec_kernel<true><<<cdiv(n, DEC_WARPS), DEC_WARPS * 32, sm, st>>>(d_jobs, n, ws, pool);
+        dec_kernel<true><<<cdiv(n, DEC_WARPS_O1), DEC_WARPS_O1 * 32, sm, st>>>(d_jobs, n, ws, pool);
     } else {
         cudaFuncSetAttribute(dec_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         dec_kernel<false><<<cdiv(n, DEC_WARPS), DEC_WARPS * 32, sm, st>>>(d_jobs, n, ws, pool);

@@ -7,12 +7,14 @@ namespace b200 {
 
 // one warp per stream, several streams per CTA
 constexpr int ENC_WARPS = 4;
+constexpr int ENC_WARPS_O1 = 2;
 constexpr int DEC_WARPS = 4;
+constexpr int DEC_WARPS_O1 = 2;
 // shared memory per warp (bytes)
 constexpr uint32_t ENC_SMEM_O0 = 5120;     // EncO0Smem
-constexpr uint32_t ENC_SMEM_O1 = 12288;    // EncO1Smem header + pair counts for <= 48 symbols
+constexpr uint32_t ENC_SMEM_O1 = 36864;    // EncO1Smem header + pair counts + 16-byte encoder symbols for <= 41 symbols
 constexpr uint32_t DEC_SMEM_O0 = 6144;     // DecO0Smem
-constexpr uint32_t DEC_SMEM_O1 = 14336;    // DecO1Smem header + tables for <= ~48 symbols
+constexpr uint32_t DEC_SMEM_O1 = 20480;    // DecO1Smem header + (start,freq) pairs + 256-bucket index for <= 41 symbols
 
 cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStream_t st);
 cudaError_t launch_dec(DecJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStream_t st);

@@ -112,6 +112,26 @@ __device__ __forceinline__ uint32_t lds_u16(const uint8_t *base, uint32_t off) {
     return v;
 }
 
+__device__ __forceinline__ uint32_t lds_u8a(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16a(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32a(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void stg_u128(uint8_t *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(__cvta_generic_to_global(p)), "r"(a), "r"(b),
+                 "r"(c), "r"(d) : "memory");
+}
+
 // One renormalisation round for the warp (rANS_word.h:414-476): lanes whose
 // state fell below 2^15 take the next words in lane order.  A lane refills only
 // if two more bytes exist, exactly like RansDecRenormSafe.
@@ -299,14 +319,15 @@ __device__ int dec_o0(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
 // A look-up is blut -> fs[r], stepping r forward while slot >= start+freq.
 struct DecO1Tabs {
     uint32_t *fs;       // [nsym][nsym]
-    uint8_t  *blut;     // [nsym][64]
+    uint8_t  *blut;     // [nsym][1 << bb]
     uint8_t  *sym;      // [nsym] rank -> symbol
     uint32_t  nsym;
 };
-constexpr int O1_BUCKET_BITS = 6;
-
-__host__ __device__ inline uint32_t dec_o1_tab_bytes(uint32_t nsym) {
-    return nsym * nsym * 4 + nsym * 64 + ((nsym + 15) & ~15u);
+// Buckets per context: 2^bb with bb in {6,7,8}; the finest that fits is used, so that
+// a look-up rarely has to step over more than one symbol (the scan is paid by the
+// whole warp for its slowest lane).
+__host__ __device__ inline uint32_t dec_o1_tab_bytes(uint32_t nsym, uint32_t bb) {
+    return nsym * nsym * 4 + (nsym << bb) + ((nsym + 15) & ~15u);
 }
 
 // one order-1 row (rANS_static16_int.h:425-456), single thread.  A[] lists the
@@ -332,6 +353,54 @@ __device__ inline int get_freq_row(const uint8_t *cp, const uint8_t *end, uint32
     }
     *tot = t;
     return (int)(cp - op);
+}
+
+// Order-1 hot loop (32 lanes, tables in shared memory, 16-byte aligned lane
+// segments): 16 steps per iteration, each lane collecting its 16 output bytes in
+// registers and writing them with one 128-bit store; no end-of-stream checks.
+template <bool ODD>
+__device__ __forceinline__ void dec_o1_fast(uint32_t &R_, uint32_t &ctx_, uint32_t &k_, uint32_t seg,
+                                            uint8_t *o, WordRing &w, uint32_t fs_s, uint32_t blut_s,
+                                            uint32_t sym_s, uint32_t ns, uint32_t shift, uint32_t bb,
+                                            int lane, uint32_t lt) {
+    uint32_t R = R_, ctx = ctx_, k = k_, pos = w.pos;
+    const uint32_t mask = (1u << shift) - 1, bw = shift - bb, ns4 = ns * 4;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(w.ring);
+    while (k + 16 <= seg && pos + 16 * 64 <= w.end) {
+        uint32_t acc[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            w.pos = pos;
+            w.advance4(lane);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                uint32_t m = R & mask;
+                uint32_t r = lds_u8a(blut_s + (ctx << bb) + (m >> bw));
+                uint32_t rowa = fs_s + ctx * ns4;
+                uint32_t e = lds_u32a(rowa + r * 4);
+                while (m - (e & 0xffff) >= (e >> 16) && r + 1 < ns) { r++; e = lds_u32a(rowa + r * 4); }
+                R = (e >> 16) * (R >> shift) + m - (e & 0xffff);
+                ctx = r;
+                acc[g] |= lds_u8a(sym_s + r) << (8 * u);
+                bool need = R < RANS_L;
+                uint32_t bal = __ballot_sync(FULL, need);
+                if (need) {
+                    uint32_t p = pos + 2 * __popc(bal & lt);
+                    uint32_t wv = ODD ? (lds_u8a(ring_s + (p & (RING - 1))) |
+                                         (lds_u8a(ring_s + ((p + 1) & (RING - 1))) << 8))
+                                      : lds_u16a(ring_s + (p & (RING - 1)));
+                    R = (R << 16) | wv;
+                }
+                pos += 2 * __popc(bal);
+            }
+        }
+        stg_u128(o + k, acc[0], acc[1], acc[2], acc[3]);
+        k += 16;
+    }
+    w.pos = pos;
+    cp_async_wait_all();
+    __syncwarp();
+    R_ = R; ctx_ = ctx; k_ = k;
 }
 
 struct __align__(16) DecO1Smem {
@@ -394,14 +463,16 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
     // --- table storage: shared memory when it fits, else the scratch pool
     DecO1Tabs T;
     T.nsym = nsym;
-    uint32_t need = dec_o1_tab_bytes(nsym);
+    uint32_t bb = 8;
+    while (bb > 6 && dec_o1_tab_bytes(nsym, bb) > smem_tab_bytes) bb--;
+    uint32_t need = dec_o1_tab_bytes(nsym, bb);
     uint8_t *tb;
     const bool in_smem = need <= smem_tab_bytes;
     if (in_smem) tb = smem_tabs;
     else { tb = pool_alloc(pool, need, lane); if (!tb) return 2; }
     T.fs = (uint32_t *)tb;
     T.blut = tb + nsym * nsym * 4;
-    T.sym = T.blut + nsym * 64;
+    T.sym = T.blut + (nsym << bb);
     for (int j = lane; j < 256; j += 32)          // presence from F0: rank 255 is a valid rank
         if (S.F0[j]) T.sym[S.rank[j]] = (uint8_t)j;
 
@@ -436,14 +507,14 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
     __threadfence_block();
     __syncwarp();
     // --- bucket look-up: lane per row
-    const uint32_t bw = shift - O1_BUCKET_BITS;
-    for (uint32_t i = lane; i < nsym; i += 32) {
+    const uint32_t bw = shift - bb, nb = 1u << bb;
+    for (uint32_t i0 = 0; i0 < nsym; i0 += 32) { const uint32_t i = i0 + lane; if (i >= nsym) continue;
         const uint32_t *row = T.fs + i * nsym;
-        uint8_t *bl = T.blut + i * 64;
+        uint8_t *bl = T.blut + (i << bb);
         uint32_t r = 0, e = row[0];
         bool empty = true;
         for (uint32_t q = 0; q < nsym; q++) empty &= (row[q] >> 16) == 0;
-        for (uint32_t b = 0; b < 64; b++) {
+        for (uint32_t b = 0; b < nb; b++) {
             uint32_t m = b << bw;
             if (!empty)
                 while (r + 1 < nsym && m >= (e & 0xffff) + (e >> 16)) e = row[++r];
@@ -481,7 +552,7 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
 
     auto step = [&](bool on) {
         uint32_t m = R & mask;
-        uint32_t r = blut[ctx * 64 + (m >> bw)];
+        uint32_t r = blut[(ctx << bb) + (m >> bw)];
         const uint32_t *row = fs + ctx * ns;
         uint32_t e = row[r];
         while (m - (e & 0xffff) >= (e >> 16) && r + 1 < ns) e = row[++r];   // unsigned: m >= start always
@@ -492,7 +563,16 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
         return (uint8_t)symtab[r];
     };
 
-    for (uint32_t k = 0; k < seg; k++) {
+    uint32_t k = 0;
+    if (N == 32 && in_smem && ((((uintptr_t)out) | seg) & 15) == 0) {
+        const uint32_t fs_s = (uint32_t)__cvta_generic_to_shared(T.fs);
+        const uint32_t bl_s = (uint32_t)__cvta_generic_to_shared(T.blut);
+        const uint32_t sy_s = (uint32_t)__cvta_generic_to_shared(T.sym);
+        __syncwarp();
+        if (w.pos & 1) dec_o1_fast<true>(R, ctx, k, seg, o, w, fs_s, bl_s, sy_s, ns, shift, bb, lane, lt);
+        else dec_o1_fast<false>(R, ctx, k, seg, o, w, fs_s, bl_s, sy_s, ns, shift, bb, lane, lt);
+    }
+    for (; k < seg; k++) {
         uint8_t s = step(act);
         if (act) o[k] = s;
         R = renorm_step(R, act, w, lane, lt);

@@ -355,8 +355,8 @@ __device__ inline uint32_t put_freq_row(uint8_t *cp, const uint32_t *F, uint32_t
 
 template <int N>
 __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_end,
-                      uint32_t *tab_len, uint8_t **ptr_out, EncO1Smem &S, uint32_t *smem_hist,
-                      uint32_t smem_hist_words, EncO0Smem *o0s, const Pool &pool, int lane) {
+                      uint32_t *tab_len, uint8_t **ptr_out, EncO1Smem &S, uint8_t *dyn, uint32_t dyn_bytes,
+                      const Pool &pool, int lane) {
     *tab_len = 0;
     *ptr_out = out_end;
     if (N == 32 && n < 32) return 1;
@@ -388,24 +388,68 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
     __syncwarp();
 
     // ---- pair counts H[rank(prev)][rank(cur)], first symbol follows 0 (utils.h:279-357)
+    // Dynamic shared memory of this warp: [pair counts H, later scratch of the table coder]
+    // [encoder symbols], whatever fits; the rest comes from the scratch pool.
     uint32_t *H;
     const uint32_t hw = nsym * nsym;
-    if (hw <= smem_hist_words) H = smem_hist;
+    const uint32_t h_bytes = max((hw * 4 + 15) & ~15u, (uint32_t)sizeof(EncO0Smem));
+    const bool h_smem = h_bytes <= dyn_bytes;
+    const bool sym_smem = h_smem && h_bytes + hw * 16 <= dyn_bytes;
+    EncO0Smem *o0s = (EncO0Smem *)dyn;           // H is dead by the time the table is coded
+    if (h_smem) H = (uint32_t *)dyn;
     else { H = (uint32_t *)pool_alloc(pool, hw * 4, lane); if (!H) return 2; }
     for (uint32_t j = lane; j < hw; j += 32) H[j] = 0;
     __syncwarp();
-    for (uint32_t base = 0; base < n; base += 32) {
-        uint32_t p = base + lane;
-        if (p < n) {
-            uint32_t prev = p ? in[p - 1] : 0, cur = in[p];
-            atomicAdd(&H[S.rank[prev] * nsym + S.rank[cur]], 1u);
+    {
+        const uint8_t *rank = S.rank;
+        uint32_t head = (uint32_t)((16 - ((uintptr_t)in & 15)) & 15);
+        if (head > n) head = n;
+        if ((uint32_t)lane < head) {
+            uint32_t prev = lane ? in[lane - 1] : 0;
+            atomicAdd(&H[rank[prev] * nsym + rank[in[lane]]], 1u);
+        }
+        const uint8_t *p = in + head;
+        uint32_t rest = n - head, nv = rest >> 4;
+        const uint4 *v = (const uint4 *)p;
+        // carry = rank of the byte just before this lane's 16 bytes
+        uint32_t carry_last = head ? in[head - 1] : 0;      // byte before the vector body
+        for (uint32_t base = 0; base < nv; base += 32) {
+            uint32_t i = base + lane;
+            bool on = i < nv;
+            uint4 q = on ? ldg_u128(v + i) : make_uint4(0, 0, 0, 0);
+            uint32_t lastb = q.w >> 24;
+            uint32_t pb = __shfl_up_sync(FULL, lastb, 1);
+            if (lane == 0) pb = carry_last;
+            // last byte of the last active lane feeds lane 0 of the next round
+            uint32_t nact = min(32u, nv - base);
+            carry_last = __shfl_sync(FULL, lastb, nact - 1);
+            if (on) {
+                uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+                uint32_t rp = rank[pb], last = 0xffffffffu, cnt = 0;
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        uint32_t rc = rank[(w4[a] >> (8 * b)) & 0xff];
+                        uint32_t idx = rp * nsym + rc;
+                        if (idx == last) cnt++;
+                        else { if (cnt) atomicAdd(&H[last], cnt); last = idx; cnt = 1; }
+                        rp = rc;
+                    }
+                atomicAdd(&H[last], cnt);
+            }
+        }
+        for (uint32_t i = (nv << 4) + lane; i < rest; i += 32) {
+            uint32_t pos = head + i;
+            uint32_t prev = pos ? in[pos - 1] : 0;
+            atomicAdd(&H[rank[prev] * nsym + rank[in[pos]]], 1u);
         }
     }
     // lanes 1..N-1 start in context 0 (rANS_static16_int.h:325-327)
     if (lane >= 1 && lane < N) atomicAdd(&H[S.rank[0] * nsym + S.rank[in[lane * seg]]], 1u);
     __syncwarp();
     // row totals; the last symbol's total gets one extra (utils.h:311,345)
-    for (uint32_t i = lane; i < nsym; i += 32) {
+    for (uint32_t i0 = 0; i0 < nsym; i0 += 32) { const uint32_t i = i0 + lane; if (i >= nsym) continue;
         uint32_t t = 0;
         for (uint32_t j = 0; j < nsym; j++) t += H[i * nsym + j];
         if (S.sym[i] == in[n - 1]) t++;
@@ -416,7 +460,7 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
     // ---- precision: 10 or 12 bits (rANS_static4x16pr.c:357-420), lane per row
     double e10 = 0, e12 = 0;
     uint32_t max_tot = 0;
-    for (uint32_t i = lane; i < nsym; i += 32) {
+    for (uint32_t i0 = 0; i0 < nsym; i0 += 32) { const uint32_t i = i0 + lane; if (i >= nsym) continue;
         const uint32_t *row = H + i * nsym;
         uint32_t Ti = S.T[i];
         if (!Ti) { S.S[i] = 0; continue; }
@@ -454,10 +498,11 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
     const uint32_t shift = (e10 / e12 < 1.01 || max_tot <= 1024) ? 10 : 12;
 
     // ---- rows: normalise to the stored total, measure, serialise, scale, symbols
-    uint4 *symtab = (uint4 *)pool_alloc(pool, hw * 16, lane);
-    if (!symtab) return 2;
+    uint4 *symtab;
+    if (sym_smem) symtab = (uint4 *)(dyn + h_bytes);
+    else { symtab = (uint4 *)pool_alloc(pool, hw * 16, lane); if (!symtab) return 2; }
     int err = 0;
-    for (uint32_t i = lane; i < nsym; i += 32) {
+    for (uint32_t i0 = 0; i0 < nsym; i0 += 32) { const uint32_t i = i0 + lane; if (i >= nsym) continue;
         uint32_t *row = H + i * nsym;
         uint32_t Ti = S.T[i];
         if (!Ti) { S.rowlen[i] = 0; continue; }
@@ -499,7 +544,7 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
     }
     uint32_t tl = __shfl_sync(FULL, hdr, 0);
     __syncwarp();
-    for (uint32_t i = lane; i < nsym; i += 32) {
+    for (uint32_t i0 = 0; i0 < nsym; i0 += 32) { const uint32_t i = i0 + lane; if (i >= nsym) continue;
         uint32_t *row = H + i * nsym;
         if (!S.T[i]) continue;
         put_freq_row(out + S.rowlen[i], row, nsym);
@@ -562,7 +607,53 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
     }
     const uint8_t *q = in + (size_t)(act ? lane : 0) * seg;
     uint32_t rs = act && seg ? rank[q[seg - 1]] : 0;         // rank of the symbol being coded
-    for (uint32_t k = seg; k-- > 1;) {
+    uint32_t kstart = seg;
+    __syncwarp();                                            // enter the hot loop converged
+    if (N == 32 && sym_smem && seg >= 32 && ((((uintptr_t)in) | seg) & 15) == 0) {
+        // Hot loop: lane segments are 16-byte aligned, so every lane reads its symbols with
+        // 128-bit loads (one group of 16 ahead) and the encoder symbols come from shared memory.
+        const uint32_t rank_s = (uint32_t)__cvta_generic_to_shared(S.rank);
+        const uint32_t sym_s = (uint32_t)__cvta_generic_to_shared(symtab);
+        const uint4 *v = (const uint4 *)q;
+        const uint32_t J = seg >> 4;
+        uint4 cur = ldg_u128(v + J - 1), nxt = ldg_u128(v + J - 2);
+        auto byte_of = [](const uint4 &x, int b) {
+            uint32_t w = b < 4 ? x.x : b < 8 ? x.y : b < 12 ? x.z : x.w;
+            return (w >> (8 * (b & 3))) & 0xff;
+        };
+        auto lds128 = [](uint32_t a) {
+            uint4 r;
+            asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+            return r;
+        };
+        auto rank_of = [&](uint32_t b) {
+            uint32_t r;
+            asm("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(rank_s + b));
+            return r;
+        };
+        for (uint32_t j = J - 1; j >= 1; j--) {
+            uint4 nn = j >= 2 ? ldg_u128(v + j - 2) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int b = 15; b >= 0; b--) {
+                uint32_t cb = b ? byte_of(cur, b - 1) : byte_of(nxt, 15);
+                uint32_t rc = rank_of(cb);
+                uint4 e = lds128(sym_s + (rc * nsym + rs) * 16);
+                R = enc_step(R, true, e, ptr, lane);
+                rs = rc;
+            }
+            cur = nxt;
+            nxt = nn;
+        }
+#pragma unroll
+        for (int b = 15; b >= 1; b--) {                      // group 0: its byte 0 is the lane's first symbol
+            uint32_t rc = rank_of(byte_of(cur, b - 1));
+            uint4 e = lds128(sym_s + (rc * nsym + rs) * 16);
+            R = enc_step(R, true, e, ptr, lane);
+            rs = rc;
+        }
+        kstart = 1;
+    }
+    for (uint32_t k = kstart; k-- > 1;) {
         uint32_t rc = rank[q[k - 1]];
         uint4 e = symtab[rc * nsym + rs];
         R = enc_step(R, act, e, ptr, lane);
