@@ -194,7 +194,7 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
     std::vector<EncJob> jobs(njobs);
     size_t o_jobs = L.take(njobs * sizeof(EncJob));
     size_t o_ctr = L.take(256);
-    uint32_t n_o0 = 0, n_o1 = 0;
+    uint32_t n_o0 = 0, n_o1 = 0, n_model = 0;
     size_t pool_bytes = 0;
     // ---- pass 2: place slots / work buffers
     auto place = [&](EncJob &J, const uint8_t *in, uint32_t isz, int ord, uint32_t cap, uint32_t item) {
@@ -204,6 +204,12 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
         J.slot_cap = slot_cap;
         J.slot = (uint8_t *)L.take(slot_cap, 256);
         if (ord & (X_PACK | X_RLE)) J.work = (uint8_t *)L.take((size_t)isz * 4 + isz / 4 + 8192, 256);
+        else if (isz >= 4096) {
+            // big plain streams: counts come from hist_kernel (order-1: up to (isz+1)^2 or 256^2 pairs)
+            size_t pairs = ((ord & 1) && isz >= 8) ? std::min<size_t>(65536, ((size_t)isz + 1) * (isz + 1)) : 0;
+            J.model = (uint32_t *)(L.take((MODEL_HDR_WORDS + pairs) * 4, 256) + 1);   // +1: null stays null
+            n_model++;
+        }
         if ((ord & 1) && isz >= 8) {
             J.route = 1;                     // the order-1 kernel (larger shared memory per warp)
             n_o1++;
@@ -220,6 +226,7 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
             sp.o_transposed = L.take(in_size[k], 256);
             place(jobs[j], d_in + in_off[k], in_size[k], order[k], cap, (uint32_t)k);
             if (jobs[j].route) { n_o1--; pool_bytes -= 256 * 256 * 20 + 300 * 1024; } else n_o0--;
+            if (jobs[j].model) { jobs[j].model = nullptr; n_model--; }
             jobs[j].route = 2;               // assembled by stripe_select, not coded
             jobs[j].stripe_n = sp.N;
             for (uint32_t s = 0; s < sp.nsub; s++) {
@@ -245,6 +252,7 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
     for (auto &J : jobs) {
         J.slot = W + (size_t)J.slot;
         if (J.work) J.work = W + (size_t)J.work;
+        if (J.model) J.model = (uint32_t *)(W + ((size_t)J.model - 1));
     }
     for (auto &sp : stripes)
         for (uint32_t s = 0; s < sp.nsub; s++) {
@@ -265,6 +273,8 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
         CK(launch_stripe_split(d_in + in_off[sp.item], W + sp.o_transposed, sp.in_size, sp.N, st));
         C.launches++;
     }
+    // ---- histograms of the plain streams at full occupancy
+    if (n_model) { CK(launch_hist(d_jobs, (uint32_t)njobs, st)); C.launches++; }
     // ---- encode: order-0 streams on the lean kernel, the rest on the order-1 kernel
     if (C.prof) CK(cudaEventRecord(C.pe[0], st));
     if (n_o0) { CK(launch_enc(d_jobs, (uint32_t)njobs, false, pool, st)); C.launches++; }

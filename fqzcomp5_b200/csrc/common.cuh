@@ -37,7 +37,11 @@ struct EncJob {
                             //     whose job indices sit at (uint32_t*)(slot + STRIPE_LIST_OFF)
     uint32_t route;         // 0: order-0 kernel, 1: order-1 kernel, 2: not coded (STRIPE parent)
     uint32_t pad_;
+    uint32_t *model;        // counts precomputed by hist_kernel, or null (the coder counts itself):
+                            //   [256] order-0 counts, [MODEL_HDR_WORDS..] order-1 pair counts in rank space
+    uint64_t pad2_;
 };
+constexpr uint32_t MODEL_HDR_WORDS = 260;   // 256 counts, nsym, 3 pad
 constexpr uint32_t STRIPE_LIST_OFF = 2048;   // header is < 7 + 5*255 bytes
 
 struct DecJob {

@@ -59,6 +59,8 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
         }
         int o1 = order & 1;
         uint8_t *work = J.work;
+        // counts from hist_kernel describe the caller's bytes: unusable once PACK/RLE rewrote them
+        const uint32_t *model = (J.model && in == J.in) ? J.model : nullptr;
 
         if ((do_pack || do_rle) && in_size && !work) status = ST_UNSUPPORTED;   // host sizes work for these
         if (status != ST_OK) {
@@ -126,6 +128,7 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
             }
         } else if (do_rle) flag &= ~X_RLE;
 
+        if (in != J.in) model = nullptr;
         cc.require((uint64_t)meta + szq);                                 // :1538
         if (o1 && in_size < 8) { flag &= ~1u; o1 = 0; }                   // :1547
         cc.require((uint64_t)compress_bound(in_size, o1) - 20 + meta + szq);   // bound > *out_size in the coder
@@ -139,14 +142,14 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
                 EncO1Smem &S = *(EncO1Smem *)smem;
                 uint8_t *dyn = smem + sizeof(EncO1Smem);
                 uint32_t dynb = smem_bytes - (uint32_t)sizeof(EncO1Smem);
-                e = do_simd ? enc_o1<32>(in, in_size, out + meta, oend, &tab, &ptr, S, dyn, dynb, pool, lane)
-                            : enc_o1<4>(in, in_size, out + meta, oend, &tab, &ptr, S, dyn, dynb, pool, lane);
+                e = do_simd ? enc_o1<32>(in, in_size, out + meta, oend, &tab, &ptr, S, dyn, dynb, pool, lane, model)
+                            : enc_o1<4>(in, in_size, out + meta, oend, &tab, &ptr, S, dyn, dynb, pool, lane, model);
             } else if (o1) {
                 e = 3;      // order-1 stream routed to the order-0-only kernel: host bug
             } else {
                 EncO0Smem &S = *(EncO0Smem *)smem;
-                e = do_simd ? enc_o0<32>(in, in_size, out + meta, oend, &tab, &ptr, S, lane)
-                            : enc_o0<4>(in, in_size, out + meta, oend, &tab, &ptr, S, lane);
+                e = do_simd ? enc_o0<32>(in, in_size, out + meta, oend, &tab, &ptr, S, lane, model)
+                            : enc_o0<4>(in, in_size, out + meta, oend, &tab, &ptr, S, lane, model);
             }
             if (e) status = (e == 2 || e == 3) ? ST_UNSUPPORTED : ST_FAIL;
         }
@@ -382,6 +385,112 @@ gather_kernel(const EncJob *jobs, uint32_t njobs, const uint64_t *out_off, uint3
         uint32_t len = tl - p < P ? tl - p : P;
         warp_copy(dst + hl + p, J.tail + p, len, lane);
     }
+}
+
+
+// ------------------------------------------------------------------------
+// Histograms at full occupancy: one CTA of 8 warps per stream counts its bytes
+// into warp-private shared-memory bins (order 0) and, for order-1 streams, its
+// (previous, current) pairs into a rank-space matrix, merging equal neighbours
+// before touching shared memory.  The coder kernels then start from the counts
+// instead of reading the stream a second time with one warp.
+// ------------------------------------------------------------------------
+constexpr int HIST_THREADS = 256;
+constexpr uint32_t HIST_SMEM_PAIRS = 6400;          // words: rank-space matrices up to 80x80 stay in shared memory
+
+__global__ void __launch_bounds__(HIST_THREADS)
+hist_kernel(EncJob *jobs, uint32_t njobs) {
+    const uint32_t jn = blockIdx.x;
+    if (jn >= njobs) return;
+    EncJob &J = jobs[jn];
+    uint32_t *model = J.model;
+    if (!model) return;
+    __shared__ uint32_t Fw[8][256];
+    __shared__ uint8_t rank[256];
+    __shared__ uint32_t wtot[8];
+    __shared__ uint32_t Hs[HIST_SMEM_PAIRS];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint8_t *in = J.in;
+    const uint32_t n = J.in_size;
+    for (int j = tid; j < 8 * 256; j += HIST_THREADS) (&Fw[0][0])[j] = 0;
+    __syncthreads();
+    uint32_t head = (uint32_t)((16 - ((uintptr_t)in & 15)) & 15);
+    if (head > n) head = n;
+    const uint8_t *p = in + head;
+    const uint32_t rest = n - head, nv = rest >> 4;
+    const uint4 *v = (const uint4 *)p;
+    {
+        uint32_t *F = Fw[wid];
+        if ((uint32_t)tid < head) atomicAdd(&F[in[tid]], 1u);
+        uint32_t i = tid;
+        for (; i + 3 * HIST_THREADS < nv; i += 4 * HIST_THREADS) {
+            uint4 q0 = ldg_u128(v + i), q1 = ldg_u128(v + i + HIST_THREADS),
+                  q2 = ldg_u128(v + i + 2 * HIST_THREADS), q3 = ldg_u128(v + i + 3 * HIST_THREADS);
+            hist16(q0, F); hist16(q1, F); hist16(q2, F); hist16(q3, F);
+        }
+        for (; i < nv; i += HIST_THREADS) hist16(ldg_u128(v + i), F);
+        for (uint32_t t = (nv << 4) + tid; t < rest; t += HIST_THREADS) atomicAdd(&F[p[t]], 1u);
+    }
+    __syncthreads();
+    uint32_t f = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) f += Fw[w][tid];
+    model[tid] = f;
+    const bool o1 = (J.order & 1) && n >= 8;
+    if (!o1) return;                                  // uniform per CTA
+    // ---- alphabet ranks (symbol 0 is always a member)
+    const bool pres = f != 0 || tid == 0;
+    uint32_t bal = __ballot_sync(FULL, pres);
+    if (lane == 0) wtot[wid] = __popc(bal);
+    __syncthreads();
+    uint32_t before = 0, nsym = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { uint32_t c = wtot[w]; if (w < wid) before += c; nsym += c; }
+    rank[tid] = (uint8_t)(before + __popc(bal & lanemask_lt()));
+    if (tid == 0) model[256] = nsym;
+    const uint32_t hw = nsym * nsym;
+    uint32_t *gH = model + MODEL_HDR_WORDS;
+    const bool in_smem = hw <= HIST_SMEM_PAIRS;
+    uint32_t *H = in_smem ? Hs : gH;
+    for (uint32_t j = tid; j < hw; j += HIST_THREADS) H[j] = 0;
+    __syncthreads();
+    // ---- pairs: H[rank(prev)][rank(cur)], the first byte follows symbol 0 (utils.h:279-357)
+    if ((uint32_t)tid < head) {
+        uint32_t prev = tid ? in[tid - 1] : 0;
+        atomicAdd(&H[rank[prev] * nsym + rank[in[tid]]], 1u);
+    }
+    for (uint32_t i = tid; i < nv; i += HIST_THREADS) {
+        uint4 q = ldg_u128(v + i);
+        uint32_t pb = (i || head) ? p[16 * (size_t)i - 1] : 0;
+        uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+        uint32_t rp = rank[pb], last = 0xffffffffu, cnt = 0;
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                uint32_t rc = rank[(w4[a] >> (8 * b)) & 0xff];
+                uint32_t idx = rp * nsym + rc;
+                if (idx == last) cnt++;
+                else { if (cnt) atomicAdd(&H[last], cnt); last = idx; cnt = 1; }
+                rp = rc;
+            }
+        atomicAdd(&H[last], cnt);
+    }
+    for (uint32_t t = (nv << 4) + tid; t < rest; t += HIST_THREADS) {
+        uint32_t pos = head + t;
+        uint32_t prev = pos ? in[pos - 1] : 0;
+        atomicAdd(&H[rank[prev] * nsym + rank[in[pos]]], 1u);
+    }
+    if (in_smem) {
+        __syncthreads();
+        for (uint32_t j = tid; j < hw; j += HIST_THREADS) gH[j] = Hs[j];
+    }
+}
+
+cudaError_t launch_hist(EncJob *d_jobs, uint32_t n, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    hist_kernel<<<n, HIST_THREADS, 0, st>>>(d_jobs, n);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------ launchers

@@ -16,6 +16,7 @@ constexpr uint32_t ENC_SMEM_O1 = 36864;    // EncO1Smem header + pair counts + 1
 constexpr uint32_t DEC_SMEM_O0 = 6144;     // DecO0Smem
 constexpr uint32_t DEC_SMEM_O1 = 20480;    // DecO1Smem header + (start,freq) pairs + 256-bucket index for <= 41 symbols
 
+cudaError_t launch_hist(EncJob *d_jobs, uint32_t n, cudaStream_t st);
 cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStream_t st);
 cudaError_t launch_dec(DecJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStream_t st);
 cudaError_t launch_pack(const EncJob *d_jobs, uint32_t n, uint64_t *d_off, uint32_t *d_size,

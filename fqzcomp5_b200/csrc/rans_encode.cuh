@@ -240,12 +240,16 @@ struct __align__(16) EncO0Smem {
 // `out_end` (backwards).  Returns 0 ok; *tab_len, *ptr_out give the two pieces.
 template <int N>
 __device__ int enc_o0(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_end,
-                      uint32_t *tab_len, uint8_t **ptr_out, EncO0Smem &S, int lane) {
+                      uint32_t *tab_len, uint8_t **ptr_out, EncO0Smem &S, int lane,
+                      const uint32_t *model = nullptr) {
     uint8_t *ptr = out_end;
     *tab_len = 0;
     *ptr_out = ptr;
     if (n == 0) return 0;
-    warp_hist8(in, n, S.F, lane);
+    if (model) {                          // counts from hist_kernel (kernels.cu)
+        for (int j = lane; j < 256; j += 32) S.F[j] = model[j];
+        __syncwarp();
+    } else warp_hist8(in, n, S.F, lane);
 
     uint32_t fsum = round2(n);
     if (fsum > 4096) fsum = 4096;
@@ -356,14 +360,17 @@ __device__ inline uint32_t put_freq_row(uint8_t *cp, const uint32_t *F, uint32_t
 template <int N>
 __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_end,
                       uint32_t *tab_len, uint8_t **ptr_out, EncO1Smem &S, uint8_t *dyn, uint32_t dyn_bytes,
-                      const Pool &pool, int lane) {
+                      const Pool &pool, int lane, const uint32_t *model = nullptr) {
     *tab_len = 0;
     *ptr_out = out_end;
     if (N == 32 && n < 32) return 1;
     const uint32_t seg = n / N;
 
     // ---- alphabet = symbols present, plus 0 (rANS_static16_int.h:357-361)
-    warp_hist8(in, n, S.T, lane);
+    if (model) {                          // counts and pair counts from hist_kernel (kernels.cu)
+        for (int j = lane; j < 256; j += 32) S.T[j] = model[j];
+        __syncwarp();
+    } else warp_hist8(in, n, S.T, lane);
     uint32_t nsym;
     {
         uint32_t loc = 0;
@@ -398,9 +405,13 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
     EncO0Smem *o0s = (EncO0Smem *)dyn;           // H is dead by the time the table is coded
     if (h_smem) H = (uint32_t *)dyn;
     else { H = (uint32_t *)pool_alloc(pool, hw * 4, lane); if (!H) return 2; }
-    for (uint32_t j = lane; j < hw; j += 32) H[j] = 0;
-    __syncwarp();
-    {
+    if (model) {
+        const uint32_t *mh = model + MODEL_HDR_WORDS;
+        for (uint32_t j = lane; j < hw; j += 32) H[j] = mh[j];
+        __syncwarp();
+    } else {
+        for (uint32_t j = lane; j < hw; j += 32) H[j] = 0;
+        __syncwarp();
         const uint8_t *rank = S.rank;
         uint32_t head = (uint32_t)((16 - ((uintptr_t)in & 15)) & 15);
         if (head > n) head = n;
