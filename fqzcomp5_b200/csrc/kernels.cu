@@ -2,6 +2,7 @@
 // rans_compress_to_4x16 / rans_uncompress_to_4x16 (rANS_static4x16pr.c:1224-1894)
 // around the coders in rans_encode.cuh / rans_decode.cuh, plus the size scan and
 // the gather that packs finished streams back to back.
+#include <stdlib.h>
 #include "kernels.h"
 #include "rans_decode.cuh"
 #include "rans_encode.cuh"
@@ -499,6 +500,10 @@ static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStream_t st) {
     if (!n) return cudaSuccess;
     uint32_t ws = o1 ? ENC_SMEM_O1 : ENC_SMEM_O0;
+    if (o1) {                              // tuning knob: shared memory per order-1 stream
+        static const char *e = getenv("B200RANS_ENC_O1_SMEM");
+        if (e && atoi(e) >= 8192 && atoi(e) <= 100000) ws = (uint32_t)atoi(e) & ~15u;
+    }
     size_t sm = (size_t)ws * (o1 ? ENC_WARPS_O1 : ENC_WARPS);
     if (o1) {
         cudaFuncSetAttribute(enc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -513,6 +518,10 @@ cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStrea
 cudaError_t launch_dec(DecJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStream_t st) {
     if (!n) return cudaSuccess;
     uint32_t ws = o1 ? DEC_SMEM_O1 : DEC_SMEM_O0;
+    if (o1) {                              // tuning knob: shared memory per order-1 stream
+        static const char *e = getenv("B200RANS_DEC_O1_SMEM");
+        if (e && atoi(e) >= 8192 && atoi(e) <= 100000) ws = (uint32_t)atoi(e) & ~15u;
+    }
     size_t sm = (size_t)ws * (o1 ? DEC_WARPS_O1 : DEC_WARPS);
     if (o1) {
         cudaFuncSetAttribute(dec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);

@@ -12,9 +12,9 @@ constexpr int DEC_WARPS = 4;
 constexpr int DEC_WARPS_O1 = 2;
 // shared memory per warp (bytes)
 constexpr uint32_t ENC_SMEM_O0 = 5120;     // EncO0Smem
-constexpr uint32_t ENC_SMEM_O1 = 36864;    // EncO1Smem header + pair counts + 16-byte encoder symbols for <= 41 symbols
+constexpr uint32_t ENC_SMEM_O1 = 16896;    // EncO1Smem header + 8-byte encoder symbols for <= 41 symbols
 constexpr uint32_t DEC_SMEM_O0 = 6144;     // DecO0Smem
-constexpr uint32_t DEC_SMEM_O1 = 20480;    // DecO1Smem header + (start,freq) pairs + 256-bucket index for <= 41 symbols
+constexpr uint32_t DEC_SMEM_O1 = 15104;    // DecO1Smem header + 16-bit cumulative rows + 256-bucket index for <= 41 symbols
 
 cudaError_t launch_hist(EncJob *d_jobs, uint32_t n, cudaStream_t st);
 cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStream_t st);

@@ -314,11 +314,12 @@ __device__ int dec_o0(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
 
 // ======================================================================== o1
 // Tables live in rank space: only symbols of the alphabet get rows/columns.
-//   fs[ctx][r]   = start | freq<<16 of the r-th listed symbol in context ctx
+//   cum[ctx][r]  = first slot of the r-th listed symbol in context ctx (r = 0..nsym; 16 bit,
+//                  the last entry is the total), so freq = cum[r+1]-cum[r]
 //   blut[ctx][b] = rank of the symbol owning slot b<<(shift-6)
-// A look-up is blut -> fs[r], stepping r forward while slot >= start+freq.
+// A look-up is blut -> cum[r], cum[r+1], stepping r forward while slot >= cum[r+1].
 struct DecO1Tabs {
-    uint32_t *fs;       // [nsym][nsym]
+    uint16_t *cum;      // [nsym][nsym+1]
     uint8_t  *blut;     // [nsym][1 << bb]
     uint8_t  *sym;      // [nsym] rank -> symbol
     uint32_t  nsym;
@@ -327,7 +328,7 @@ struct DecO1Tabs {
 // a look-up rarely has to step over more than one symbol (the scan is paid by the
 // whole warp for its slowest lane).
 __host__ __device__ inline uint32_t dec_o1_tab_bytes(uint32_t nsym, uint32_t bb) {
-    return nsym * nsym * 4 + (nsym << bb) + ((nsym + 15) & ~15u);
+    return ((nsym * (nsym + 1) * 2 + 15) & ~15u) + (nsym << bb) + ((nsym + 15) & ~15u);
 }
 
 // one order-1 row (rANS_static16_int.h:425-456), single thread.  A[] lists the
@@ -364,7 +365,7 @@ __device__ __forceinline__ void dec_o1_fast(uint32_t &R_, uint32_t &ctx_, uint32
                                             uint32_t sym_s, uint32_t ns, uint32_t shift, uint32_t bb,
                                             int lane, uint32_t lt) {
     uint32_t R = R_, ctx = ctx_, k = k_, pos = w.pos;
-    const uint32_t mask = (1u << shift) - 1, bw = shift - bb, ns4 = ns * 4;
+    const uint32_t mask = (1u << shift) - 1, bw = shift - bb, rs2 = (ns + 1) * 2;
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(w.ring);
     while (k + 16 <= seg && pos + 16 * 64 <= w.end) {
         uint32_t acc[4] = {0, 0, 0, 0};
@@ -376,10 +377,10 @@ __device__ __forceinline__ void dec_o1_fast(uint32_t &R_, uint32_t &ctx_, uint32
             for (int u = 0; u < 4; u++) {
                 uint32_t m = R & mask;
                 uint32_t r = lds_u8a(blut_s + (ctx << bb) + (m >> bw));
-                uint32_t rowa = fs_s + ctx * ns4;
-                uint32_t e = lds_u32a(rowa + r * 4);
-                while (m - (e & 0xffff) >= (e >> 16) && r + 1 < ns) { r++; e = lds_u32a(rowa + r * 4); }
-                R = (e >> 16) * (R >> shift) + m - (e & 0xffff);
+                uint32_t ea = fs_s + ctx * rs2 + r * 2;
+                uint32_t c0 = lds_u16a(ea), c1 = lds_u16a(ea + 2);
+                while (m >= c1 && r + 1 < ns) { r++; ea += 2; c0 = c1; c1 = lds_u16a(ea + 2); }
+                R = (c1 - c0) * (R >> shift) + m - c0;
                 ctx = r;
                 acc[g] |= lds_u8a(sym_s + r) << (8 * u);
                 bool need = R < RANS_L;
@@ -404,8 +405,10 @@ __device__ __forceinline__ void dec_o1_fast(uint32_t &R_, uint32_t &ctx_, uint32
 }
 
 struct __align__(16) DecO1Smem {
-    uint8_t  ring[RING];
-    uint32_t F0[256];           // alphabet marks / scratch
+    union {                     // the alphabet marks are dead before the word ring is filled
+        uint8_t  ring[RING];
+        uint32_t F0[256];
+    };
     uint8_t  rank[256];
 };                              // followed by dynamic table storage (DecO1Tabs) when it fits
 
@@ -470,34 +473,63 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
     const bool in_smem = need <= smem_tab_bytes;
     if (in_smem) tb = smem_tabs;
     else { tb = pool_alloc(pool, need, lane); if (!tb) return 2; }
-    T.fs = (uint32_t *)tb;
-    T.blut = tb + nsym * nsym * 4;
+    const uint32_t ns1 = nsym + 1;
+    T.cum = (uint16_t *)tb;
+    T.blut = tb + ((nsym * ns1 * 2 + 15) & ~15u);
     T.sym = T.blut + (nsym << bb);
     for (int j = lane; j < 256; j += 32)          // presence from F0: rank 255 is a valid rank
         if (S.F0[j]) T.sym[S.rank[j]] = (uint8_t)j;
 
-    // --- rows, in alphabet order (rANS_static16_int.h:488-530); serial varint parse
+    // --- rows, in alphabet order (rANS_static16_int.h:488-530).  The byte stream can
+    // only be walked serially (lane 0, raw counts into fs[]); scaling, cumulative
+    // starts and validation of each row then run one lane per row.
     int err = 0;
     if (lane == 0) {
         for (uint32_t i = 0; i < nsym && !err; i++) {
-            uint32_t *row = T.fs + i * nsym, tsum = 0;
-            int c = get_freq_row(cp, tend, nsym, row, &tsum);
-            if (!c) { err = 1; break; }
-            cp += c;
-            if (!tsum) { for (uint32_t r = 0; r < nsym; r++) row[r] = 0; continue; }
-            int sh = 0;
-            { uint32_t z = tsum; while (z < tot) { z *= 2; sh++; } }   // normalise_freq_shift
-            uint32_t x = 0;
+            uint16_t *row = T.cum + i * ns1;
+            if (cp >= tend) { err = 1; break; }
+            uint32_t zrun = 0;
             for (uint32_t r = 0; r < nsym; r++) {
-                uint32_t f = row[r] << sh;
-                if (row[r] > tot || f > tot - x) { err = 1; break; }
-                row[r] = x | (f << 16);
-                x += f;
+                uint32_t f = 0;
+                if (zrun) zrun--;
+                else if (cp < tend) {
+                    uint32_t c = *cp++;
+                    f = c & 0x7f;
+                    int cnt = 1;
+                    while ((c & 0x80) && cp < tend && cnt < 6) { c = *cp++; f = (f << 7) | (c & 0x7f); cnt++; }
+                    if (f == 0) {
+                        if (cp >= tend) { err = 1; break; }
+                        zrun = *cp++;
+                    }
+                }
+                if (f > tot) { err = 1; break; }
+                row[r + 1] = (uint16_t)f;
             }
-            if (!err && x != tot) err = 1;
         }
     }
     err = __shfl_sync(FULL, err, 0);
+    if (err) return 1;
+    __syncwarp();
+    for (uint32_t i0 = 0; i0 < nsym; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        if (i < nsym) {
+            uint16_t *row = T.cum + i * ns1;
+            uint32_t tsum = 0;
+            for (uint32_t r = 0; r < nsym; r++) tsum += row[r + 1];
+            int sh = 0;
+            if (tsum) { uint32_t z = tsum; while (z < tot) { z *= 2; sh++; } }   // normalise_freq_shift
+            uint32_t x = 0;
+            for (uint32_t r = 0; r < nsym; r++) {          // in place: raw count of r sits at [r+1]
+                uint32_t f = (uint32_t)row[r + 1] << sh;
+                if (f > tot - x) { err = 1; break; }
+                row[r] = (uint16_t)x;
+                x += f;
+            }
+            row[nsym] = (uint16_t)x;
+            if (!err && tsum && x != tot) err = 1;
+        }
+    }
+    err = __any_sync(FULL, err);
     if (err) return 1;
     {   // only lane 0 walked the table: share where it ended
         const uint8_t *tbase = comp ? tend : in;     // any pointer all lanes agree on
@@ -509,15 +541,12 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
     // --- bucket look-up: lane per row
     const uint32_t bw = shift - bb, nb = 1u << bb;
     for (uint32_t i0 = 0; i0 < nsym; i0 += 32) { const uint32_t i = i0 + lane; if (i >= nsym) continue;
-        const uint32_t *row = T.fs + i * nsym;
+        const uint16_t *row = T.cum + i * ns1;
         uint8_t *bl = T.blut + (i << bb);
-        uint32_t r = 0, e = row[0];
-        bool empty = true;
-        for (uint32_t q = 0; q < nsym; q++) empty &= (row[q] >> 16) == 0;
+        uint32_t r = 0;
         for (uint32_t b = 0; b < nb; b++) {
             uint32_t m = b << bw;
-            if (!empty)
-                while (r + 1 < nsym && m >= (e & 0xffff) + (e >> 16)) e = row[++r];
+            while (r + 1 < nsym && m >= row[r + 1]) r++;
             bl[b] = (uint8_t)r;
         }
     }
@@ -534,30 +563,31 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
 #ifdef B200_DEBUG
     if (lane == 0) {
         printf("dec_o1<%d> in_size=%u out_sz=%u shift=%u comp=%d nsym=%u in_smem=%d cpoff=%ld R0=%x\n", N, in_size, out_sz, shift, (int)comp, nsym, (int)in_smem, (long)(cp - in), R);
-        for (uint32_t i = 0; i < nsym && i < 4; i++) { printf(" row%u:", i); for (uint32_t r = 0; r < nsym && r < 8; r++) printf(" %u+%u", T.fs[i*nsym+r] & 0xffff, T.fs[i*nsym+r] >> 16); printf(" | blut"); for (int b = 0; b < 8; b++) printf(" %u", T.blut[i*64+b*8]); printf(" sym %u\n", T.sym[i]); }
+        for (uint32_t i = 0; i < nsym && i < 4; i++) { printf(" row%u:", i); for (uint32_t r = 0; r < nsym && r < 8; r++) printf(" %u", T.cum[i*ns1+r]); printf(" | blut"); for (int b = 0; b < 8; b++) printf(" %u", T.blut[i*64+b*8]); printf(" sym %u\n", T.sym[i]); }
     }
 #endif
     WordRing w;
-    w.init(in, (uint32_t)(cp - in) + 4 * N, in_size, S.ring, lane);
+    if (!S.F0[0]) return 1;                 // symbol 0 is always listed by the encoder
+    __syncwarp();
+    w.init(in, (uint32_t)(cp - in) + 4 * N, in_size, S.ring, lane);      // overwrites F0
     __threadfence_block();
     __syncwarp();
     const uint32_t lt = lanemask_lt();
     const uint32_t seg = out_sz / N, mask = tot - 1;
     uint8_t *o = out + (size_t)lane * seg;
     uint32_t ctx = S.rank[0];               // every lane starts in context 0
-    if (!S.F0[0]) return 1;                 // symbol 0 is always listed by the encoder
-    const uint32_t *fs = T.fs;
+    const uint16_t *cumt = T.cum;
     const uint8_t *blut = T.blut, *symtab = T.sym;
     const uint32_t ns = nsym;
 
     auto step = [&](bool on) {
         uint32_t m = R & mask;
         uint32_t r = blut[(ctx << bb) + (m >> bw)];
-        const uint32_t *row = fs + ctx * ns;
-        uint32_t e = row[r];
-        while (m - (e & 0xffff) >= (e >> 16) && r + 1 < ns) e = row[++r];   // unsigned: m >= start always
+        const uint16_t *row = cumt + ctx * (ns + 1);
+        uint32_t c0 = row[r], c1 = row[r + 1];
+        while (m >= c1 && r + 1 < ns) { r++; c0 = c1; c1 = row[r + 1]; }
         if (on) {
-            R = (e >> 16) * (R >> shift) + m - (e & 0xffff);
+            R = (c1 - c0) * (R >> shift) + m - c0;
             ctx = r;
         }
         return (uint8_t)symtab[r];
@@ -565,7 +595,7 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
 
     uint32_t k = 0;
     if (N == 32 && in_smem && ((((uintptr_t)out) | seg) & 15) == 0) {
-        const uint32_t fs_s = (uint32_t)__cvta_generic_to_shared(T.fs);
+        const uint32_t fs_s = (uint32_t)__cvta_generic_to_shared(T.cum);
         const uint32_t bl_s = (uint32_t)__cvta_generic_to_shared(T.blut);
         const uint32_t sy_s = (uint32_t)__cvta_generic_to_shared(T.sym);
         __syncwarp();

@@ -202,6 +202,22 @@ __device__ __forceinline__ uint4 enc_sym_init(uint32_t start, uint32_t freq, uin
     return s;
 }
 
+// Compact 8-byte form for the order-1 tables (nsym^2 entries per stream):
+//   x = rcp_freq, y = bias | freq<<13 | (rcp_shift-32)<<26.  x_max and cmpl_freq follow from
+// freq and the stream's precision, so shared memory holds twice as many streams.
+__device__ __forceinline__ uint2 enc_sym_pack(uint4 s, uint32_t freq) {
+    return make_uint2(s.y, s.z | (freq << 13) | ((s.w >> 16) << 26));
+}
+__device__ __forceinline__ uint4 enc_sym_unpack(uint2 c, uint32_t bits) {
+    uint32_t f = (c.y >> 13) & 0x1fff;
+    uint4 s;
+    s.x = (f << (31 - bits)) - 1;
+    s.y = c.x;
+    s.z = c.y & 0x1fff;
+    s.w = (((1u << bits) - f) & 0xffff) | ((c.y >> 26) << 16);
+    return s;
+}
+
 // One encode step for the warp (rANS_word.h:287-336 + the lane order of
 // rANS_static32x16pr.c:187-231): lanes whose state exceeds x_max emit their low
 // 16 bits; lane 31's word lands at the highest address.  ptr moves down.
@@ -395,21 +411,21 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
     __syncwarp();
 
     // ---- pair counts H[rank(prev)][rank(cur)], first symbol follows 0 (utils.h:279-357)
-    // Dynamic shared memory of this warp: [pair counts H, later scratch of the table coder]
-    // [encoder symbols], whatever fits; the rest comes from the scratch pool.
+    // Pair counts H: with counts from hist_kernel they are used in place in global memory (L2)
+    // and the dynamic shared memory holds only the encoder symbols (the table coder's scratch
+    // aliases it, it runs before they are built).  Otherwise H sits in shared memory in front
+    // of the symbols when it fits, else in the scratch pool.
     uint32_t *H;
     const uint32_t hw = nsym * nsym;
-    const uint32_t h_bytes = max((hw * 4 + 15) & ~15u, (uint32_t)sizeof(EncO0Smem));
-    const bool h_smem = h_bytes <= dyn_bytes;
-    const bool sym_smem = h_smem && h_bytes + hw * 16 <= dyn_bytes;
-    EncO0Smem *o0s = (EncO0Smem *)dyn;           // H is dead by the time the table is coded
-    if (h_smem) H = (uint32_t *)dyn;
+    const bool h_global = model != nullptr;
+    const uint32_t h_bytes = h_global ? 0 : max((hw * 4 + 15) & ~15u, (uint32_t)sizeof(EncO0Smem));
+    const bool h_smem = !h_global && h_bytes <= dyn_bytes;
+    const bool sym_smem = (h_global || h_smem) && h_bytes + hw * 8 <= dyn_bytes;
+    EncO0Smem *o0s = (EncO0Smem *)dyn;           // dead H, or not-yet-built symbols
+    if (h_global) H = const_cast<uint32_t *>(model) + MODEL_HDR_WORDS;
+    else if (h_smem) H = (uint32_t *)dyn;
     else { H = (uint32_t *)pool_alloc(pool, hw * 4, lane); if (!H) return 2; }
-    if (model) {
-        const uint32_t *mh = model + MODEL_HDR_WORDS;
-        for (uint32_t j = lane; j < hw; j += 32) H[j] = mh[j];
-        __syncwarp();
-    } else {
+    if (!model) {
         for (uint32_t j = lane; j < hw; j += 32) H[j] = 0;
         __syncwarp();
         const uint8_t *rank = S.rank;
@@ -509,9 +525,9 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
     const uint32_t shift = (e10 / e12 < 1.01 || max_tot <= 1024) ? 10 : 12;
 
     // ---- rows: normalise to the stored total, measure, serialise, scale, symbols
-    uint4 *symtab;
-    if (sym_smem) symtab = (uint4 *)(dyn + h_bytes);
-    else { symtab = (uint4 *)pool_alloc(pool, hw * 16, lane); if (!symtab) return 2; }
+    uint2 *symtab;
+    if (sym_smem) symtab = (uint2 *)(dyn + h_bytes);
+    else { symtab = (uint2 *)pool_alloc(pool, hw * 8, lane); if (!symtab) return 2; }
     int err = 0;
     for (uint32_t i0 = 0; i0 < nsym; i0 += 32) { const uint32_t i = i0 + lane; if (i >= nsym) continue;
         uint32_t *row = H + i * nsym;
@@ -556,28 +572,20 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
     uint32_t tl = __shfl_sync(FULL, hdr, 0);
     __syncwarp();
     for (uint32_t i0 = 0; i0 < nsym; i0 += 32) { const uint32_t i = i0 + lane; if (i >= nsym) continue;
-        uint32_t *row = H + i * nsym;
-        if (!S.T[i]) continue;
-        put_freq_row(out + S.rowlen[i], row, nsym);
-        uint32_t mv = S.S[i];
-        int sh = 0;
-        while ((mv << sh) < (1u << shift)) sh++;
-        uint32_t x = 0;
-        for (uint32_t j = 0; j < nsym; j++) {
-            uint32_t f = row[j] << sh;
-            symtab[i * nsym + j] = enc_sym_init(x, f, shift);
-            x += f;
-        }
+        if (S.T[i]) put_freq_row(out + S.rowlen[i], H + i * nsym, nsym);
     }
     __threadfence_block();
     __syncwarp();
-
     out[0] = (uint8_t)(shift << 4);
-    if (tl > 1000) {                          // try the 4-lane o0 coder on the table (:396-412)
+
+    // the table, once complete, may itself go through the 4-lane order-0 coder (:396-412)
+    int pool_fail = 0;
+    auto compress_table = [&]() {
+        if (tl <= 1000) return;
         uint32_t usz = tl - 1;
         uint32_t cb = compress_bound(usz, 0) - 20;
         uint8_t *tmp = pool_alloc(pool, cb + 16, lane);
-        if (!tmp) return 2;
+        if (!tmp) { pool_fail = 1; return; }
         uint32_t ctab = 0;
         uint8_t *cptr = nullptr;
         __syncwarp();
@@ -599,7 +607,25 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
             }
         }
         __syncwarp();
+    };
+    if (h_global) compress_table();               // its scratch aliases the symbol area
+    for (uint32_t i0 = 0; i0 < nsym; i0 += 32) { const uint32_t i = i0 + lane; if (i >= nsym) continue;
+        uint32_t *row = H + i * nsym;
+        if (!S.T[i]) continue;
+        uint32_t mv = S.S[i];
+        int sh = 0;
+        while ((mv << sh) < (1u << shift)) sh++;
+        uint32_t x = 0;
+        for (uint32_t j = 0; j < nsym; j++) {
+            uint32_t f = row[j] << sh;
+            symtab[i * nsym + j] = enc_sym_pack(enc_sym_init(x, f, shift), f);
+            x += f;
+        }
     }
+    __threadfence_block();
+    __syncwarp();
+    if (!h_global) compress_table();              // its scratch aliases the (now dead) pair counts
+    if (pool_fail) return 2;
     *tab_len = tl;
 
     // ---- encode.  Lane z owns [z*seg,(z+1)*seg); lane N-1 also the tail; every
@@ -612,7 +638,7 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
         const bool lastl = lane == N - 1;
         for (uint32_t p = n - 1; p >= N * seg && p > 0; p--) {
             uint4 e = make_uint4(0, 0, 0, 0);
-            if (lastl) e = symtab[rank[in[p - 1]] * nsym + rank[in[p]]];
+            if (lastl) e = enc_sym_unpack(symtab[rank[in[p - 1]] * nsym + rank[in[p]]], shift);
             R = enc_step(R, lastl, e, ptr, lane);
         }
     }
@@ -632,10 +658,10 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
             uint32_t w = b < 4 ? x.x : b < 8 ? x.y : b < 12 ? x.z : x.w;
             return (w >> (8 * (b & 3))) & 0xff;
         };
-        auto lds128 = [](uint32_t a) {
-            uint4 r;
-            asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
-            return r;
+        auto lds_sym = [&](uint32_t a) {
+            uint2 r;
+            asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a));
+            return enc_sym_unpack(r, shift);
         };
         auto rank_of = [&](uint32_t b) {
             uint32_t r;
@@ -648,7 +674,7 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
             for (int b = 15; b >= 0; b--) {
                 uint32_t cb = b ? byte_of(cur, b - 1) : byte_of(nxt, 15);
                 uint32_t rc = rank_of(cb);
-                uint4 e = lds128(sym_s + (rc * nsym + rs) * 16);
+                uint4 e = lds_sym(sym_s + (rc * nsym + rs) * 8);
                 R = enc_step(R, true, e, ptr, lane);
                 rs = rc;
             }
@@ -658,7 +684,7 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
 #pragma unroll
         for (int b = 15; b >= 1; b--) {                      // group 0: its byte 0 is the lane's first symbol
             uint32_t rc = rank_of(byte_of(cur, b - 1));
-            uint4 e = lds128(sym_s + (rc * nsym + rs) * 16);
+            uint4 e = lds_sym(sym_s + (rc * nsym + rs) * 8);
             R = enc_step(R, true, e, ptr, lane);
             rs = rc;
         }
@@ -666,12 +692,12 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
     }
     for (uint32_t k = kstart; k-- > 1;) {
         uint32_t rc = rank[q[k - 1]];
-        uint4 e = symtab[rc * nsym + rs];
+        uint4 e = enc_sym_unpack(symtab[rc * nsym + rs], shift);
         R = enc_step(R, act, e, ptr, lane);
         rs = rc;
     }
     if (seg) {
-        uint4 e = symtab[rank[0] * nsym + rs];
+        uint4 e = enc_sym_unpack(symtab[rank[0] * nsym + rs], shift);
         R = enc_step(R, act, e, ptr, lane);
     }
     enc_flush(R, act, N, ptr, lane);
