@@ -11,8 +11,8 @@ constexpr int ENC_WARPS_O1 = 2;
 constexpr int DEC_WARPS = 4;
 constexpr int DEC_WARPS_O1 = 2;
 // shared memory per warp (bytes)
-constexpr uint32_t ENC_SMEM_O0 = 5120;     // EncO0Smem
-constexpr uint32_t ENC_SMEM_O1 = 16896;    // EncO1Smem header + 8-byte encoder symbols for <= 41 symbols
+constexpr uint32_t ENC_SMEM_O0 = 6144;     // EncO0Smem: ring + 256 encoder symbols + histogram
+constexpr uint32_t ENC_SMEM_O1 = 18432;    // EncO1Smem header + 8-byte encoder symbols for <= 41 symbols
 constexpr uint32_t DEC_SMEM_O0 = 6144;     // DecO0Smem
 constexpr uint32_t DEC_SMEM_O1 = 15104;    // DecO1Smem header + 16-bit cumulative rows + 256-bucket index for <= 41 symbols
 

@@ -31,6 +31,9 @@ __device__ __forceinline__ uint4 ldg_u128(const uint4 *p) {
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(__cvta_generic_to_global(p)));
     return v;
 }
+// 16 bytes into shared-memory bins; equal neighbours are merged before an atomic is
+// issued (quality strings are sticky).  (A word-level "four equal bytes" shortcut was
+// measured slower: the two paths diverge within the warp.)
 __device__ __forceinline__ void hist16(uint4 q, uint32_t *F) {
     uint32_t w[4] = {q.x, q.y, q.z, q.w};
     uint32_t prev = w[0] & 0xff, cnt = 0;
@@ -218,18 +221,81 @@ __device__ __forceinline__ uint4 enc_sym_unpack(uint2 c, uint32_t bits) {
     return s;
 }
 
+// ------------------------------------------------------------------------
+// Output staging.  The encoder's 16-bit words (and the final states) are written
+// DOWNWARD; one step emits up to 64 bytes in lane order.  They are collected in a
+// 1 KiB shared-memory ring indexed by the low bits of the offset within the
+// (256-byte aligned) slot and leave for global memory as aligned 16-byte stores,
+// 512 bytes at a time, instead of millions of scattered 2-byte stores.
+// ------------------------------------------------------------------------
+constexpr uint32_t ORING = 1024;
+struct OutRing {
+    uint8_t *slot;       // slot base (global, 256-byte aligned)
+    uint32_t ring_s;     // shared-space address of the ring (16-byte aligned)
+    uint32_t off;        // next byte to write is off-1 (downward), offset from slot
+    uint32_t hi;         // bytes [off, hi) are still in the ring; hi is a multiple of 16
+
+    // lo: any address at or below everything that will be written; out_end: even address
+    // where writing starts (downward).  Up to 15 bytes above out_end may be overwritten
+    // when out_end is not 16-byte aligned (callers leave that slack).
+    __device__ __forceinline__ void init(uint8_t *lo, uint8_t *out_end, uint8_t *ring) {
+        slot = (uint8_t *)((uintptr_t)lo & ~(uintptr_t)255);
+        ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+        off = (uint32_t)(out_end - slot);
+        hi = (off + 15) & ~15u;
+    }
+    // flush the highest 512-byte block(s) while more than 512 bytes are pending
+    __device__ __forceinline__ void maybe_flush(int lane) {
+        while (hi - off > 512) {
+            uint32_t c = (hi - 1) & ~511u;
+            __syncwarp();
+            uint32_t o = c + 16 * lane;
+            if (o < hi) {
+                uint4 v;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ring_s + (o & (ORING - 1))));
+                asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(__cvta_generic_to_global(slot + o)),
+                             "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+            }
+            __syncwarp();
+            hi = c;
+        }
+    }
+    // everything that is left: [off, hi)
+    __device__ __forceinline__ void final_flush(int lane) {
+        __syncwarp();
+        uint32_t a = (off + 15) & ~15u;     // first 16-byte aligned offset
+        if (a > hi) a = hi;
+        for (uint32_t o = off + 2 * lane; o < a; o += 64) {          // leading 2-byte pieces (off is even)
+            uint32_t v;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(ring_s + (o & (ORING - 1))));
+            *(uint16_t *)(slot + o) = (uint16_t)v;
+        }
+        for (uint32_t o = a + 16 * lane; o < hi; o += 512) {
+            uint4 v;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ring_s + (o & (ORING - 1))));
+            asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(__cvta_generic_to_global(slot + o)),
+                         "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        }
+        hi = off;
+        __syncwarp();
+    }
+};
+
 // One encode step for the warp (rANS_word.h:287-336 + the lane order of
 // rANS_static32x16pr.c:187-231): lanes whose state exceeds x_max emit their low
-// 16 bits; lane 31's word lands at the highest address.  ptr moves down.
-__device__ __forceinline__ uint32_t enc_step(uint32_t R, bool on, uint4 e, uint8_t *&ptr, int lane) {
+// 16 bits; lane 31's word lands at the highest address.  At most 4 steps may
+// pass between two maybe_flush() calls.
+__device__ __forceinline__ uint32_t enc_step(uint32_t R, bool on, uint4 e, OutRing &w, int lane) {
     bool emit = on && R > e.x;
     uint32_t mask = __ballot_sync(FULL, emit);
     if (emit) {
         uint32_t k = __popc(mask >> lane);
-        *(uint16_t *)(ptr - 2 * k) = (uint16_t)R;
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(w.ring_s + ((w.off - 2 * k) & (ORING - 1))), "r"(R) : "memory");
         R >>= 16;
     }
-    ptr -= 2 * __popc(mask);
+    w.off -= 2 * __popc(mask);
     if (on) {
         uint32_t q = __umulhi(R, e.y) >> (e.w >> 16);
         R = R + e.z + q * (e.w & 0xffff);
@@ -237,18 +303,22 @@ __device__ __forceinline__ uint32_t enc_step(uint32_t R, bool on, uint4 e, uint8
     return R;
 }
 
-__device__ __forceinline__ void enc_flush(uint32_t R, bool act, int N, uint8_t *&ptr, int lane) {
-    ptr -= 4 * N;
+// final states, lane 0 lowest (rANS_word.h:105-117); then everything leaves the ring
+__device__ __forceinline__ void enc_flush(uint32_t R, bool act, int N, OutRing &w, int lane) {
+    w.maybe_flush(lane);
+    w.off -= 4 * N;
     if (act) {
-        uint16_t *p = (uint16_t *)(ptr + 4 * lane);       // ptr is 2-byte aligned only
-        p[0] = (uint16_t)R;
-        p[1] = (uint16_t)(R >> 16);
+        uint32_t a = w.off + 4 * lane;       // off is 2-byte aligned only
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(w.ring_s + (a & (ORING - 1))), "r"(R) : "memory");
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(w.ring_s + ((a + 2) & (ORING - 1))), "r"(R >> 16) : "memory");
     }
+    w.final_flush(lane);
 }
 
 // ======================================================================== o0
 struct __align__(16) EncO0Smem {
-    uint4    sym[256];
+    uint8_t  ring[ORING];   // output staging (OutRing)
+    uint4    sym[256];      // encoder symbols (enc_sym_init)
     uint32_t F[256];
 };
 
@@ -258,9 +328,8 @@ template <int N>
 __device__ int enc_o0(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_end,
                       uint32_t *tab_len, uint8_t **ptr_out, EncO0Smem &S, int lane,
                       const uint32_t *model = nullptr) {
-    uint8_t *ptr = out_end;
     *tab_len = 0;
-    *ptr_out = ptr;
+    *ptr_out = out_end;
     if (n == 0) return 0;
     if (model) {                          // counts from hist_kernel (kernels.cu)
         for (int j = lane; j < 256; j += 32) S.F[j] = model[j];
@@ -297,43 +366,51 @@ __device__ int enc_o0(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
 
     // NB every lane runs the same ballots: lanes >= N (N == 4) are predicated off.
     const bool act = (N == 32) ? true : lane < N;
+    OutRing w;
+    w.init(out, out_end, S.ring);
     uint32_t R = RANS_L;
     const uint32_t rem = n % N;
     uint32_t i = n - rem;
     if (rem) {                                               // symbols i..n-1 on lanes 0..rem-1
         bool on = (uint32_t)lane < rem;
         uint4 e = S.sym[on ? in[i + lane] : 0];
-        R = enc_step(R, on, e, ptr, lane);
+        R = enc_step(R, on, e, w, lane);
     }
     const uint8_t *q = in + (act ? lane : 0);
-    // Symbols are fetched two groups (8 steps) ahead of their use so that the
-    // DRAM latency of a new 128-byte line is off the state chain.
-    uint32_t sA[4] = {0, 0, 0, 0}, sB[4] = {0, 0, 0, 0};
-    if (i >= 4 * N) {
+    // Symbols are fetched three groups (12 steps) ahead of their use, into three register
+    // sets that are refilled right after they are consumed (no register rotation, so no
+    // instruction waits on a load younger than a full trip of this loop): the DRAM latency of
+    // a new 128-byte line stays off the state chain.
+    uint32_t sA[4], sB[4], sC[4];
+    auto fetch = [&](uint32_t (&s4)[4], uint32_t at) {       // symbols of the group ending at `at`
 #pragma unroll
-        for (int u = 0; u < 4; u++) sA[u] = ldg_u8(q + i - (u + 1) * N);
-    }
-    if (i >= 8 * N) {
-#pragma unroll
-        for (int u = 0; u < 4; u++) sB[u] = ldg_u8(q + i - (u + 5) * N);
-    }
-    for (; i >= 4 * N; i -= 4 * N) {
-        uint32_t sC[4] = {0, 0, 0, 0};
-        if (i >= 12 * N) {
-#pragma unroll
-            for (int u = 0; u < 4; u++) sC[u] = ldg_u8(q + i - (u + 9) * N);
+        for (int u = 0; u < 4; u++) s4[u] = ldg_u8(q + at - (u + 1) * N);
+    };
+    auto group = [&](const uint32_t (&s4)[4]) {
+        w.maybe_flush(lane);
+        uint4 e0 = S.sym[s4[0]], e1 = S.sym[s4[1]], e2 = S.sym[s4[2]], e3 = S.sym[s4[3]];
+        R = enc_step(R, act, e0, w, lane);
+        R = enc_step(R, act, e1, w, lane);
+        R = enc_step(R, act, e2, w, lane);
+        R = enc_step(R, act, e3, w, lane);
+    };
+    if (i >= 24 * N) {
+        fetch(sA, i); fetch(sB, i - 4 * N); fetch(sC, i - 8 * N);
+        for (; i >= 24 * N; i -= 12 * N) {
+            group(sA); fetch(sA, i - 12 * N);
+            group(sB); fetch(sB, i - 16 * N);
+            group(sC); fetch(sC, i - 20 * N);
         }
-        uint4 e0 = S.sym[sA[0]], e1 = S.sym[sA[1]], e2 = S.sym[sA[2]], e3 = S.sym[sA[3]];
-        R = enc_step(R, act, e0, ptr, lane);
-        R = enc_step(R, act, e1, ptr, lane);
-        R = enc_step(R, act, e2, ptr, lane);
-        R = enc_step(R, act, e3, ptr, lane);
-#pragma unroll
-        for (int u = 0; u < 4; u++) { sA[u] = sB[u]; sB[u] = sC[u]; }
+        group(sA); group(sB); group(sC);                     // the three groups already in registers
+        i -= 12 * N;
     }
-    for (; i > 0; i -= N) R = enc_step(R, act, S.sym[q[i - N]], ptr, lane);
-    enc_flush(R, act, N, ptr, lane);
-    *ptr_out = ptr;
+    for (; i >= 4 * N; i -= 4 * N) { fetch(sA, i); group(sA); }
+    for (; i > 0; i -= N) {
+        w.maybe_flush(lane);
+        R = enc_step(R, act, S.sym[q[i - N]], w, lane);
+    }
+    enc_flush(R, act, N, w, lane);
+    *ptr_out = w.slot + w.off;
     __syncwarp();
     return 0;
 }
@@ -352,6 +429,7 @@ struct __align__(16) EncO1Smem {
     uint32_t rowlen[256];   // serialised row lengths / offsets (rank space)
     uint32_t pres[8];       // alphabet membership bitmap (symbol space)
     uint32_t pad_[4];
+    uint8_t  ring[ORING];   // output staging (OutRing)
 };                          // followed by dynamic storage: nsym*nsym pair counts when they fit
 
 // serialise one row against the alphabet (rANS_static16_int.h:278-306): every
@@ -631,7 +709,8 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
     // ---- encode.  Lane z owns [z*seg,(z+1)*seg); lane N-1 also the tail; every
     // symbol is coded in the context of its predecessor, lane starts in context 0.
     const bool act = lane < N;
-    uint8_t *ptr = out_end;
+    OutRing w;
+    w.init(out, out_end, S.ring);
     uint32_t R = RANS_L;
     const uint8_t *rank = S.rank;
     {   // tail on lane N-1, from the end down to N*seg
@@ -639,7 +718,8 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
         for (uint32_t p = n - 1; p >= N * seg && p > 0; p--) {
             uint4 e = make_uint4(0, 0, 0, 0);
             if (lastl) e = enc_sym_unpack(symtab[rank[in[p - 1]] * nsym + rank[in[p]]], shift);
-            R = enc_step(R, lastl, e, ptr, lane);
+            w.maybe_flush(lane);
+            R = enc_step(R, lastl, e, w, lane);
         }
     }
     const uint8_t *q = in + (size_t)(act ? lane : 0) * seg;
@@ -675,7 +755,8 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
                 uint32_t cb = b ? byte_of(cur, b - 1) : byte_of(nxt, 15);
                 uint32_t rc = rank_of(cb);
                 uint4 e = lds_sym(sym_s + (rc * nsym + rs) * 8);
-                R = enc_step(R, true, e, ptr, lane);
+                if ((b & 3) == 3) w.maybe_flush(lane);
+                R = enc_step(R, true, e, w, lane);
                 rs = rc;
             }
             cur = nxt;
@@ -685,7 +766,8 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
         for (int b = 15; b >= 1; b--) {                      // group 0: its byte 0 is the lane's first symbol
             uint32_t rc = rank_of(byte_of(cur, b - 1));
             uint4 e = lds_sym(sym_s + (rc * nsym + rs) * 8);
-            R = enc_step(R, true, e, ptr, lane);
+            if ((b & 3) == 3) w.maybe_flush(lane);
+            R = enc_step(R, true, e, w, lane);
             rs = rc;
         }
         kstart = 1;
@@ -693,15 +775,17 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
     for (uint32_t k = kstart; k-- > 1;) {
         uint32_t rc = rank[q[k - 1]];
         uint4 e = enc_sym_unpack(symtab[rc * nsym + rs], shift);
-        R = enc_step(R, act, e, ptr, lane);
+        w.maybe_flush(lane);
+        R = enc_step(R, act, e, w, lane);
         rs = rc;
     }
     if (seg) {
         uint4 e = enc_sym_unpack(symtab[rank[0] * nsym + rs], shift);
-        R = enc_step(R, act, e, ptr, lane);
+        w.maybe_flush(lane);
+        R = enc_step(R, act, e, w, lane);
     }
-    enc_flush(R, act, N, ptr, lane);
-    *ptr_out = ptr;
+    enc_flush(R, act, N, w, lane);
+    *ptr_out = w.slot + w.off;
     __syncwarp();
     return 0;
 }
