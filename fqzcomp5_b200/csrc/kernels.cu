@@ -302,10 +302,13 @@ __device__ void dec_stream(DecJob &J, uint8_t *smem, uint32_t smem_bytes, const 
 template <bool O1>
 __global__ void __launch_bounds__((O1 ? DEC_WARPS_O1 : DEC_WARPS) * 32)
 dec_kernel(DecJob *jobs, uint32_t njobs, uint32_t warp_smem, Pool pool) {
-    extern __shared__ __align__(16) uint8_t smem_all[];
+    extern __shared__ __align__(8192) uint8_t smem_dec[];
+    uint8_t *smem_all = smem_dec;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t j = blockIdx.x * (O1 ? DEC_WARPS_O1 : DEC_WARPS) + wid;
     if (j >= njobs || jobs[j].route != (O1 ? 1u : 0u)) return;
+    // order-0 blocks are 8 KiB each: when the dynamic shared memory itself starts 8 KiB aligned
+    // (checked at run time in dec_o0) the decoder uses OR-addressing into its tables
     dec_stream<O1>(jobs[j], smem_all + (size_t)wid * warp_smem, warp_smem, pool, lane);
 }
 

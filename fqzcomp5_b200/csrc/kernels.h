@@ -8,12 +8,12 @@ namespace b200 {
 // one warp per stream, several streams per CTA
 constexpr int ENC_WARPS = 4;
 constexpr int ENC_WARPS_O1 = 2;
-constexpr int DEC_WARPS = 4;
+constexpr int DEC_WARPS = 2;
 constexpr int DEC_WARPS_O1 = 2;
 // shared memory per warp (bytes)
 constexpr uint32_t ENC_SMEM_O0 = 6144;     // EncO0Smem: ring + 256 encoder symbols + histogram
 constexpr uint32_t ENC_SMEM_O1 = 18432;    // EncO1Smem header + 8-byte encoder symbols for <= 41 symbols
-constexpr uint32_t DEC_SMEM_O0 = 6144;     // DecO0Smem
+constexpr uint32_t DEC_SMEM_O0 = 8192;     // DecO0Smem, 8 KiB aligned
 constexpr uint32_t DEC_SMEM_O1 = 15104;    // DecO1Smem header + 16-bit cumulative rows + 256-bucket index for <= 41 symbols
 
 cudaError_t launch_hist(EncJob *d_jobs, uint32_t n, cudaStream_t st);

@@ -35,68 +35,76 @@ __device__ inline uint8_t *pool_alloc(const Pool &p, uint32_t bytes, int lane) {
 // chunks), indexed by the low bits of the global address so that alignment is
 // preserved; bytes past the end of the stream are zero-filled, never read.
 // ------------------------------------------------------------------------
-constexpr uint32_t RING = 1024, CHUNK = 256;
+constexpr uint32_t RING = 1024, CHUNK = 256;      // order-1 decoder: 1 KiB ring
 
-struct WordRing {
-    const uint8_t *a0;   // 256-byte aligned global base
-    uint8_t *ring;       // shared memory, RING bytes, 16-byte aligned
+// RS: ring bytes (power of two); refill unit RS/4; `GROUP` steps (64 bytes each at most)
+// may be consumed between two advance_group() calls as long as GROUP*64 <= RS/4.
+template <uint32_t RS>
+struct WordRingT {
+    static constexpr uint32_t CH = RS / 4;
+    const uint8_t *a0;   // CH-byte aligned global base
+    uint8_t *ring;       // shared memory, RS bytes, 16-byte aligned
     uint32_t pos;        // next unread byte, offset from a0
     uint32_t end;        // end of stream, offset from a0
-    uint32_t fe;         // ring holds [fe-RING, fe)
+    uint32_t fe;         // ring holds [fe-RS, fe)
 
     __device__ __forceinline__ void fill_chunk(uint32_t c, int lane) const {
-        if (lane < 16) {
+        if ((uint32_t)lane < CH / 16) {
             uint32_t p = c + lane * 16;
             uint32_t nb = p + 16 <= end ? 16u : (p < end ? end - p : 0u);
-            cp_async16_zfill(ring + (p & (RING - 1)), a0 + p, nb);
+            cp_async16_zfill(ring + (p & (RS - 1)), a0 + p, nb);
         }
     }
     __device__ __forceinline__ void init(const uint8_t *in, uint32_t start, uint32_t in_size,
                                          uint8_t *ring_, int lane) {
         uintptr_t A = (uintptr_t)in;
-        a0 = (const uint8_t *)(A & ~(uintptr_t)(CHUNK - 1));
+        a0 = (const uint8_t *)(A & ~(uintptr_t)(CH - 1));
         uint32_t d = (uint32_t)(A - (uintptr_t)a0);
         ring = ring_;
         pos = d + start;
         end = d + in_size;
-        uint32_t c0 = pos & ~(CHUNK - 1);
+        uint32_t c0 = pos & ~(CH - 1);
         __syncwarp();
-        for (uint32_t c = 0; c < RING; c += CHUNK) fill_chunk(c0 + c, lane);
+        for (uint32_t c = 0; c < RS; c += CH) fill_chunk(c0 + c, lane);
         cp_async_commit();
         cp_async_wait_all();
         __syncwarp();
-        fe = c0 + RING;
+        fe = c0 + RS;
     }
     // Called once per step (a step consumes at most 64 bytes).
     __device__ __forceinline__ void advance(int lane) {
-        if (pos + (RING - CHUNK) >= fe) {
+        if (pos + (RS - CH) >= fe) {
             cp_async_wait_all();       // the chunk issued one refill ago
             __syncwarp();
             fill_chunk(fe, lane);
             cp_async_commit();
-            fe += CHUNK;
+            fe += CH;
         }
     }
-    // Fast-path maintenance, once per group of 4 steps (<= 256 bytes consumed):
-    // keep at least 768 bytes ahead; the chunk issued here is not read before
-    // the next call, which first waits for it.
-    __device__ __forceinline__ void advance4(int lane) {
+    // Fast-path maintenance, once per group of steps consuming <= CH bytes: keep at least
+    // RS-CH bytes ahead; the chunk issued here is not read before the next call, which
+    // first waits for it.
+    __device__ __forceinline__ void advance_group(int lane) {
         cp_async_wait_all();
         __syncwarp();
-        if (pos + (RING - CHUNK) >= fe) {
+        if (pos + (RS - CH) >= fe) {
             fill_chunk(fe, lane);
             cp_async_commit();
-            fe += CHUNK;
+            fe += CH;
         }
     }
+    __device__ __forceinline__ void advance4(int lane) { advance_group(lane); }
     __device__ __forceinline__ uint32_t word_at(uint32_t p) const {
         // p may be odd when the stream sits at an odd address
-        uint32_t o = p & (RING - 1);
-        if (p & 1) return ring[o] | ((uint32_t)ring[(o + 1) & (RING - 1)] << 8);
+        uint32_t o = p & (RS - 1);
+        if (p & 1) return ring[o] | ((uint32_t)ring[(o + 1) & (RS - 1)] << 8);
         return *(const uint16_t *)(ring + o);
     }
     __device__ __forceinline__ void drain() const { cp_async_wait_all(); __syncwarp(); }
 };
+typedef WordRingT<RING> WordRing;                 // order-1 decoder
+constexpr uint32_t RING0 = 2048;                  // order-0 decoder: 8 steps per refill check
+typedef WordRingT<RING0> WordRing0;
 
 __device__ __forceinline__ void stg_u8(uint8_t *p, uint32_t v) {
     asm volatile("st.global.u8 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(v) : "memory");
@@ -135,7 +143,8 @@ __device__ __forceinline__ void stg_u128(uint8_t *p, uint32_t a, uint32_t b, uin
 // One renormalisation round for the warp (rANS_word.h:414-476): lanes whose
 // state fell below 2^15 take the next words in lane order.  A lane refills only
 // if two more bytes exist, exactly like RansDecRenormSafe.
-__device__ __forceinline__ uint32_t renorm_step(uint32_t R, bool act, WordRing &w, int lane,
+template <typename WR>
+__device__ __forceinline__ uint32_t renorm_step(uint32_t R, bool act, WR &w, int lane,
                                                 uint32_t lt) {
     bool need = act && R < RANS_L;
     uint32_t mask = __ballot_sync(FULL, need);
@@ -178,41 +187,52 @@ __device__ inline int get_alphabet(const uint8_t *cp, const uint8_t *end, uint32
 }
 
 // ======================================================================== o0
+// 8 KiB per stream.  In dec_kernel<false> the block is 8 KiB aligned in the shared window, so
+// the slot look-up address is (state & 4095) | lut and the ring address (pos & 2047) | ring:
+// one LOP3 each.  freq and start are split into two 16-bit arrays: two independent loads
+// instead of a load plus two bit-field extractions on the state chain.
 struct __align__(16) DecO0Smem {
-    uint8_t  ring[RING];
-    uint32_t tab[256];     // freq | start<<16 (freq may be 4096: no 12-bit wrap)
     uint8_t  lut[4096];    // slot -> symbol
+    uint16_t f16[256];     // freq (may be 4096: no 12-bit wrap)
+    uint16_t b16[256];     // start
+    uint32_t tab[256];     // parse scratch: raw counts
+    uint8_t  ring[RING0];
 };
+static_assert(sizeof(DecO0Smem) == 8192, "DecO0Smem layout");
 
-template <int N, bool ODD>
+template <int N, bool ODD, bool AL>
 __device__ __forceinline__ void dec_o0_fast(uint32_t &R_, uint32_t &i_, uint32_t full, uint8_t *out,
-                                            WordRing &w, const DecO0Smem &S, int lane, uint32_t lt) {
+                                            WordRing0 &w, const DecO0Smem &S, int lane, uint32_t lt) {
     const bool act = (N == 32) ? true : lane < N;
     uint32_t R = R_, i = i_, pos = w.pos;
     uint8_t *o = out + i + (act ? lane : 0);
-    const uint8_t *ring = w.ring;
-    while (i + 4 * N <= full && pos + 4 * 64 <= w.end) {
+    const uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(S.lut);
+    const uint32_t f_s = (uint32_t)__cvta_generic_to_shared(S.f16);
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(w.ring);
+    while (i + 8 * N <= full && pos + 8 * 64 <= w.end) {
         w.pos = pos;
-        w.advance4(lane);
+        w.advance_group(lane);
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < 8; u++) {
             uint32_t m = R & 4095;
-            uint32_t s = S.lut[m];
-            uint32_t fb = S.tab[s];
-            R = (fb & 0xffff) * (R >> 12) + m - (fb >> 16);
+            uint32_t s = lds_u8a(AL ? (lut_s | m) : (lut_s + m));
+            uint32_t fa = f_s + 2 * s;
+            uint32_t f = lds_u16a(fa), b = lds_u16a(fa + 512);
+            R = f * (R >> 12) + m - b;
             if (act) stg_u8(o + u * N, s);
             bool need = act && R < RANS_L;
             uint32_t mask = __ballot_sync(FULL, need);
             if (need) {
                 uint32_t p = pos + 2 * __popc(mask & lt);
-                uint32_t wv = ODD ? (lds_u8(ring, p & (RING - 1)) | (lds_u8(ring, (p + 1) & (RING - 1)) << 8))
-                                  : lds_u16(ring, p & (RING - 1));
+                uint32_t wv;
+                if (ODD) wv = lds_u8a(ring_s + (p & (RING0 - 1))) | (lds_u8a(ring_s + ((p + 1) & (RING0 - 1))) << 8);
+                else wv = lds_u16a(AL ? (ring_s | (p & (RING0 - 1))) : (ring_s + (p & (RING0 - 1))));
                 R = (R << 16) | wv;
             }
             pos += 2 * __popc(mask);
         }
-        o += 4 * N;
-        i += 4 * N;
+        o += 8 * N;
+        i += 8 * N;
     }
     w.pos = pos;
     // hand over to the careful loop with the ring in its per-step regime
@@ -270,12 +290,13 @@ __device__ int dec_o0(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
 #pragma unroll
     for (int t = 0; t < 8; t++) {
         uint32_t ff = f[t] << sh;
-        S.tab[lane * 8 + t] = ff | (x << 16);
+        S.f16[lane * 8 + t] = (uint16_t)ff;
+        S.b16[lane * 8 + t] = (uint16_t)x;
         x += ff;
     }
     __syncwarp();
     for (int j = 0; j < 256; j++) {
-        uint32_t fb = S.tab[j], ff = fb & 0xffff, b = fb >> 16;
+        uint32_t ff = S.f16[j], b = S.b16[j];
         for (uint32_t y = lane; y < ff; y += 32) S.lut[b + y] = (uint8_t)j;
     }
 
@@ -289,20 +310,25 @@ __device__ int dec_o0(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
     }
     if (__any_sync(FULL, R < RANS_L)) return 1;
 
-    WordRing w;
+    WordRing0 w;
     w.init(in, hdr + 4 * N, in_size, S.ring, lane);     // ends with __syncwarp: lut visible
     const uint32_t lt = lanemask_lt();
     const uint32_t full = out_sz - out_sz % N;
     uint32_t i = 0;
-    // Hot loop: groups of 4 steps while 4*64 bytes of words are certainly left,
-    // so no end-of-stream bookkeeping and one ring check per group.
-    if (w.pos & 1) dec_o0_fast<N, true>(R, i, full, out, w, S, lane, lt);
-    else dec_o0_fast<N, false>(R, i, full, out, w, S, lane, lt);
+    // Hot loop: groups of 8 steps while 8*64 bytes of words are certainly left, so no
+    // end-of-stream bookkeeping and one ring check per group.
+    const bool al = (((uint32_t)__cvta_generic_to_shared(S.lut)) & 8191) == 0;
+    if (al) {
+        if (w.pos & 1) dec_o0_fast<N, true, true>(R, i, full, out, w, S, lane, lt);
+        else dec_o0_fast<N, false, true>(R, i, full, out, w, S, lane, lt);
+    } else {
+        if (w.pos & 1) dec_o0_fast<N, true, false>(R, i, full, out, w, S, lane, lt);
+        else dec_o0_fast<N, false, false>(R, i, full, out, w, S, lane, lt);
+    }
     for (; i < full; i += N) {
         uint32_t m = R & 4095;
         uint32_t s = S.lut[m];
-        uint32_t fb = S.tab[s];
-        R = (fb & 0xffff) * (R >> 12) + m - (fb >> 16);
+        R = (uint32_t)S.f16[s] * (R >> 12) + m - S.b16[s];
         if (act) out[i + lane] = (uint8_t)s;
         R = renorm_step(R, act, w, lane, lt);
     }

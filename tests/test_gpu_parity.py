@@ -200,3 +200,56 @@ def test_concurrent_callers(gpu_codec, checker):
     [t.start() for t in th]
     [t.join() for t in th]
     assert res == want
+
+
+def test_unaligned_buffers_and_odd_word_streams(gpu_codec, checker):
+    """Streams, inputs and outputs at every byte alignment: the coders' vector paths and the
+    word ring must not depend on alignment (the word stream itself starts at an odd address
+    for about half of all tables)."""
+    base = np.frombuffer(corpus.make("illumina_qual", 200000, 7), np.uint8)
+    for shift in range(0, 17, 3):
+        for order in (4, 5):
+            n = 150000 + shift
+            buf = np.zeros(n + 64, np.uint8)
+            buf[shift:shift + n] = base[:n]
+            out, ooff, osz = gpu_codec.compress_batch(buf, [shift], [n], [order])
+            want = checker.compress(buf[shift:shift + n].tobytes(), order)
+            got = out[int(ooff[0]):int(ooff[0]) + int(osz[0])].tobytes()
+            assert got == want, (shift, order)
+            # decode from an arena where the stream sits at an odd offset, into an odd offset
+            comp = np.zeros(len(want) + 64, np.uint8)
+            comp[shift + 1:shift + 1 + len(want)] = np.frombuffer(want, np.uint8)
+            back = np.zeros(n + 64, np.uint8)
+            rsz, st = gpu_codec.uncompress_batch(comp, [shift + 1], [len(want)], back, [shift + 3], [n])
+            assert st[0] == 0 and rsz[0] == n
+            assert np.array_equal(back[shift + 3:shift + 3 + n], buf[shift:shift + n]), (shift, order)
+
+
+def test_one_large_stream_per_call(gpu_codec, checker):
+    """A whole buffer as ONE call (K = 1, the single-warp latency floor of SURVEY F4):
+    still the reference's bytes."""
+    data = corpus.make("illumina_qual", 24 << 20, 11)
+    for order in (4, 5, 0, 1):
+        want = checker.compress(data, order)
+        assert gpu_codec.rans_compress_to_4x16(data, order) == want, hex(order)
+        assert gpu_codec.rans_uncompress_4x16(want) == data, hex(order)
+
+
+def test_multi_gpu_batch_api(gpu_codec, checker):
+    """b200rans_*_batch_multi: blocks dealt round-robin to the GPUs of the box, results in call
+    order (runs with however many GPUs are visible, 1 included)."""
+    import torch
+    ngpu = min(torch.cuda.device_count(), 2)
+    parts = [np.frombuffer(corpus.make("illumina_qual", 262144, s), np.uint8) for s in range(12)]
+    buf = np.concatenate(parts)
+    offs = [262144 * i for i in range(12)]
+    sizes = [262144] * 12
+    orders = [4, 5] * 6
+    out, ooff, osz = gpu_codec.compress_batch(buf, offs, sizes, orders, ngpu=ngpu,
+                                              block_of=[i // 3 for i in range(12)])
+    for k in range(12):
+        assert out[int(ooff[k]):int(ooff[k]) + int(osz[k])].tobytes() == checker.compress(parts[k].tobytes(), orders[k])
+    back = np.empty(buf.size, np.uint8)
+    rsz, st = gpu_codec.uncompress_batch(out, ooff, osz, back, offs, sizes, ngpu=ngpu,
+                                         block_of=[i // 3 for i in range(12)])
+    assert (st == 0).all() and np.array_equal(back, buf)
