@@ -748,27 +748,36 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
             asm("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(rank_s + b));
             return r;
         };
+        // the encoder symbol of the NEXT step is fetched (rank look-up, table look-up, unpack)
+        // while the current step runs: none of it depends on the state
+        uint32_t rc = rank_of(byte_of(cur, 14));
+        uint4 e = lds_sym(sym_s + (rc * nsym + rs) * 8);
         for (uint32_t j = J - 1; j >= 1; j--) {
             uint4 nn = j >= 2 ? ldg_u128(v + j - 2) : make_uint4(0, 0, 0, 0);
 #pragma unroll
             for (int b = 15; b >= 0; b--) {
-                uint32_t cb = b ? byte_of(cur, b - 1) : byte_of(nxt, 15);
-                uint32_t rc = rank_of(cb);
-                uint4 e = lds_sym(sym_s + (rc * nsym + rs) * 8);
+                // next step codes byte b-1 in the context of byte b-2 (crossing into nxt at the low end)
+                uint32_t nb = b >= 2 ? byte_of(cur, b - 2) : byte_of(nxt, 14 + b);
+                uint32_t rn = rank_of(nb);
+                uint4 en = lds_sym(sym_s + (rn * nsym + rc) * 8);
                 if ((b & 3) == 3) w.maybe_flush(lane);
                 R = enc_step(R, true, e, w, lane);
+                e = en;
                 rs = rc;
+                rc = rn;
             }
             cur = nxt;
             nxt = nn;
         }
 #pragma unroll
         for (int b = 15; b >= 1; b--) {                      // group 0: its byte 0 is the lane's first symbol
-            uint32_t rc = rank_of(byte_of(cur, b - 1));
-            uint4 e = lds_sym(sym_s + (rc * nsym + rs) * 8);
+            uint32_t rn = b >= 2 ? rank_of(byte_of(cur, b - 2)) : 0;
+            uint4 en = b >= 2 ? lds_sym(sym_s + (rn * nsym + rc) * 8) : e;
             if ((b & 3) == 3) w.maybe_flush(lane);
             R = enc_step(R, true, e, w, lane);
+            e = en;
             rs = rc;
+            rc = rn;
         }
         kstart = 1;
     }
