@@ -172,8 +172,10 @@ def run_reference(args, gen, order, total, S):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": (te + td) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32",
         "data": "synthetic",
-        "config": {"workload": args.workload, "order": hex(order), "slice_bytes": S,
-                   "streams": len(sl), "sample_bytes": sample},
+        "config": {"workload": args.workload, "description": WORKLOADS[args.workload][3],
+                   "order": hex(order), "block_bytes": total, "slice_bytes": S, "streams": len(sl),
+                   "sample_bytes": sample,
+                   "note": "CPU arm: each step codes a bounded sample of the block on all host threads"},
         "enc_gbs": sample / te / 1e9, "dec_gbs": sample / td / 1e9, "ratio": csize / sample,
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": kind_name(codec),
                          "sample": "%d slices of %d B (%.0f MB) of the workload, %s build, %d threads"
@@ -323,10 +325,19 @@ def run_b200(args, gen, order, total, S):
         U, Cc = total, csize
         kd, ke = float(np.mean(k_dec)), float(np.mean(k_enc))
 
+        traffic = {}
+        try:        # DRAM bytes per launch from the committed ncu --set full capture of this workload
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if args.workload in tj and total == WORKLOADS[args.workload][2] and S == (256 << 10):
+                traffic = tj[args.workload]
+        except Exception:
+            pass
+
         def roof(ms, name):
             a = (U + Cc) / (ms * 1e-3) / 1e9
             return {"kernel": name, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s",
-                    "frac": a / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": a / peak, "traffic": traffic.get(name), "traffic_source": traffic.get("source"),
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": U + Cc, "kernel_ms": ms}
         r_enc, r_dec = roof(ke, "enc_kernel"), roof(kd, "dec_kernel")
         dominant = r_enc if ke >= kd else r_dec
