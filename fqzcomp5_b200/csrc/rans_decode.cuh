@@ -202,16 +202,20 @@ static_assert(sizeof(DecO0Smem) == 8192, "DecO0Smem layout");
 
 template <int N, bool ODD, bool AL>
 __device__ __forceinline__ void dec_o0_fast(uint32_t &R_, uint32_t &i_, uint32_t full, uint8_t *out,
-                                            WordRing0 &w, const DecO0Smem &S, int lane, uint32_t lt) {
+                                            WordRing0 &w, DecO0Smem &S, int lane, uint32_t lt) {
     const bool act = (N == 32) ? true : lane < N;
     uint32_t R = R_, i = i_, pos = w.pos;
-    uint8_t *o = out + i + (act ? lane : 0);
     const uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(S.lut);
     const uint32_t f_s = (uint32_t)__cvta_generic_to_shared(S.f16);
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(w.ring);
+    // N == 32: the 8 x 32 symbols of a group are collected in shared memory (the parse scratch
+    // is free by now) and leave as sixteen 16-byte stores when `out` allows it
+    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(S.tab);
+    const bool wide = N == 32 && ((uintptr_t)out & 15) == 0;
+    uint8_t *o = out + i + (act ? lane : 0);
     while (i + 8 * N <= full && pos + 8 * 64 <= w.end) {
         w.pos = pos;
-        w.advance_group(lane);
+        w.advance_group(lane);          // also orders the previous group's tile reads before new writes
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             uint32_t m = R & 4095;
@@ -219,17 +223,27 @@ __device__ __forceinline__ void dec_o0_fast(uint32_t &R_, uint32_t &i_, uint32_t
             uint32_t fa = f_s + 2 * s;
             uint32_t f = lds_u16a(fa), b = lds_u16a(fa + 512);
             R = f * (R >> 12) + m - b;
-            if (act) stg_u8(o + u * N, s);
+            if (wide) asm volatile("st.shared.u8 [%0], %1;" ::"r"(tile_s + u * 32 + lane), "r"(s) : "memory");
+            else if (act) stg_u8(o + u * N, s);
             bool need = act && R < RANS_L;
             uint32_t mask = __ballot_sync(FULL, need);
-            if (need) {
-                uint32_t p = pos + 2 * __popc(mask & lt);
-                uint32_t wv;
-                if (ODD) wv = lds_u8a(ring_s + (p & (RING0 - 1))) | (lds_u8a(ring_s + ((p + 1) & (RING0 - 1))) << 8);
-                else wv = lds_u16a(AL ? (ring_s | (p & (RING0 - 1))) : (ring_s + (p & (RING0 - 1))));
-                R = (R << 16) | wv;
-            }
+            // branch-free refill: every lane reads a word (lanes that do not need one read a
+            // valid but unused position), then selects
+            uint32_t p = pos + 2 * __popc(mask & lt);
+            uint32_t wv;
+            if (ODD) wv = lds_u8a(ring_s + (p & (RING0 - 1))) | (lds_u8a(ring_s + ((p + 1) & (RING0 - 1))) << 8);
+            else wv = lds_u16a(AL ? (ring_s | (p & (RING0 - 1))) : (ring_s + (p & (RING0 - 1))));
+            R = need ? ((R << 16) | wv) : R;
             pos += 2 * __popc(mask);
+        }
+        if (wide) {
+            __syncwarp();
+            if (lane < 16) {
+                uint4 v;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(tile_s + 16 * lane));
+                stg_u128(out + i + 16 * lane, v.x, v.y, v.z, v.w);
+            }
         }
         o += 8 * N;
         i += 8 * N;
