@@ -60,8 +60,9 @@ struct Layout {
 };
 
 constexpr int NSTAGE = 4;
-constexpr int NPIPE = 3;                  // chunks in flight in the host-buffer API
-constexpr size_t CHUNK_BYTES = 48u << 20; // uncompressed bytes per pipeline chunk
+constexpr int NPIPE = 4;                  // chunks in flight in the host-buffer API
+constexpr size_t CHUNK_BYTES = 48u << 20; // uncompressed bytes per pipeline chunk ...
+constexpr int CHUNK_MIN_STREAMS = 256;    // ... but at least this many streams: a chunk of few streams is latency bound
 struct Stage { Arena h; cudaEvent_t ev = nullptr; bool busy = false; };
 
 // One pipeline lane: a stream plus the arenas a chunk of work needs.  Chunks of a
@@ -404,7 +405,8 @@ int compress_batch_impl(int n, const unsigned char *const *in, const unsigned in
         EncChunk c;
         c.k0 = k;
         size_t acc = 0;
-        while (k < n && (k == c.k0 || (acc + in_size[k] <= CHUNK_BYTES && k - c.k0 < 16384))) acc += in_size[k++];
+        while (k < n && (k == c.k0 || ((acc + in_size[k] <= CHUNK_BYTES || k - c.k0 < CHUNK_MIN_STREAMS) && k - c.k0 < 16384)))
+            acc += in_size[k++];
         c.k1 = k;
         ch.push_back(c);
     }
@@ -465,7 +467,7 @@ int compress_batch_impl(int n, const unsigned char *const *in, const unsigned in
         ch[c].L = &C->lane[c % NPIPE];
         rc = submit(ch[c]);
         if (!rc && c >= 1) rc = readback(ch[c - 1]);
-        if (!rc && c >= 2) rc = finish(ch[c - 2]);      // frees the lane chunk c+1 will use
+        if (!rc && c >= NPIPE - 1) rc = finish(ch[c - (NPIPE - 1)]);      // frees the lane chunk c+1 will use
     }
     if (!rc) rc = readback(ch[nc - 1]);
     for (auto &l : C->lane) cudaStreamSynchronize(l.st);
@@ -540,7 +542,7 @@ int uncompress_batch_impl(int n, const unsigned char *const *in, const unsigned 
             }
             it.njobs = (uint32_t)jin.size() - it.first_job;
             acc += ocap[k];
-            if (acc >= CHUNK_BYTES || k - c.k0 + 1 >= 16384 || k == n - 1) {
+            if ((acc >= CHUNK_BYTES && k - c.k0 + 1 >= CHUNK_MIN_STREAMS) || k - c.k0 + 1 >= 16384 || k == n - 1) {
                 c.k1 = k + 1; c.j1 = (int)jin.size();
                 ch.push_back(c);
                 c = DecChunk(); c.k0 = k + 1; c.j0 = (int)jin.size();
@@ -636,7 +638,7 @@ int uncompress_batch_impl(int n, const unsigned char *const *in, const unsigned 
         ch[c].L = &C->lane[c % NPIPE];
         rc = submit(ch[c]);
         if (!rc && c >= 1) rc = readback(ch[c - 1]);
-        if (!rc && c >= 2) rc = finish(ch[c - 2]);
+        if (!rc && c >= NPIPE - 1) rc = finish(ch[c - (NPIPE - 1)]);
     }
     if (!rc && nc) rc = readback(ch[nc - 1]);
     for (auto &l : C->lane) cudaStreamSynchronize(l.st);
