@@ -456,6 +456,7 @@ hist_kernel(EncJob *jobs, uint32_t njobs) {
     uint32_t *gH = model + MODEL_HDR_WORDS;
     const bool in_smem = hw <= HIST_SMEM_PAIRS;
     uint32_t *H = in_smem ? Hs : gH;
+    const uint32_t Hs_s = (uint32_t)__cvta_generic_to_shared(Hs);
     for (uint32_t j = tid; j < hw; j += HIST_THREADS) H[j] = 0;
     __syncthreads();
     // ---- pairs: H[rank(prev)][rank(cur)], the first byte follows symbol 0 (utils.h:279-357)
@@ -467,15 +468,19 @@ hist_kernel(EncJob *jobs, uint32_t njobs) {
         uint4 q = ldg_u128(v + i);
         uint32_t pb = (i || head) ? p[16 * (size_t)i - 1] : 0;
         uint32_t w4[4] = {q.x, q.y, q.z, q.w};
-        uint32_t rp = rank[pb], last = 0xffffffffu, cnt = 0;
+        uint32_t rp = rank[pb], last = 0, cnt = 0;          // cnt == 0: adding it is harmless
 #pragma unroll
         for (int a = 0; a < 4; a++)
 #pragma unroll
             for (int b = 0; b < 4; b++) {
                 uint32_t rc = rank[(w4[a] >> (8 * b)) & 0xff];
                 uint32_t idx = rp * nsym + rc;
-                if (idx == last) cnt++;
-                else { if (cnt) atomicAdd(&H[last], cnt); last = idx; cnt = 1; }
+                if (in_smem) {      // branch-free: predicated reduction when the pair changes
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, %1;\n\t@p red.shared.add.u32 [%2], %3;\n\t}"
+                                 ::"r"(idx), "r"(last), "r"(Hs_s + last * 4), "r"(cnt) : "memory");
+                } else if (idx != last && cnt) atomicAdd(&H[last], cnt);
+                cnt = (idx == last) ? cnt + 1 : 1;
+                last = idx;
                 rp = rc;
             }
         atomicAdd(&H[last], cnt);

@@ -35,6 +35,7 @@ __device__ __forceinline__ uint4 ldg_u128(const uint4 *p) {
 // issued (quality strings are sticky).  (A word-level "four equal bytes" shortcut was
 // measured slower: the two paths diverge within the warp.)
 __device__ __forceinline__ void hist16(uint4 q, uint32_t *F) {
+    const uint32_t F_s = (uint32_t)__cvta_generic_to_shared(F);
     uint32_t w[4] = {q.x, q.y, q.z, q.w};
     uint32_t prev = w[0] & 0xff, cnt = 0;
 #pragma unroll
@@ -42,10 +43,13 @@ __device__ __forceinline__ void hist16(uint4 q, uint32_t *F) {
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             uint32_t c = (w[a] >> (8 * b)) & 0xff;
-            if (c == prev) cnt++;
-            else { atomicAdd(&F[prev], cnt); prev = c; cnt = 1; }
+            // branch-free: a predicated shared-memory reduction closes the run when the byte changes
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, %1;\n\t@p red.shared.add.u32 [%2], %3;\n\t}"
+                         ::"r"(c), "r"(prev), "r"(F_s + prev * 4), "r"(cnt) : "memory");
+            cnt = (c == prev) ? cnt + 1 : 1;
+            prev = c;
         }
-    atomicAdd(&F[prev], cnt);
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(F_s + prev * 4), "r"(cnt) : "memory");
 }
 
 __device__ inline void warp_hist8(const uint8_t *in, uint32_t n, uint32_t *F, int lane) {
