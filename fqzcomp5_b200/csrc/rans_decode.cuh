@@ -444,6 +444,79 @@ __device__ __forceinline__ void dec_o1_fast(uint32_t &R_, uint32_t &ctx_, uint32
     R_ = R; ctx_ = ctx; k_ = k;
 }
 
+// ------------------------------------------------------------------------
+// Order-1 table rows (rANS_static16_int.h:425-456, 488-530) parsed by the whole warp.
+// The byte stream is a sequence of tokens -- a varint count, or 0x00 followed by a raw
+// byte z meaning z further zero counts -- with no delimiters between rows.  Which byte
+// starts a token is decided by a three-state machine (token start / inside a varint /
+// raw run byte); its per-byte transition functions are composed with a warp scan, 32
+// bytes per round, so token starts, their slot numbers (exclusive scan of 1 or 1+z) and
+// hence (row, column) are known without walking the stream serially.
+// Raw counts are written to cum[row*ns1 + col + 1]; rows must be zeroed beforehand.
+// Returns 0 and the end of the table in *end_out, or 1 on malformed input.
+// ------------------------------------------------------------------------
+__device__ inline int parse_o1_rows(const uint8_t *cp, const uint8_t *tend, uint32_t nsym, uint32_t tot,
+                                    uint16_t *cum, uint32_t ns1, int lane, const uint8_t **end_out) {
+    const uint32_t total = nsym * nsym;
+    const uint32_t avail = (uint32_t)(tend - cp);
+    const uint32_t lt = lanemask_lt();
+    uint32_t state = 0, slot_base = 0, end_off = 0;     // 0 start, 1 varint, 2 run byte
+    int err = 0;
+    for (uint32_t base = 0; slot_base < total; base += 32) {
+        if (base >= avail) return 1;                    // ran out of bytes before the last row
+        const uint32_t i = base + lane;
+        const bool in = i < avail;
+        const uint32_t b = in ? cp[i] : 0x01;           // padding: harmless one-byte tokens
+        // transition function of this byte, 2 bits per source state
+        uint32_t f = (b == 0 ? 2u : (b < 128 ? 0u : 1u)) | ((b < 128 ? 0u : 1u) << 2) | (0u << 4);
+        // inclusive scan: F_i = f_i o ... o f_0
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t g = __shfl_up_sync(FULL, f, o);    // earlier bytes: applied first
+            if (lane >= o) {
+                uint32_t a0 = (g >> 0) & 3, a1 = (g >> 2) & 3, a2 = (g >> 4) & 3;
+                f = ((f >> (2 * a0)) & 3) | (((f >> (2 * a1)) & 3) << 2) | (((f >> (2 * a2)) & 3) << 4);
+            }
+        }
+        uint32_t fprev = __shfl_up_sync(FULL, f, 1);
+        uint32_t before = lane ? ((fprev >> (2 * state)) & 3) : state;
+        const bool start = in && before == 0;
+        // token at a start byte
+        uint32_t val = 0, slots = 0, len = 0;
+        bool terr = false;                              // only counts if the token belongs to the table
+        if (start) {
+            if (b == 0) {
+                if (i + 1 >= avail) { terr = true; slots = 1; len = 1; }
+                else { slots = 1 + cp[i + 1]; len = 2; }
+            } else {
+                uint32_t c = b;
+                val = c & 0x7f; len = 1; slots = 1;
+                while ((c & 0x80) && i + len < avail && len < 6) { c = cp[i + len]; val = (val << 7) | (c & 0x7f); len++; }
+                terr = (c & 0x80) || val == 0 || val > tot;     // unterminated, non-canonical zero, too large
+            }
+        }
+        uint32_t incl = warp_incl_scan(slots, lane);
+        uint32_t s0 = slot_base + incl - slots;
+        if (start && s0 < total) {
+            uint32_t row = s0 / nsym, col = s0 - row * nsym;
+            if (terr || col + slots > nsym) err = 1;    // a zero run never crosses a row
+            else if (val) cum[row * ns1 + col + 1] = (uint16_t)val;
+            if (s0 + slots >= total) end_off = i + len; // the token that completes the last row
+        }
+        uint32_t chunk_slots = __shfl_sync(FULL, incl, 31);
+        state = (__shfl_sync(FULL, f, 31) >> (2 * state)) & 3;
+        slot_base += chunk_slots;
+        if (__any_sync(FULL, err)) return 1;
+        (void)lt;
+    }
+    // exactly one lane saw the closing token
+    uint32_t m = __ballot_sync(FULL, end_off != 0);
+    if (!m) return 1;
+    end_off = __shfl_sync(FULL, end_off, __ffs(m) - 1);
+    *end_out = cp + end_off;
+    return 0;
+}
+
 struct __align__(16) DecO1Smem {
     union {                     // the alphabet marks are dead before the word ring is filled
         uint8_t  ring[RING];
@@ -520,35 +593,17 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
     for (int j = lane; j < 256; j += 32)          // presence from F0: rank 255 is a valid rank
         if (S.F0[j]) T.sym[S.rank[j]] = (uint8_t)j;
 
-    // --- rows, in alphabet order (rANS_static16_int.h:488-530).  The byte stream can
-    // only be walked serially (lane 0, raw counts into fs[]); scaling, cumulative
-    // starts and validation of each row then run one lane per row.
+    // --- rows, in alphabet order: raw counts by parse_o1_rows, then scaling, cumulative
+    // starts and validation one lane per row
     int err = 0;
-    if (lane == 0) {
-        for (uint32_t i = 0; i < nsym && !err; i++) {
-            uint16_t *row = T.cum + i * ns1;
-            if (cp >= tend) { err = 1; break; }
-            uint32_t zrun = 0;
-            for (uint32_t r = 0; r < nsym; r++) {
-                uint32_t f = 0;
-                if (zrun) zrun--;
-                else if (cp < tend) {
-                    uint32_t c = *cp++;
-                    f = c & 0x7f;
-                    int cnt = 1;
-                    while ((c & 0x80) && cp < tend && cnt < 6) { c = *cp++; f = (f << 7) | (c & 0x7f); cnt++; }
-                    if (f == 0) {
-                        if (cp >= tend) { err = 1; break; }
-                        zrun = *cp++;
-                    }
-                }
-                if (f > tot) { err = 1; break; }
-                row[r + 1] = (uint16_t)f;
-            }
-        }
+    for (uint32_t j = lane; j < nsym * ns1; j += 32) T.cum[j] = 0;
+    __syncwarp();
+    if (cp >= tend) return 1;
+    {
+        const uint8_t *table_end = nullptr;
+        if (parse_o1_rows(cp, tend, nsym, tot, T.cum, ns1, lane, &table_end)) return 1;
+        cp = table_end;
     }
-    err = __shfl_sync(FULL, err, 0);
-    if (err) return 1;
     __syncwarp();
     for (uint32_t i0 = 0; i0 < nsym; i0 += 32) {
         const uint32_t i = i0 + lane;
@@ -571,11 +626,6 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
     }
     err = __any_sync(FULL, err);
     if (err) return 1;
-    {   // only lane 0 walked the table: share where it ended
-        const uint8_t *tbase = comp ? tend : in;     // any pointer all lanes agree on
-        long long d = __shfl_sync(FULL, (long long)(cp - tbase), 0);
-        cp = tbase + d;
-    }
     __threadfence_block();
     __syncwarp();
     // --- bucket look-up: lane per row
