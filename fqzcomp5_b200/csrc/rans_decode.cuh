@@ -605,41 +605,78 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
         cp = table_end;
     }
     __syncwarp();
-    for (uint32_t i0 = 0; i0 < nsym; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        if (i < nsym) {
-            uint16_t *row = T.cum + i * ns1;
-            uint32_t tsum = 0;
-            for (uint32_t r = 0; r < nsym; r++) tsum += row[r + 1];
-            int sh = 0;
-            if (tsum) { uint32_t z = tsum; while (z < tot) { z *= 2; sh++; } }   // normalise_freq_shift
-            uint32_t x = 0;
-            for (uint32_t r = 0; r < nsym; r++) {          // in place: raw count of r sits at [r+1]
-                uint32_t f = (uint32_t)row[r + 1] << sh;
-                if (f > tot - x) { err = 1; break; }
-                row[r] = (uint16_t)x;
-                x += f;
+    const uint32_t bw = shift - bb, nb = 1u << bb;
+    if (nsym <= 64) {
+        // small alphabets (tables in shared memory): one lane per row
+        for (uint32_t i0 = 0; i0 < nsym; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            if (i < nsym) {
+                uint16_t *row = T.cum + i * ns1;
+                uint32_t tsum = 0;
+                for (uint32_t r = 0; r < nsym; r++) tsum += row[r + 1];
+                int sh = 0;
+                if (tsum) { uint32_t z = tsum; while (z < tot) { z *= 2; sh++; } }   // normalise_freq_shift
+                uint32_t x = 0;
+                for (uint32_t r = 0; r < nsym; r++) {          // in place: raw count of r sits at [r+1]
+                    uint32_t f = (uint32_t)row[r + 1] << sh;
+                    if (f > tot - x) { err = 1; break; }
+                    row[r] = (uint16_t)x;
+                    x += f;
+                }
+                row[nsym] = (uint16_t)x;
+                if (!err && tsum && x != tot) err = 1;
+                // bucket index: rank of the symbol owning the first slot of each bucket
+                uint8_t *bl = T.blut + (i << bb);
+                uint32_t r = 0;
+                for (uint32_t bk = 0; bk < nb && !err; bk++) {
+                    uint32_t m = bk << bw;
+                    while (r + 1 < nsym && m >= row[r + 1]) r++;
+                    bl[bk] = (uint8_t)r;
+                }
             }
-            row[nsym] = (uint16_t)x;
-            if (!err && tsum && x != tot) err = 1;
+        }
+    } else {
+        // large alphabets (tables in the L2-resident pool): the warp walks the rows together,
+        // lanes over columns, so that global accesses coalesce
+        for (uint32_t i = 0; i < nsym; i++) {
+            uint16_t *row = T.cum + i * ns1;
+            uint8_t *bl = T.blut + (i << bb);
+            uint32_t f[8], tsum = 0;
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                uint32_t c = lane + 32 * t;
+                f[t] = c < nsym ? row[c + 1] : 0;
+                tsum += f[t];
+            }
+            tsum = warp_sum(tsum);
+            int sh = 0;
+            if (tsum) { uint32_t z = tsum; while (z < tot) { z *= 2; sh++; } }
+            __syncwarp();
+            uint32_t basex = 0;
+            bool bad = false;
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                uint32_t c = lane + 32 * t, ff = f[t] << sh;
+                uint32_t incl = warp_incl_scan(ff, lane);
+                uint32_t x = basex + incl - ff;
+                if (c < nsym) {
+                    bad |= ff > tot || x > tot - ff;
+                    row[c] = (uint16_t)min(x, 65535u);
+                    if (ff && !bad) {      // buckets whose first slot falls inside [x, x+ff)
+                        for (uint32_t bk = (x + (1u << bw) - 1) >> bw; (bk << bw) < x + ff && bk < nb; bk++) bl[bk] = (uint8_t)c;
+                    }
+                }
+                basex += __shfl_sync(FULL, incl, 31);
+            }
+            if (lane == 0) row[nsym] = (uint16_t)min(basex, 65535u);
+            if (bad || (tsum && basex != tot)) err = 1;
+            if (!tsum && lane == 0) for (uint32_t bk = 0; bk < nb; bk++) bl[bk] = 0;
         }
     }
     err = __any_sync(FULL, err);
     if (err) return 1;
     __threadfence_block();
     __syncwarp();
-    // --- bucket look-up: lane per row
-    const uint32_t bw = shift - bb, nb = 1u << bb;
-    for (uint32_t i0 = 0; i0 < nsym; i0 += 32) { const uint32_t i = i0 + lane; if (i >= nsym) continue;
-        const uint16_t *row = T.cum + i * ns1;
-        uint8_t *bl = T.blut + (i << bb);
-        uint32_t r = 0;
-        for (uint32_t b = 0; b < nb; b++) {
-            uint32_t m = b << bw;
-            while (r + 1 < nsym && m >= row[r + 1]) r++;
-            bl[b] = (uint8_t)r;
-        }
-    }
     if (after) cp = after;
     if ((uint32_t)(end - cp) < (uint32_t)N * 4) return 1;
     const bool act = lane < N;
