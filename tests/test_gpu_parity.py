@@ -253,3 +253,12 @@ def test_multi_gpu_batch_api(gpu_codec, checker):
     rsz, st = gpu_codec.uncompress_batch(out, ooff, osz, back, offs, sizes, ngpu=ngpu,
                                          block_of=[i // 3 for i in range(12)])
     assert (st == 0).all() and np.array_equal(back, buf)
+
+
+def test_randomised_differential(gpu_codec, checker):
+    """A slice of scripts/gpu_fuzz.py: random distributions, sizes and order flags."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "gpu_fuzz.py"), "400", "99"],
+                         capture_output=True, text=True, timeout=600).stdout
+    assert "cases 400 mismatches 0" in out, out[-2000:]
