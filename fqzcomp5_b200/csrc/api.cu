@@ -316,7 +316,7 @@ int dec_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
         if (f & (X_PACK | X_RLE)) J.tmp = (uint8_t *)L.take((size_t)out_cap[k] * 2 + 4096, 256);
         if ((f & 1) && !(f & X_CAT)) {
             J.route = 1; n_o1++;
-            pool_bytes += 257 * 257 * 3 + 257 * 256 * 2 + 80 * 1024;
+            pool_bytes += 257 * 257 * 3 + 257 * 256 * 4 + 256 * 256 + 16 * 1024;   // table text + DecO1Big
         } else n_o0++;
     }
     pool_bytes = std::min<size_t>(pool_bytes, (size_t)2 << 30);

@@ -444,6 +444,78 @@ __device__ __forceinline__ void dec_o1_fast(uint32_t &R_, uint32_t &ctx_, uint32
     R_ = R; ctx_ = ctx; k_ = k;
 }
 
+// Large alphabets (nsym > 64): tables in global memory (L2), rows COMPACTED to the symbols
+// that occur in the context:
+//   ent[ctx][k]  = start | rank << 16 of the k-th symbol with a non-zero frequency in ctx,
+//                  closed by a sentinel whose start is the total (so freq = next.start - start
+//                  and the forward scan needs no bound)
+//   blut[ctx][b] = k of the symbol owning the first slot of bucket b (256 buckets)
+// so a look-up never walks over the (many) absent symbols of a sparse row.
+__device__ __forceinline__ uint32_t ldg_u8d(const uint8_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(__cvta_generic_to_global(p)));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldg_u32d(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(__cvta_generic_to_global(p)));
+    return v;
+}
+struct DecO1Big {
+    const uint32_t *ent;    // [nsym][nsym+1]
+    const uint8_t *blut;    // [nsym][256]
+    uint32_t ns1, shift;
+    __device__ __forceinline__ uint32_t look(uint32_t R, uint32_t ctx, uint32_t &c0, uint32_t &c1) const {
+        const uint32_t m = R & ((1u << shift) - 1);
+        uint32_t k = ldg_u8d(blut + (ctx << 8) + (m >> (shift - 8)));
+        const uint32_t *row = ent + ctx * ns1 + k;
+        uint32_t e0 = ldg_u32d(row), e1 = ldg_u32d(row + 1);
+        while (m >= (e1 & 0xffff)) { row++; e0 = e1; e1 = ldg_u32d(row + 1); }
+        c0 = e0 & 0xffff; c1 = e1 & 0xffff;
+        return e0 >> 16;    // rank
+    }
+};
+template <bool ODD>
+__device__ __forceinline__ void dec_o1_fast_big(uint32_t &R_, uint32_t &ctx_, uint32_t &k_, uint32_t seg,
+                                                uint8_t *o, WordRing &w, const DecO1Big &T, uint32_t sym_s,
+                                                int lane, uint32_t lt) {
+    uint32_t R = R_, ctx = ctx_, k = k_, pos = w.pos;
+    const uint32_t mask = (1u << T.shift) - 1;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(w.ring);
+    while (k + 16 <= seg && pos + 16 * 64 <= w.end) {
+        uint32_t acc[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            w.pos = pos;
+            w.advance4(lane);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                uint32_t c0, c1;
+                const uint32_t r = T.look(R, ctx, c0, c1);
+                R = (c1 - c0) * (R >> T.shift) + (R & mask) - c0;
+                ctx = r;
+                acc[g] |= lds_u8a(sym_s + r) << (8 * u);
+                bool need = R < RANS_L;
+                uint32_t bal = __ballot_sync(FULL, need);
+                if (need) {
+                    uint32_t p = pos + 2 * __popc(bal & lt);
+                    uint32_t wv = ODD ? (lds_u8a(ring_s + (p & (RING - 1))) |
+                                         (lds_u8a(ring_s + ((p + 1) & (RING - 1))) << 8))
+                                      : lds_u16a(ring_s + (p & (RING - 1)));
+                    R = (R << 16) | wv;
+                }
+                pos += 2 * __popc(bal);
+            }
+        }
+        stg_u128(o + k, acc[0], acc[1], acc[2], acc[3]);
+        k += 16;
+    }
+    w.pos = pos;
+    cp_async_wait_all();
+    __syncwarp();
+    R_ = R; ctx_ = ctx; k_ = k;
+}
+
 // ------------------------------------------------------------------------
 // Order-1 table rows (rANS_static16_int.h:425-456, 488-530) parsed by the whole warp.
 // The byte stream is a sequence of tokens -- a varint count, or 0x00 followed by a raw
@@ -579,29 +651,42 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
     // --- table storage: shared memory when it fits, else the scratch pool
     DecO1Tabs T;
     T.nsym = nsym;
+    const bool big = nsym > 64;
+    const uint32_t ns1 = nsym + 1;
     uint32_t bb = 8;
     while (bb > 6 && dec_o1_tab_bytes(nsym, bb) > smem_tab_bytes) bb--;
-    uint32_t need = dec_o1_tab_bytes(nsym, bb);
+    uint32_t need = big ? nsym * ns1 * 4 + (nsym << 8) + 256 : dec_o1_tab_bytes(nsym, bb);
     uint8_t *tb;
-    const bool in_smem = need <= smem_tab_bytes;
+    const bool in_smem = !big && need <= smem_tab_bytes;
     if (in_smem) tb = smem_tabs;
     else { tb = pool_alloc(pool, need, lane); if (!tb) return 2; }
-    const uint32_t ns1 = nsym + 1;
-    T.cum = (uint16_t *)tb;
-    T.blut = tb + ((nsym * ns1 * 2 + 15) & ~15u);
-    T.sym = T.blut + (nsym << bb);
+    uint32_t *ent = (uint32_t *)tb;               // big: compact rows (DecO1Big)
+    uint32_t craw_stride = ns1;                   // raw counts: row stride in 16-bit units
+    if (big) {
+        // the raw 16-bit counts of row i are parsed into the upper half of ent row i and are
+        // in registers before the compact row overwrites them
+        T.cum = (uint16_t *)tb + ns1;
+        craw_stride = 2 * ns1;
+        T.blut = tb + nsym * ns1 * 4;
+        T.sym = T.blut + (nsym << 8);
+    } else {
+        T.cum = (uint16_t *)tb;
+        T.blut = tb + ((nsym * ns1 * 2 + 15) & ~15u);
+        T.sym = T.blut + (nsym << bb);
+    }
     for (int j = lane; j < 256; j += 32)          // presence from F0: rank 255 is a valid rank
         if (S.F0[j]) T.sym[S.rank[j]] = (uint8_t)j;
 
     // --- rows, in alphabet order: raw counts by parse_o1_rows, then scaling, cumulative
     // starts and validation one lane per row
     int err = 0;
-    for (uint32_t j = lane; j < nsym * ns1; j += 32) T.cum[j] = 0;
+    if (big) { for (uint32_t j = lane; j < nsym * ns1; j += 32) ent[j] = 0; }
+    else for (uint32_t j = lane; j < nsym * ns1; j += 32) T.cum[j] = 0;
     __syncwarp();
     if (cp >= tend) return 1;
     {
         const uint8_t *table_end = nullptr;
-        if (parse_o1_rows(cp, tend, nsym, tot, T.cum, ns1, lane, &table_end)) return 1;
+        if (parse_o1_rows(cp, tend, nsym, tot, T.cum, craw_stride, lane, &table_end)) return 1;
         cp = table_end;
     }
     __syncwarp();
@@ -638,39 +723,72 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
     } else {
         // large alphabets (tables in the L2-resident pool): the warp walks the rows together,
         // lanes over columns, so that global accesses coalesce
+        // (lane l holds columns 8l..8l+7: one prefix over the lane's eight and one warp scan)
+        const uint32_t bwb = shift - 8;
+        uint32_t *cnt = (uint32_t *)smem_tabs;                // 1 KiB scratch: the tables are in the pool
         for (uint32_t i = 0; i < nsym; i++) {
-            uint16_t *row = T.cum + i * ns1;
-            uint8_t *bl = T.blut + (i << bb);
-            uint32_t f[8], tsum = 0;
+            const uint16_t *raw = T.cum + i * craw_stride;
+            uint32_t *row = ent + i * ns1;
+            uint8_t *bl = T.blut + (i << 8);
+            uint32_t f[8], tsum = 0, nz = 0;
 #pragma unroll
             for (int t = 0; t < 8; t++) {
-                uint32_t c = lane + 32 * t;
-                f[t] = c < nsym ? row[c + 1] : 0;
+                uint32_t c = lane * 8 + t;
+                f[t] = c < nsym ? raw[c + 1] : 0;
                 tsum += f[t];
+                nz += f[t] ? 1 : 0;
             }
-            tsum = warp_sum(tsum);
+            if (warp_sum(tsum) > tot) { err = 1; continue; }            // (uniform) keeps the packed scan exact
+            uint32_t pk = warp_incl_scan(tsum | (nz << 16), lane);      // sum <= 4096, <= 256 non-zero
+            const uint32_t all = __shfl_sync(FULL, pk, 31);
+            const uint32_t rsum = all & 0xffff, nnz = all >> 16;
+            pk -= tsum | (nz << 16);
             int sh = 0;
-            if (tsum) { uint32_t z = tsum; while (z < tot) { z *= 2; sh++; } }
+            if (rsum) { uint32_t z = rsum; while (z < tot) { z *= 2; sh++; } }
+            __syncwarp();                                // every lane has read its raw counts
+            uint32_t x = (pk & 0xffff) << sh, k = pk >> 16;
+            bool bad = (rsum << sh) != tot && rsum != 0;
+            // bucket index: bucket b belongs to the last entry starting at or before its first
+            // slot, i.e. k(b) = #{entries with ceil(start / bucket) <= b} - 1: count the entries per
+            // first bucket in shared memory, then one prefix sum over the 256 buckets
+            *(uint4 *)(cnt + lane * 8) = make_uint4(0, 0, 0, 0);
+            *(uint4 *)(cnt + lane * 8 + 4) = make_uint4(0, 0, 0, 0);
             __syncwarp();
-            uint32_t basex = 0;
-            bool bad = false;
 #pragma unroll
             for (int t = 0; t < 8; t++) {
-                uint32_t c = lane + 32 * t, ff = f[t] << sh;
-                uint32_t incl = warp_incl_scan(ff, lane);
-                uint32_t x = basex + incl - ff;
-                if (c < nsym) {
-                    bad |= ff > tot || x > tot - ff;
-                    row[c] = (uint16_t)min(x, 65535u);
-                    if (ff && !bad) {      // buckets whose first slot falls inside [x, x+ff)
-                        for (uint32_t bk = (x + (1u << bw) - 1) >> bw; (bk << bw) < x + ff && bk < nb; bk++) bl[bk] = (uint8_t)c;
+                const uint32_t ff = f[t] << sh;
+                if (ff && !bad) {
+                    if (x + ff > tot) bad = true;
+                    else {
+                        row[k++] = x | ((lane * 8 + t) << 16);
+                        const uint32_t fb = (x + (1u << bwb) - 1) >> bwb;
+                        if (fb < 256) atomicAdd(&cnt[fb], 1u);
                     }
                 }
-                basex += __shfl_sync(FULL, incl, 31);
+                x += ff;
             }
-            if (lane == 0) row[nsym] = (uint16_t)min(basex, 65535u);
-            if (bad || (tsum && basex != tot)) err = 1;
-            if (!tsum && lane == 0) for (uint32_t bk = 0; bk < nb; bk++) bl[bk] = 0;
+            if (bad) err = 1;
+            if (lane == 0) {
+                if (rsum) row[nnz] = tot;                // sentinel
+                else { row[0] = 0; row[1] = tot; }       // empty row: never used by a valid stream
+            }
+            __syncwarp();
+            {
+                const uint4 a = *(const uint4 *)(cnt + lane * 8), b = *(const uint4 *)(cnt + lane * 8 + 4);
+                uint32_t c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}, loc = 0;
+#pragma unroll
+                for (int t = 0; t < 8; t++) { loc += c[t]; c[t] = loc; }
+                const uint32_t before = warp_incl_scan(loc, lane) - loc;
+                uint32_t o0 = 0, o1 = 0;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const uint32_t k0 = before + c[t], k1 = before + c[t + 4];
+                    o0 |= ((k0 ? k0 - 1 : 0) & 0xff) << (8 * t);
+                    o1 |= ((k1 ? k1 - 1 : 0) & 0xff) << (8 * t);
+                }
+                *(uint2 *)(bl + lane * 8) = make_uint2(o0, o1);
+            }
+            __syncwarp();
         }
     }
     err = __any_sync(FULL, err);
@@ -707,12 +825,26 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
     const uint8_t *blut = T.blut, *symtab = T.sym;
     const uint32_t ns = nsym;
 
+    DecO1Big B{ent, T.blut, ns1, shift};
+    if (big) {                                // rank -> symbol moves to shared memory (ranks are dead)
+        uint32_t v[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) v[t] = (uint32_t)lane + 32 * t < ns ? symtab[lane + 32 * t] : 0;
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 8; t++) S.rank[lane + 32 * t] = (uint8_t)v[t];
+        __syncwarp();
+        symtab = S.rank;
+    }
     auto step = [&](bool on) {
-        uint32_t m = R & mask;
-        uint32_t r = blut[(ctx << bb) + (m >> bw)];
-        const uint16_t *row = cumt + ctx * (ns + 1);
-        uint32_t c0 = row[r], c1 = row[r + 1];
-        while (m >= c1 && r + 1 < ns) { r++; c0 = c1; c1 = row[r + 1]; }
+        uint32_t m = R & mask, r, c0, c1;
+        if (big) r = B.look(R, ctx, c0, c1);
+        else {
+            r = blut[(ctx << bb) + (m >> bw)];
+            const uint16_t *row = cumt + ctx * (ns + 1);
+            c0 = row[r]; c1 = row[r + 1];
+            while (m >= c1 && r + 1 < ns) { r++; c0 = c1; c1 = row[r + 1]; }
+        }
         if (on) {
             R = (c1 - c0) * (R >> shift) + m - c0;
             ctx = r;
@@ -721,7 +853,11 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
     };
 
     uint32_t k = 0;
-    if (N == 32 && in_smem && ((((uintptr_t)out) | seg) & 15) == 0) {
+    if (N == 32 && big && ((((uintptr_t)out) | seg) & 15) == 0) {
+        const uint32_t sy_s = (uint32_t)__cvta_generic_to_shared(S.rank);
+        if (w.pos & 1) dec_o1_fast_big<true>(R, ctx, k, seg, o, w, B, sy_s, lane, lt);
+        else dec_o1_fast_big<false>(R, ctx, k, seg, o, w, B, sy_s, lane, lt);
+    } else if (N == 32 && in_smem && ((((uintptr_t)out) | seg) & 15) == 0) {
         const uint32_t fs_s = (uint32_t)__cvta_generic_to_shared(T.cum);
         const uint32_t bl_s = (uint32_t)__cvta_generic_to_shared(T.blut);
         const uint32_t sy_s = (uint32_t)__cvta_generic_to_shared(T.sym);

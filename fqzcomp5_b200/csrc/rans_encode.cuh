@@ -31,6 +31,17 @@ __device__ __forceinline__ uint4 ldg_u128(const uint4 *p) {
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(__cvta_generic_to_global(p)));
     return v;
 }
+// 16 bytes from any address: aligned 32-bit words funnel-shifted into place.  Reads only
+// words that hold at least one of the 16 bytes.  Plain (coherent) loads: the bytes may have
+// been produced by this kernel (PACK / RLE output).
+__device__ __forceinline__ uint4 ld16_any(const uint8_t *p) {
+    const uint32_t a = (uint32_t)((uintptr_t)p & 3);
+    const uint32_t *w = (const uint32_t *)(p - a);
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = a ? w[4] : 0u;
+    const uint32_t sh = a * 8;
+    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                      __funnelshift_r(w3, w4, sh));
+}
 // 16 bytes into shared-memory bins; equal neighbours are merged before an atomic is
 // issued (quality strings are sticky).  (A word-level "four equal bytes" shortcut was
 // measured slower: the two paths diverge within the warp.)
@@ -455,6 +466,254 @@ __device__ inline uint32_t put_freq_row(uint8_t *cp, const uint32_t *F, uint32_t
     return len;
 }
 
+// Alverson reciprocal of enc_sym_init without the 64-bit division: ceil(2^(sh+31) / freq) for
+// 2 <= freq <= 4096, 2^(sh-1) < freq <= 2^sh, by two 32-bit long-division steps.
+__device__ __forceinline__ uint32_t rcp_freq_small(uint32_t freq, uint32_t sh) {
+    uint32_t a = 1u << (sh + 19);                 // <= 2^31
+    uint32_t q1 = a / freq, r1 = a - q1 * freq;   // r1 < 4096
+    uint32_t b = r1 << 12;
+    uint32_t q2 = b / freq, r2 = b - q2 * freq;
+    return (q1 << 12) + q2 + (r2 ? 1u : 0u);
+}
+__device__ __forceinline__ uint2 enc_sym_make8(uint32_t start, uint32_t freq, uint32_t bits) {
+    if (freq < 2) return make_uint2(~0u, (start + (1u << bits) - 1) | (freq << 13));
+    uint32_t sh = 32 - __clz(freq - 1);
+    return make_uint2(rcp_freq_small(freq, sh), start | (freq << 13) | ((sh - 1) << 26));
+}
+
+// ------------------------------------------------------------------------
+// Order-1 model for large alphabets (nsym > 64): the warp walks the context rows one at a
+// time, lane l holding columns 8l..8l+7 in registers, so every access to the pair counts
+// and to the encoder symbols is a contiguous 32/64-byte piece per lane and nothing is
+// serialised over the row length.  Same arithmetic as the per-row code in enc_o1:
+//   sweep 1  row totals and the statistics of rans_compute_shift (rANS_static4x16pr.c:357-420)
+//   sweep 2  normalise_freq (rANS_static16_int.h:97-146), encode_freq_d (:278-306) at a
+//            running offset, scaled starts and encoder symbols (rANS_word.h:201-272)
+// H rows are left normalised (as the per-row code leaves them).  Returns 0 ok, 1 fail.
+// ------------------------------------------------------------------------
+__device__ inline int enc_o1_rows_wide(uint32_t *H, uint32_t nsym, EncO1Smem &S, const uint8_t *in, uint32_t n,
+                                       uint8_t *out, uint32_t hdr, uint2 *symtab, int lane,
+                                       uint32_t *shift_out, uint32_t *tl_out) {
+    const uint32_t j0 = (uint32_t)lane * 8;
+    const uint32_t last_rank = S.rank[in[n - 1]];
+    const bool vec = (nsym & 3) == 0;
+    auto load_row = [&](const uint32_t *row, uint32_t (&f)[8]) {
+        if (vec && j0 + 8 <= nsym) {
+            uint4 a = *(const uint4 *)(row + j0), b = *(const uint4 *)(row + j0 + 4);
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+        } else {
+#pragma unroll
+            for (int t = 0; t < 8; t++) f[t] = j0 + t < nsym ? row[j0 + t] : 0;
+        }
+    };
+    // ---- sweep 1
+    double e10 = 0, e12 = 0;
+    uint32_t max_tot = 0;
+    for (uint32_t i = 0; i < nsym; i++) {
+        uint32_t f[8], loc = 0;
+        load_row(H + (size_t)i * nsym, f);
+#pragma unroll
+        for (int t = 0; t < 8; t++) loc += f[t];
+        const uint32_t Ti = warp_sum(loc) + (i == last_rank ? 1u : 0u);
+        if (lane == 0) S.T[i] = Ti;
+        if (!Ti) { if (lane == 0) S.S[i] = 0; continue; }
+        uint32_t max_val = round2(Ti);
+        uint32_t cnt = 0;                           // ns | sm10 << 10 | sm12 << 20
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            if (!f[t]) continue;
+            cnt += 1;
+            if ((uint64_t)f[t] * 1025 <= max_val) cnt += 1u << 10;     // max_val / f > 1024
+            if ((uint64_t)f[t] * 4097 <= max_val) cnt += 1u << 20;     // max_val / f > 4096
+        }
+        cnt = warp_sum(cnt);
+        const uint32_t ns = cnt & 1023, sm10 = (cnt >> 10) & 1023, sm12 = cnt >> 20;
+        const double l10 = log((double)(1024 + sm10)), l12 = log((double)(4096 + sm12));
+        const double T_slow = (double)4096 / Ti, T_fast = (double)1024 / Ti;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            if (!f[t]) continue;
+            double a = f[t] * T_fast, b = f[t] * T_slow;
+            e10 -= f[t] * (fast_log(a > 1 ? a : 1) - l10);
+            e12 -= f[t] * (fast_log(b > 1 ? b : 1) - l12);
+            e10 += 1.3;
+            e12 += 4.7;
+        }
+        if (ns < 64 && max_val > 128) max_val /= 2;
+        if (max_val > 1024) max_val /= 2;
+        if (max_val > 4096) max_val = 4096;
+        if (lane == 0) S.S[i] = (uint16_t)max_val;
+        if (max_tot < max_val) max_tot = max_val;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        e10 += __shfl_xor_sync(FULL, e10, o);
+        e12 += __shfl_xor_sync(FULL, e12, o);
+    }
+    const uint32_t shift = (e10 / e12 < 1.01 || max_tot <= 1024) ? 10 : 12;
+    __syncwarp();
+
+    // ---- sweep 2
+    uint32_t off = hdr;
+    int err = 0;
+    for (uint32_t i = 0; i < nsym; i++) {
+        const uint32_t Ti = S.T[i];
+        if (!Ti) continue;
+        uint32_t *row = H + (size_t)i * nsym;
+        uint32_t f[8];
+        load_row(row, f);
+        uint32_t mv = S.S[i];
+        if (shift == 10 && mv > 1024) mv = 1024;
+        // normalise_freq(row, Ti, mv)
+        {
+            uint32_t size = Ti;
+            for (int pass = 0; pass < 2; pass++) {
+                const uint64_t tr = ((uint64_t)mv << 31) / size + (uint32_t)((1 << 30) / (int)size);
+                uint32_t top = 0, arg = 0, sum = 0;
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    uint32_t v = f[t];
+                    if (!v) continue;
+                    if (top < v) { top = v; arg = j0 + t; }
+                    v = (uint32_t)((v * tr) >> 31);
+                    if (!v) v = 1;
+                    f[t] = v;
+                    sum += v;
+                }
+                sum = warp_sum(sum);
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {      // max, ties -> lowest index
+                    uint32_t t2 = __shfl_xor_sync(FULL, top, o), a2 = __shfl_xor_sync(FULL, arg, o);
+                    if (t2 > top || (t2 == top && a2 < arg)) { top = t2; arg = a2; }
+                }
+                const uint32_t big = top ? arg : 0;
+                uint32_t mine = 0;
+#pragma unroll
+                for (int t = 0; t < 8; t++) if ((big & 7) == (uint32_t)t) mine = f[t];
+                const uint32_t fb = __shfl_sync(FULL, mine, big >> 3);
+                int adjust = (int)mv - (int)sum;
+                const bool own = (big >> 3) == (uint32_t)lane;
+                if (adjust >= 0 || (fb > (uint32_t)-adjust && (pass == 1 || fb / 2 >= (uint32_t)-adjust))) {
+                    if (own) {
+#pragma unroll
+                        for (int t = 0; t < 8; t++) if ((big & 7) == (uint32_t)t) f[t] += adjust;
+                    }
+                    break;
+                }
+                if (pass == 0) { size = sum; continue; }
+                // greedy shave (rare): serial over the row through shared memory
+                uint32_t *tmp = S.rowlen;
+#pragma unroll
+                for (int t = 0; t < 8; t++) tmp[j0 + t] = f[t];
+                __syncwarp();
+                if (lane == 0) {
+                    adjust += (int)fb - 1;
+                    tmp[big] = 1;
+                    for (uint32_t j = 0; adjust && j < nsym; j++) {
+                        if (tmp[j] < 2) continue;
+                        int d = (tmp[j] > (uint32_t)-adjust) ? adjust : 1 - (int)tmp[j];
+                        tmp[j] += d;
+                        adjust -= d;
+                    }
+                    if (!tmp[big]) err = 1;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < 8; t++) f[t] = tmp[j0 + t];
+                __syncwarp();
+            }
+        }
+        if (lane == 0) S.S[i] = (uint16_t)mv;
+        // the row stays normalised in H (the table coder and later readers expect it)
+        if (vec && j0 + 8 <= nsym) {
+            *(uint4 *)(row + j0) = make_uint4(f[0], f[1], f[2], f[3]);
+            *(uint4 *)(row + j0 + 4) = make_uint4(f[4], f[5], f[6], f[7]);
+        } else {
+#pragma unroll
+            for (int t = 0; t < 8; t++) if (j0 + t < nsym) row[j0 + t] = f[t];
+        }
+        // zero bitmap of the row: zb[u] covers columns 32u..32u+31 (columns >= nsym read as non-zero)
+        uint32_t m8 = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) if (j0 + t < nsym && !f[t]) m8 |= 1u << t;
+        uint32_t wz = m8 << (8 * (lane & 3));
+        wz |= __shfl_xor_sync(FULL, wz, 1);
+        wz |= __shfl_xor_sync(FULL, wz, 2);
+        uint32_t zb[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) zb[u] = __shfl_sync(FULL, wz, 4 * u);
+        // first non-zero column at or after the start of word u (256 if none)
+        uint32_t nz[9];
+        nz[8] = 256;
+#pragma unroll
+        for (int u = 7; u >= 0; u--) nz[u] = ~zb[u] ? 32 * u + __ffs(~zb[u]) - 1 : nz[u + 1];
+        // bytes per entry and scaled frequency, prefix over the row in column order
+        int sh = 0;
+        while ((mv << sh) < (1u << shift)) sh++;
+        uint32_t len[8], run[8], tot8 = 0;
+        const uint32_t myw = lane >> 2;                       // word holding this lane's 8 columns
+        uint32_t zw = 0, nzn = 256;
+#pragma unroll
+        for (int u = 0; u < 8; u++) if (myw == (uint32_t)u) { zw = zb[u]; nzn = nz[u + 1]; }
+        const uint32_t prevw_top = myw ? 0u : 0u;
+        (void)prevw_top;
+        uint32_t zprev = 0;                                   // bit 31 of the previous word
+#pragma unroll
+        for (int u = 1; u < 8; u++) if (myw == (uint32_t)u) zprev = zb[u - 1] >> 31;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const uint32_t j = j0 + t, bit = j & 31;
+            uint32_t l = 0, r = 0;
+            if (j < nsym) {
+                if (f[t]) l = f[t] >= 128 ? 2 : 1;
+                else {
+                    const uint32_t pz = bit ? (zw >> (bit - 1)) & 1 : zprev;
+                    if (!pz) {
+                        const uint32_t w = (~zw) >> bit;
+                        const uint32_t end = w ? j + __ffs(w) - 1 : nzn;
+                        l = 2;
+                        r = min(end, nsym) - j;
+                    }
+                }
+            }
+            len[t] = l; run[t] = r;
+            tot8 += l | ((f[t] << sh) << 16);
+        }
+        uint32_t ex = warp_incl_scan(tot8, lane);
+        const uint32_t rowbytes = __shfl_sync(FULL, ex, 31) & 0xffff;
+        ex -= tot8;
+        uint32_t o = off + (ex & 0xffff), x = ex >> 16;
+        uint2 e8[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const uint32_t fs = f[t] << sh;
+            if (len[t]) {
+                if (f[t]) {
+                    if (len[t] == 2) { out[o] = (uint8_t)(0x80 | (f[t] >> 7)); out[o + 1] = (uint8_t)(f[t] & 0x7f); }
+                    else out[o] = (uint8_t)f[t];
+                } else { out[o] = 0; out[o + 1] = (uint8_t)(run[t] - 1); }
+                o += len[t];
+            }
+            e8[t] = enc_sym_make8(x, fs, shift);
+            x += fs;
+        }
+        uint2 *srow = symtab + (size_t)i * nsym;
+        if (vec && j0 + 8 <= nsym) {
+#pragma unroll
+            for (int t = 0; t < 8; t += 2)
+                *(uint4 *)(srow + j0 + t) = make_uint4(e8[t].x, e8[t].y, e8[t + 1].x, e8[t + 1].y);
+        } else {
+#pragma unroll
+            for (int t = 0; t < 8; t++) if (j0 + t < nsym) srow[j0 + t] = e8[t];
+        }
+        off += rowbytes;
+    }
+    if (__any_sync(FULL, err)) return 1;
+    *shift_out = shift;
+    *tl_out = off;
+    return 0;
+}
+
 template <int N>
 __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_end,
                       uint32_t *tab_len, uint8_t **ptr_out, EncO1Smem &S, uint8_t *dyn, uint32_t dyn_bytes,
@@ -557,108 +816,138 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
     // lanes 1..N-1 start in context 0 (rANS_static16_int.h:325-327)
     if (lane >= 1 && lane < N) atomicAdd(&H[S.rank[0] * nsym + S.rank[in[lane * seg]]], 1u);
     __syncwarp();
-    // row totals; the last symbol's total gets one extra (utils.h:311,345)
-    for (uint32_t i0 = 0; i0 < nsym; i0 += 32) { const uint32_t i = i0 + lane; if (i >= nsym) continue;
-        uint32_t t = 0;
-        for (uint32_t j = 0; j < nsym; j++) t += H[i * nsym + j];
-        if (S.sym[i] == in[n - 1]) t++;
-        S.T[i] = t;                     // now rank space
-    }
-    __syncwarp();
-
-    // ---- precision: 10 or 12 bits (rANS_static4x16pr.c:357-420), lane per row
-    double e10 = 0, e12 = 0;
-    uint32_t max_tot = 0;
-    for (uint32_t i0 = 0; i0 < nsym; i0 += 32) { const uint32_t i = i0 + lane; if (i >= nsym) continue;
-        const uint32_t *row = H + i * nsym;
-        uint32_t Ti = S.T[i];
-        if (!Ti) { S.S[i] = 0; continue; }
-        uint32_t max_val = round2(Ti);
-        int ns = 0, sm10 = 0, sm12 = 0;
-        for (uint32_t j = 0; j < nsym; j++) {
-            uint32_t f = row[j];
-            if (f && max_val / f > 1024) sm10++;
-            if (f && max_val / f > 4096) sm12++;
-        }
-        double l10 = log((double)(1024 + sm10)), l12 = log((double)(4096 + sm12));
-        double T_slow = (double)4096 / Ti, T_fast = (double)1024 / Ti;
-        for (uint32_t j = 0; j < nsym; j++) {
-            uint32_t f = row[j];
-            if (!f) continue;
-            ns++;
-            double a = f * T_fast, b = f * T_slow;
-            e10 -= f * (fast_log(a > 1 ? a : 1) - l10);
-            e12 -= f * (fast_log(b > 1 ? b : 1) - l12);
-            e10 += 1.3;
-            e12 += 4.7;
-        }
-        if (ns < 64 && max_val > 128) max_val /= 2;
-        if (max_val > 1024) max_val /= 2;
-        if (max_val > 4096) max_val = 4096;
-        S.S[i] = (uint16_t)max_val;
-        if (max_tot < max_val) max_tot = max_val;
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        e10 += __shfl_xor_sync(FULL, e10, o);
-        e12 += __shfl_xor_sync(FULL, e12, o);
-        max_tot = max(max_tot, __shfl_xor_sync(FULL, max_tot, o));
-    }
-    const uint32_t shift = (e10 / e12 < 1.01 || max_tot <= 1024) ? 10 : 12;
-
-    // ---- rows: normalise to the stored total, measure, serialise, scale, symbols
     uint2 *symtab;
     if (sym_smem) symtab = (uint2 *)(dyn + h_bytes);
     else { symtab = (uint2 *)pool_alloc(pool, hw * 8, lane); if (!symtab) return 2; }
-    int err = 0;
-    for (uint32_t i0 = 0; i0 < nsym; i0 += 32) { const uint32_t i = i0 + lane; if (i >= nsym) continue;
-        uint32_t *row = H + i * nsym;
-        uint32_t Ti = S.T[i];
-        if (!Ti) { S.rowlen[i] = 0; continue; }
-        uint32_t mv = S.S[i];
-        if (shift == 10 && mv > 1024) mv = 1024;
-        if (normalise_freq_row(row, nsym, Ti, mv) < 0) err = 1;
-        S.S[i] = (uint16_t)mv;
-        S.rowlen[i] = put_freq_row(nullptr, row, nsym);
-    }
-    if (__any_sync(FULL, err)) return 1;
-    __syncwarp();
-    uint32_t hdr = 0;
-    if (lane == 0) {
-        // alphabet of the CONTEXTS that have a row, with 0 forced in (:357-361)
-        uint32_t *A = S.rowlen + 0;            // reuse not possible: build a private mark array
-        (void)A;
-        uint8_t *cp = out;
-        *cp++ = 0;
-        // put_alphabet over symbol space: mark = row total != 0 (or symbol 0)
-        int j = 0;
-        // listed = occurs in the data (or is 0); every such symbol has a non-zero row total.
-        // (rank 255 is a valid rank, so presence is kept separately from rank[])
-        auto present = [&](int s) { return (S.pres[s >> 5] >> (s & 31)) & 1; };
-        while (j < 256) {
-            if (!present(j)) { j++; continue; }
-            *cp++ = (uint8_t)j;
-            if (j && present(j - 1)) {
-                int k = j + 1;
-                while (k < 256 && present(k)) k++;
-                *cp++ = (uint8_t)(k - (j + 1));
-                j = k;
-            } else j++;
+    uint32_t shift = 12, tl = 0;
+    const bool wide = nsym > 64;              // large alphabets: row-at-a-time, lanes across columns
+    if (wide) {
+        uint32_t hdr = 0;
+        if (lane == 0) {                      // alphabet of the contexts, 0 forced in (:357-361)
+            uint8_t *cp = out;
+            *cp++ = 0;
+            auto present = [&](int s) { return (S.pres[s >> 5] >> (s & 31)) & 1; };
+            int j = 0;
+            while (j < 256) {
+                if (!present(j)) { j++; continue; }
+                *cp++ = (uint8_t)j;
+                if (j && present(j - 1)) {
+                    int k = j + 1;
+                    while (k < 256 && present(k)) k++;
+                    *cp++ = (uint8_t)(k - (j + 1));
+                    j = k;
+                } else j++;
+            }
+            *cp++ = 0;
+            hdr = (uint32_t)(cp - out);
         }
-        *cp++ = 0;
-        hdr = (uint32_t)(cp - out);
-        uint32_t off = hdr;                      // exclusive scan of row lengths
-        for (uint32_t i = 0; i < nsym; i++) { uint32_t l = S.rowlen[i]; S.rowlen[i] = off; off += l; }
-        hdr = off;
+        hdr = __shfl_sync(FULL, hdr, 0);
+        __syncwarp();
+        if (enc_o1_rows_wide(H, nsym, S, in, n, out, hdr, symtab, lane, &shift, &tl)) return 1;
+        __threadfence_block();
+        __syncwarp();
+        out[0] = (uint8_t)(shift << 4);
+    } else {
+        // row totals; the last symbol's total gets one extra (utils.h:311,345)
+        for (uint32_t i0 = 0; i0 < nsym; i0 += 32) { const uint32_t i = i0 + lane; if (i >= nsym) continue;
+            uint32_t t = 0;
+            for (uint32_t j = 0; j < nsym; j++) t += H[i * nsym + j];
+            if (S.sym[i] == in[n - 1]) t++;
+            S.T[i] = t;                     // now rank space
+        }
+        __syncwarp();
+
+        // ---- precision: 10 or 12 bits (rANS_static4x16pr.c:357-420), lane per row
+        double e10 = 0, e12 = 0;
+        uint32_t max_tot = 0;
+        for (uint32_t i0 = 0; i0 < nsym; i0 += 32) { const uint32_t i = i0 + lane; if (i >= nsym) continue;
+            const uint32_t *row = H + i * nsym;
+            uint32_t Ti = S.T[i];
+            if (!Ti) { S.S[i] = 0; continue; }
+            uint32_t max_val = round2(Ti);
+            int ns = 0, sm10 = 0, sm12 = 0;
+            for (uint32_t j = 0; j < nsym; j++) {
+                uint32_t f = row[j];
+                if (f && max_val / f > 1024) sm10++;
+                if (f && max_val / f > 4096) sm12++;
+            }
+            double l10 = log((double)(1024 + sm10)), l12 = log((double)(4096 + sm12));
+            double T_slow = (double)4096 / Ti, T_fast = (double)1024 / Ti;
+            for (uint32_t j = 0; j < nsym; j++) {
+                uint32_t f = row[j];
+                if (!f) continue;
+                ns++;
+                double a = f * T_fast, b = f * T_slow;
+                e10 -= f * (fast_log(a > 1 ? a : 1) - l10);
+                e12 -= f * (fast_log(b > 1 ? b : 1) - l12);
+                e10 += 1.3;
+                e12 += 4.7;
+            }
+            if (ns < 64 && max_val > 128) max_val /= 2;
+            if (max_val > 1024) max_val /= 2;
+            if (max_val > 4096) max_val = 4096;
+            S.S[i] = (uint16_t)max_val;
+            if (max_tot < max_val) max_tot = max_val;
+        }
+    #pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            e10 += __shfl_xor_sync(FULL, e10, o);
+            e12 += __shfl_xor_sync(FULL, e12, o);
+            max_tot = max(max_tot, __shfl_xor_sync(FULL, max_tot, o));
+        }
+        shift = (e10 / e12 < 1.01 || max_tot <= 1024) ? 10 : 12;
+
+        // ---- rows: normalise to the stored total, measure, serialise, scale, symbols
+        int err = 0;
+        for (uint32_t i0 = 0; i0 < nsym; i0 += 32) { const uint32_t i = i0 + lane; if (i >= nsym) continue;
+            uint32_t *row = H + i * nsym;
+            uint32_t Ti = S.T[i];
+            if (!Ti) { S.rowlen[i] = 0; continue; }
+            uint32_t mv = S.S[i];
+            if (shift == 10 && mv > 1024) mv = 1024;
+            if (normalise_freq_row(row, nsym, Ti, mv) < 0) err = 1;
+            S.S[i] = (uint16_t)mv;
+            S.rowlen[i] = put_freq_row(nullptr, row, nsym);
+        }
+        if (__any_sync(FULL, err)) return 1;
+        __syncwarp();
+        uint32_t hdr = 0;
+        if (lane == 0) {
+            // alphabet of the CONTEXTS that have a row, with 0 forced in (:357-361)
+            uint32_t *A = S.rowlen + 0;            // reuse not possible: build a private mark array
+            (void)A;
+            uint8_t *cp = out;
+            *cp++ = 0;
+            // put_alphabet over symbol space: mark = row total != 0 (or symbol 0)
+            int j = 0;
+            // listed = occurs in the data (or is 0); every such symbol has a non-zero row total.
+            // (rank 255 is a valid rank, so presence is kept separately from rank[])
+            auto present = [&](int s) { return (S.pres[s >> 5] >> (s & 31)) & 1; };
+            while (j < 256) {
+                if (!present(j)) { j++; continue; }
+                *cp++ = (uint8_t)j;
+                if (j && present(j - 1)) {
+                    int k = j + 1;
+                    while (k < 256 && present(k)) k++;
+                    *cp++ = (uint8_t)(k - (j + 1));
+                    j = k;
+                } else j++;
+            }
+            *cp++ = 0;
+            hdr = (uint32_t)(cp - out);
+            uint32_t off = hdr;                      // exclusive scan of row lengths
+            for (uint32_t i = 0; i < nsym; i++) { uint32_t l = S.rowlen[i]; S.rowlen[i] = off; off += l; }
+            hdr = off;
+        }
+        tl = __shfl_sync(FULL, hdr, 0);
+        __syncwarp();
+        for (uint32_t i0 = 0; i0 < nsym; i0 += 32) { const uint32_t i = i0 + lane; if (i >= nsym) continue;
+            if (S.T[i]) put_freq_row(out + S.rowlen[i], H + i * nsym, nsym);
+        }
+        __threadfence_block();
+        __syncwarp();
+        out[0] = (uint8_t)(shift << 4);
     }
-    uint32_t tl = __shfl_sync(FULL, hdr, 0);
-    __syncwarp();
-    for (uint32_t i0 = 0; i0 < nsym; i0 += 32) { const uint32_t i = i0 + lane; if (i >= nsym) continue;
-        if (S.T[i]) put_freq_row(out + S.rowlen[i], H + i * nsym, nsym);
-    }
-    __threadfence_block();
-    __syncwarp();
-    out[0] = (uint8_t)(shift << 4);
 
     // the table, once complete, may itself go through the 4-lane order-0 coder (:396-412)
     int pool_fail = 0;
@@ -690,7 +979,8 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
         }
         __syncwarp();
     };
-    if (h_global) compress_table();               // its scratch aliases the symbol area
+    if (h_global || wide) compress_table();       // its scratch aliases the symbol area
+    if (!wide)
     for (uint32_t i0 = 0; i0 < nsym; i0 += 32) { const uint32_t i = i0 + lane; if (i >= nsym) continue;
         uint32_t *row = H + i * nsym;
         if (!S.T[i]) continue;
@@ -706,7 +996,7 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
     }
     __threadfence_block();
     __syncwarp();
-    if (!h_global) compress_table();              // its scratch aliases the (now dead) pair counts
+    if (!h_global && !wide) compress_table();     // its scratch aliases the (now dead) pair counts
     if (pool_fail) return 2;
     *tab_len = tl;
 
@@ -784,6 +1074,41 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
             rc = rn;
         }
         kstart = 1;
+    } else if (N == 32 && seg >= 32) {
+        // Encoder symbols in global memory (large alphabets): the 16 symbols of a group are
+        // requested together before the group's 16 steps run, so one L2/DRAM round trip is paid
+        // per group instead of per step.  Groups are counted from the END of the lane's segment
+        // (any alignment, any length); the seg % 16 bytes at its start go through the loop below.
+        const uint32_t rank_s = (uint32_t)__cvta_generic_to_shared(S.rank);
+        const uint32_t J = seg >> 4, lead = seg & 15;
+        const uint8_t *g0 = q + lead;                          // group j = bytes g0[16j .. 16j+15]
+        auto rank_of = [&](uint32_t b) {
+            uint32_t r;
+            asm("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(rank_s + b));
+            return r;
+        };
+        const uint32_t rank0 = rank_of(0);
+        uint4 cur = ld16_any(g0 + 16 * (J - 1));
+        for (uint32_t j = J; j-- > 0;) {
+            uint4 prv = j ? ld16_any(g0 + 16 * (j - 1)) : make_uint4(0, 0, 0, 0);
+            const uint32_t w4[4] = {cur.x, cur.y, cur.z, cur.w};
+            uint32_t rk[17];
+            rk[0] = j ? rank_of(prv.w >> 24) : (lead ? rank_of(g0[-1]) : rank0);
+#pragma unroll
+            for (int b = 0; b < 16; b++) rk[b + 1] = rank_of((w4[b >> 2] >> (8 * (b & 3))) & 0xff);
+            uint2 ev[16];
+#pragma unroll
+            for (int b = 0; b < 16; b++) ev[b] = symtab[rk[b] * nsym + rk[b + 1]];      // (written by this kernel: no ld.nc)
+#pragma unroll
+            for (int b = 15; b >= 0; b--) {
+                if (b == 0 && j == 0 && !lead) break;        // the lane's first symbol is coded below
+                if ((b & 3) == 3) w.maybe_flush(lane);
+                R = enc_step(R, true, enc_sym_unpack(ev[b], shift), w, lane);
+            }
+            rs = lead ? rk[0] : rk[1];                       // rank of the next symbol to code
+            cur = prv;
+        }
+        kstart = lead ? lead : 1;
     }
     for (uint32_t k = kstart; k-- > 1;) {
         uint32_t rc = rank[q[k - 1]];
