@@ -215,7 +215,8 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
             J.route = 1;                     // the order-1 kernel (larger shared memory per warp)
             n_o1++;
             // symbol table (16 B/pair), pair counts (4 B/pair), coded table scratch
-            pool_bytes += 256 * 256 * 12 + 300 * 1024;
+            // + 16-bit pair keys of the partitioned pair count (large alphabets without a model)
+            pool_bytes += 256 * 256 * 12 + 300 * 1024 + (J.model ? 0 : 2 * (size_t)isz + 2048);
         } else n_o0++;
     };
     size_t si = 0;
@@ -226,7 +227,7 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
             StripePlan &sp = stripes[si++];
             sp.o_transposed = L.take(in_size[k], 256);
             place(jobs[j], d_in + in_off[k], in_size[k], order[k], cap, (uint32_t)k);
-            if (jobs[j].route) { n_o1--; pool_bytes -= 256 * 256 * 12 + 300 * 1024; } else n_o0--;
+            if (jobs[j].route) { n_o1--; pool_bytes -= 256 * 256 * 12 + 300 * 1024 + (jobs[j].model ? 0 : 2 * (size_t)in_size[k] + 2048); } else n_o0--;
             if (jobs[j].model) { jobs[j].model = nullptr; n_model--; }
             jobs[j].route = 2;               // assembled by stripe_select, not coded
             jobs[j].stripe_n = sp.N;
@@ -316,10 +317,10 @@ int dec_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
         if (f & (X_PACK | X_RLE)) J.tmp = (uint8_t *)L.take((size_t)out_cap[k] * 2 + 4096, 256);
         if ((f & 1) && !(f & X_CAT)) {
             J.route = 1; n_o1++;
-            pool_bytes += 257 * 257 * 3 + 257 * 256 * 4 + 256 * 256 + 16 * 1024;   // table text + DecO1Big
+            pool_bytes += 257 * 257 * 3 + 257 * 256 * 4 + 256 * 2048 + 16 * 1024;   // table text + DecO1Big
         } else n_o0++;
     }
-    pool_bytes = std::min<size_t>(pool_bytes, (size_t)2 << 30);
+    pool_bytes = std::min<size_t>(pool_bytes, (size_t)16 << 30);
     pool_bytes = std::max<size_t>(pool_bytes, (size_t)8 << 20);
     size_t o_pool = L.take(pool_bytes, 256);
     int r = Ln.work.ensure(L.off + 256);

@@ -444,35 +444,52 @@ __device__ __forceinline__ void dec_o1_fast(uint32_t &R_, uint32_t &ctx_, uint32
     R_ = R; ctx_ = ctx; k_ = k;
 }
 
-// Large alphabets (nsym > 64): tables in global memory (L2), rows COMPACTED to the symbols
-// that occur in the context:
-//   ent[ctx][k]  = start | rank << 16 of the k-th symbol with a non-zero frequency in ctx,
-//                  closed by a sentinel whose start is the total (so freq = next.start - start
-//                  and the forward scan needs no bound)
-//   blut[ctx][b] = k of the symbol owning the first slot of bucket b (256 buckets)
-// so a look-up never walks over the (many) absent symbols of a sparse row.
-__device__ __forceinline__ uint32_t ldg_u8d(const uint8_t *p) {
-    uint32_t v;
-    asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(__cvta_generic_to_global(p)));
-    return v;
-}
+// Large alphabets (nsym > 64): tables in global memory.  With thousands of streams and up to
+// 64 Ki (context, symbol) pairs each, a look-up is a DRAM access, so the layout makes it ONE
+// 32-byte sector and no dependent second load:
+//   entry        = start << 20 | (freq - 1) << 8 | rank      (start < 4096, freq <= 4096)
+//   rec[ctx][b]  = 8 words for bucket b of 64 (slot >> (shift - 6)): the entry owning the
+//                  bucket's first slot and the next six that start inside the bucket (padded by
+//                  repeating the last one), then an overflow word: 0xffffffff, or
+//                  start << 20 | k of the eighth such entry (rare; continues in ent)
+//   ent[ctx][k]  = the context's entries in slot order (only symbols with a non-zero
+//                  frequency), closed by 0xffffffff
+// The symbol is the entry with the largest start <= slot: a max over seven selects.
 __device__ __forceinline__ uint32_t ldg_u32d(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(__cvta_generic_to_global(p)));
     return v;
 }
 struct DecO1Big {
+    const uint32_t *rec;    // [nsym][64][8]
     const uint32_t *ent;    // [nsym][nsym+1]
-    const uint8_t *blut;    // [nsym][256]
     uint32_t ns1, shift;
-    __device__ __forceinline__ uint32_t look(uint32_t R, uint32_t ctx, uint32_t &c0, uint32_t &c1) const {
-        const uint32_t m = R & ((1u << shift) - 1);
-        uint32_t k = ldg_u8d(blut + (ctx << 8) + (m >> (shift - 8)));
-        const uint32_t *row = ent + ctx * ns1 + k;
-        uint32_t e0 = ldg_u32d(row), e1 = ldg_u32d(row + 1);
-        while (m >= (e1 & 0xffff)) { row++; e0 = e1; e1 = ldg_u32d(row + 1); }
-        c0 = e0 & 0xffff; c1 = e1 & 0xffff;
-        return e0 >> 16;    // rank
+    // returns the entry for slot m in context ctx
+    __device__ __forceinline__ uint32_t look(uint32_t m, uint32_t ctx) const {
+        const uint32_t *r = rec + (((ctx << 6) + (m >> (shift - 6))) << 3);
+        uint4 a, c;
+        asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w)
+                     : "l"(__cvta_generic_to_global(r)));
+        asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w)
+                     : "l"(__cvta_generic_to_global(r + 4)));
+        const uint32_t T = (m << 20) | 0xfffff;              // entries with start <= m are <= T
+        uint32_t best = a.x;                                 // the bucket's first entry always qualifies
+        best = max(best, a.y <= T ? a.y : 0u);
+        best = max(best, a.z <= T ? a.z : 0u);
+        best = max(best, a.w <= T ? a.w : 0u);
+        best = max(best, c.x <= T ? c.x : 0u);
+        best = max(best, c.y <= T ? c.y : 0u);
+        best = max(best, c.z <= T ? c.z : 0u);
+        if (c.w <= T && c.w != 0xffffffffu) {                // more than seven entries reach into the bucket
+            const uint32_t *e = ent + ctx * ns1 + (c.w & 0xfffff);
+            best = ldg_u32d(e);
+            for (;;) {
+                const uint32_t nx = ldg_u32d(++e);
+                if (nx == 0xffffffffu || nx > T) break;
+                best = nx;
+            }
+        }
+        return best;
     }
 };
 template <bool ODD>
@@ -490,9 +507,10 @@ __device__ __forceinline__ void dec_o1_fast_big(uint32_t &R_, uint32_t &ctx_, ui
             w.advance4(lane);
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                uint32_t c0, c1;
-                const uint32_t r = T.look(R, ctx, c0, c1);
-                R = (c1 - c0) * (R >> T.shift) + (R & mask) - c0;
+                const uint32_t m = R & mask;
+                const uint32_t e = T.look(m, ctx);
+                const uint32_t r = e & 0xff;
+                R = (((e >> 8) & 0xfff) + 1) * (R >> T.shift) + m - (e >> 20);
                 ctx = r;
                 acc[g] |= lds_u8a(sym_s + r) << (8 * u);
                 bool need = R < RANS_L;
@@ -655,7 +673,8 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
     const uint32_t ns1 = nsym + 1;
     uint32_t bb = 8;
     while (bb > 6 && dec_o1_tab_bytes(nsym, bb) > smem_tab_bytes) bb--;
-    uint32_t need = big ? nsym * ns1 * 4 + (nsym << 8) + 256 : dec_o1_tab_bytes(nsym, bb);
+    const uint32_t ent_bytes = (nsym * ns1 * 4 + 31) & ~31u;      // records start on a sector boundary
+    uint32_t need = big ? ent_bytes + (nsym << 11) + 256 : dec_o1_tab_bytes(nsym, bb);
     uint8_t *tb;
     const bool in_smem = !big && need <= smem_tab_bytes;
     if (in_smem) tb = smem_tabs;
@@ -667,8 +686,8 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
         // in registers before the compact row overwrites them
         T.cum = (uint16_t *)tb + ns1;
         craw_stride = 2 * ns1;
-        T.blut = tb + nsym * ns1 * 4;
-        T.sym = T.blut + (nsym << 8);
+        T.blut = tb + ent_bytes;                      // big: the bucket records (DecO1Big::rec)
+        T.sym = T.blut + (nsym << 11);
     } else {
         T.cum = (uint16_t *)tb;
         T.blut = tb + ((nsym * ns1 * 2 + 15) & ~15u);
@@ -724,12 +743,13 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
         // large alphabets (tables in the L2-resident pool): the warp walks the rows together,
         // lanes over columns, so that global accesses coalesce
         // (lane l holds columns 8l..8l+7: one prefix over the lane's eight and one warp scan)
-        const uint32_t bwb = shift - 8;
-        uint32_t *cnt = (uint32_t *)smem_tabs;                // 1 KiB scratch: the tables are in the pool
+        const uint32_t bwb = shift - 6, B = 1u << bwb;        // 64 buckets of B slots
+        uint32_t *cnt = (uint32_t *)smem_tabs;                // scratch: the tables are in the pool
+        uint32_t *crow = cnt + 64;                            // the row's entries, <= 257 words
+        uint32_t *recs = (uint32_t *)T.blut;
         for (uint32_t i = 0; i < nsym; i++) {
             const uint16_t *raw = T.cum + i * craw_stride;
             uint32_t *row = ent + i * ns1;
-            uint8_t *bl = T.blut + (i << 8);
             uint32_t f[8], tsum = 0, nz = 0;
 #pragma unroll
             for (int t = 0; t < 8; t++) {
@@ -745,48 +765,54 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
             pk -= tsum | (nz << 16);
             int sh = 0;
             if (rsum) { uint32_t z = rsum; while (z < tot) { z *= 2; sh++; } }
+            if (rsum && (rsum << sh) != tot) { err = 1; continue; }     // (uniform)
+            cnt[lane] = 0; cnt[lane + 32] = 0;
             __syncwarp();                                // every lane has read its raw counts
             uint32_t x = (pk & 0xffff) << sh, k = pk >> 16;
-            bool bad = (rsum << sh) != tot && rsum != 0;
-            // bucket index: bucket b belongs to the last entry starting at or before its first
-            // slot, i.e. k(b) = #{entries with ceil(start / bucket) <= b} - 1: count the entries per
-            // first bucket in shared memory, then one prefix sum over the 256 buckets
-            *(uint4 *)(cnt + lane * 8) = make_uint4(0, 0, 0, 0);
-            *(uint4 *)(cnt + lane * 8 + 4) = make_uint4(0, 0, 0, 0);
-            __syncwarp();
 #pragma unroll
             for (int t = 0; t < 8; t++) {
                 const uint32_t ff = f[t] << sh;
-                if (ff && !bad) {
-                    if (x + ff > tot) bad = true;
-                    else {
-                        row[k++] = x | ((lane * 8 + t) << 16);
-                        const uint32_t fb = (x + (1u << bwb) - 1) >> bwb;
-                        if (fb < 256) atomicAdd(&cnt[fb], 1u);
-                    }
+                if (ff) {
+                    const uint32_t e = (x << 20) | ((ff - 1) << 8) | (lane * 8 + t);
+                    crow[k] = e;
+                    row[k++] = e;
+                    // an entry belongs to the bucket records from ceil(start / B) on
+                    const uint32_t fb = (x + B - 1) >> bwb;
+                    if (fb < 64) atomicAdd(&cnt[fb], 1u);
                 }
                 x += ff;
             }
-            if (bad) err = 1;
-            if (lane == 0) {
-                if (rsum) row[nnz] = tot;                // sentinel
-                else { row[0] = 0; row[1] = tot; }       // empty row: never used by a valid stream
-            }
+            if (lane == 0) row[nnz] = 0xffffffffu;       // closes the row (an empty row is only this)
             __syncwarp();
-            {
-                const uint4 a = *(const uint4 *)(cnt + lane * 8), b = *(const uint4 *)(cnt + lane * 8 + 4);
-                uint32_t c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}, loc = 0;
+            // bucket b's first entry: k(b) = #{entries with ceil(start / B) <= b} - 1
+            const uint32_t c0 = cnt[2 * lane], c1 = cnt[2 * lane + 1];
+            const uint32_t upto = warp_incl_scan(c0 + c1, lane);
 #pragma unroll
-                for (int t = 0; t < 8; t++) { loc += c[t]; c[t] = loc; }
-                const uint32_t before = warp_incl_scan(loc, lane) - loc;
-                uint32_t o0 = 0, o1 = 0;
+            for (int h = 0; h < 2; h++) {
+                const uint32_t b = 2 * lane + h;
+                const uint32_t kin = h ? upto : upto - c1;              // entries starting at or before b*B
+                const uint32_t bend = (b + 1) << bwb;
+                uint32_t wv[8];
+                uint32_t lastv = 0;
 #pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    const uint32_t k0 = before + c[t], k1 = before + c[t + 4];
-                    o0 |= ((k0 ? k0 - 1 : 0) & 0xff) << (8 * t);
-                    o1 |= ((k1 ? k1 - 1 : 0) & 0xff) << (8 * t);
+                for (int q = 0; q < 7; q++) {
+                    const uint32_t kk = kin - 1 + q;
+                    uint32_t e = lastv;
+                    if (kin && kk < nnz) {
+                        const uint32_t ce = crow[kk];
+                        if (q == 0 || (ce >> 20) < bend) e = ce;
+                    }
+                    wv[q] = e;
+                    lastv = e;
                 }
-                *(uint2 *)(bl + lane * 8) = make_uint2(o0, o1);
+                wv[7] = 0xffffffffu;
+                if (kin && kin + 6 < nnz) {
+                    const uint32_t ce = crow[kin + 6];
+                    if ((ce >> 20) < bend) wv[7] = (ce & 0xfff00000u) | (kin + 6);
+                }
+                uint4 *dst = (uint4 *)(recs + ((size_t)((i << 6) + b) << 3));
+                dst[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                dst[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
             }
             __syncwarp();
         }
@@ -825,7 +851,7 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
     const uint8_t *blut = T.blut, *symtab = T.sym;
     const uint32_t ns = nsym;
 
-    DecO1Big B{ent, T.blut, ns1, shift};
+    DecO1Big B{(const uint32_t *)T.blut, ent, ns1, shift};
     if (big) {                                // rank -> symbol moves to shared memory (ranks are dead)
         uint32_t v[8];
 #pragma unroll
@@ -838,8 +864,10 @@ __device__ int dec_o1(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
     }
     auto step = [&](bool on) {
         uint32_t m = R & mask, r, c0, c1;
-        if (big) r = B.look(R, ctx, c0, c1);
-        else {
+        if (big) {
+            const uint32_t e = B.look(m, ctx);
+            r = e & 0xff; c0 = e >> 20; c1 = c0 + ((e >> 8) & 0xfff) + 1;
+        } else {
             r = blut[(ctx << bb) + (m >> bw)];
             const uint16_t *row = cumt + ctx * (ns + 1);
             c0 = row[r]; c1 = row[r + 1];

@@ -714,6 +714,100 @@ __device__ inline int enc_o1_rows_wide(uint32_t *H, uint32_t nsym, EncO1Smem &S,
     return 0;
 }
 
+// ------------------------------------------------------------------------
+// Pair counts for large alphabets without random read-modify-write on a 256 KiB table per
+// stream (thousands of streams thrash L2 and every increment becomes a DRAM round trip):
+//   1. the number of pairs per context follows from the order-0 counts, so the pairs can be
+//      dealt straight into per-bucket regions (bucket = 8 consecutive context ranks) as
+//      16-bit keys (rank(prev) & 7) * nsym + rank(cur): sequential writes to <= 32 cursors;
+//   2. each bucket is counted in shared memory (8 rows x nsym counters) and its rows are
+//      written to H once, contiguously.  H needs no zeroing.
+// T = order-0 counts in symbol space; cur = 32 cursors in shared memory; cnt = 8*nsym words.
+// ------------------------------------------------------------------------
+__device__ inline void pair_counts_partitioned(const uint8_t *in, uint32_t n, uint32_t nsym, const uint32_t *T,
+                                               const uint8_t *rank, const uint8_t *symof, uint32_t *H,
+                                               uint16_t *keys, uint32_t *cur, uint32_t *cnt, int lane) {
+    const uint32_t nb = (nsym + 7) >> 3;
+    // pairs whose context is symbol s: occurrences of s except as the last byte, plus the
+    // virtual 0 in front of the first byte
+    uint32_t bsize = 0;
+    if ((uint32_t)lane < nb) {
+        for (uint32_t r = lane * 8; r < min(nsym, (uint32_t)lane * 8 + 8); r++) {
+            const uint32_t s = symof[r];
+            bsize += T[s] - (s == in[n - 1] ? 1u : 0u) + (s == 0 ? 1u : 0u);
+        }
+    }
+    const uint32_t padded = (bsize + 7) & ~7u;                 // regions start on 16-byte boundaries
+    const uint32_t boff = warp_incl_scan(padded, lane) - padded;
+    cur[lane] = boff;
+    __syncwarp();
+    auto deal = [&](uint32_t rp, uint32_t rc) {
+        const uint32_t pos = atomicAdd(&cur[rp >> 3], 1u);
+        keys[pos] = (uint16_t)((rp & 7) * nsym + rc);
+    };
+    {
+        uint32_t head = (uint32_t)((16 - ((uintptr_t)in & 15)) & 15);
+        if (head > n) head = n;
+        if ((uint32_t)lane < head) deal(rank[lane ? in[lane - 1] : 0], rank[in[lane]]);
+        const uint8_t *p = in + head;
+        const uint32_t rest = n - head, nv = rest >> 4;
+        const uint4 *v = (const uint4 *)p;
+        uint32_t carry_last = head ? in[head - 1] : 0;
+        uint4 q = (uint32_t)lane < nv ? v[lane] : make_uint4(0, 0, 0, 0);
+        for (uint32_t base = 0; base < nv; base += 32) {
+            const uint32_t i = base + lane;
+            const bool on = i < nv;
+            const uint4 qn = i + 32 < nv ? v[i + 32] : make_uint4(0, 0, 0, 0);   // next round, in flight
+            const uint32_t lastb = q.w >> 24;
+            uint32_t pb = __shfl_up_sync(FULL, lastb, 1);
+            if (lane == 0) pb = carry_last;
+            const uint32_t nact = min(32u, nv - base);
+            carry_last = __shfl_sync(FULL, lastb, nact - 1);
+            if (on) {
+                const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+                uint32_t rp = rank[pb];
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const uint32_t rc = rank[(w4[a] >> (8 * b)) & 0xff];
+                        deal(rp, rc);
+                        rp = rc;
+                    }
+            }
+            q = qn;
+        }
+        for (uint32_t i = (nv << 4) + lane; i < rest; i += 32) {
+            const uint32_t pos = head + i;
+            deal(rank[pos ? in[pos - 1] : 0], rank[in[pos]]);
+        }
+    }
+    __threadfence_block();
+    __syncwarp();
+    const uint32_t words = 8 * nsym;
+    for (uint32_t b = 0; b < nb; b++) {
+        for (uint32_t j = lane * 4; j < words; j += 128) *(uint4 *)(cnt + j) = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        const uint32_t o = __shfl_sync(FULL, boff, b), sz = __shfl_sync(FULL, bsize, b);
+        const uint4 *kv = (const uint4 *)(keys + o);             // 8 keys per load
+        for (uint32_t i = lane; i * 8 < sz; i += 32) {
+            const uint4 k8 = kv[i];
+            const uint32_t w4[4] = {k8.x, k8.y, k8.z, k8.w};
+            const uint32_t left = sz - i * 8;
+#pragma unroll
+            for (int a = 0; a < 8; a++)
+                if ((uint32_t)a < left) atomicAdd(&cnt[(w4[a >> 1] >> (16 * (a & 1))) & 0xffff], 1u);
+        }
+        __syncwarp();
+        const uint32_t rows = min(8u, nsym - 8 * b);
+        uint32_t *dst = H + (size_t)8 * b * nsym;
+        for (uint32_t j = lane; j < rows * nsym; j += 32) dst[j] = cnt[j];
+        __syncwarp();
+    }
+    __threadfence_block();
+    __syncwarp();
+}
+
 template <int N>
 __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_end,
                       uint32_t *tab_len, uint8_t **ptr_out, EncO1Smem &S, uint8_t *dyn, uint32_t dyn_bytes,
@@ -766,7 +860,11 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
     if (h_global) H = const_cast<uint32_t *>(model) + MODEL_HDR_WORDS;
     else if (h_smem) H = (uint32_t *)dyn;
     else { H = (uint32_t *)pool_alloc(pool, hw * 4, lane); if (!H) return 2; }
-    if (!model) {
+    if (!model && nsym > 64 && 8 * nsym * 4 <= dyn_bytes && n >= 2) {
+        uint16_t *keys = (uint16_t *)pool_alloc(pool, 2 * n + 2048, lane);
+        if (!keys) return 2;
+        pair_counts_partitioned(in, n, nsym, S.T, S.rank, S.sym, H, keys, S.rowlen, (uint32_t *)dyn, lane);
+    } else if (!model) {
         for (uint32_t j = lane; j < hw; j += 32) H[j] = 0;
         __syncwarp();
         const uint8_t *rank = S.rank;
