@@ -3,6 +3,7 @@
 // around the coders in rans_encode.cuh / rans_decode.cuh, plus the size scan and
 // the gather that packs finished streams back to back.
 #include <stdlib.h>
+#include <atomic>
 #include "kernels.h"
 #include "rans_decode.cuh"
 #include "rans_encode.cuh"
@@ -176,7 +177,7 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
 }
 
 template <bool O1>
-__global__ void __launch_bounds__((O1 ? ENC_WARPS_O1 : ENC_WARPS) * 32)
+__global__ void __launch_bounds__((O1 ? ENC_WARPS_O1 : ENC_WARPS) * 32, O1 ? 11 : 1)   // O1: 22 warps per SM (<= 92 registers)
 enc_kernel(EncJob *jobs, uint32_t njobs, uint32_t warp_smem, Pool pool) {
     extern __shared__ __align__(16) uint8_t smem_all[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -505,8 +506,27 @@ cudaError_t launch_hist(EncJob *d_jobs, uint32_t n, cudaStream_t st) {
 // ------------------------------------------------------------------------ launchers
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
+// the shared reciprocal table of the order-1 encoder, filled once per device
+static cudaError_t ensure_rcp_table(cudaStream_t st) {
+    static std::atomic<bool> done[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) dev = 63;
+    if (dev == 63 || !done[dev].load(std::memory_order_acquire)) {
+        rcp_table_kernel<<<17, 256, 0, st>>>();      // idempotent; later work on `st` is ordered after it
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(st);               // other streams of this device may encode next
+        if (e != cudaSuccess) return e;
+        done[dev].store(true, std::memory_order_release);
+    }
+    return cudaSuccess;
+}
+
 cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStream_t st) {
     if (!n) return cudaSuccess;
+    if (o1) { cudaError_t e = ensure_rcp_table(st); if (e != cudaSuccess) return e; }
     uint32_t ws = o1 ? ENC_SMEM_O1 : ENC_SMEM_O0;
     if (o1) {                              // tuning knob: shared memory per order-1 stream
         static const char *e = getenv("B200RANS_ENC_O1_SMEM");

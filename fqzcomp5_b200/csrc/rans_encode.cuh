@@ -220,19 +220,28 @@ __device__ __forceinline__ uint4 enc_sym_init(uint32_t start, uint32_t freq, uin
     return s;
 }
 
-// Compact 8-byte form for the order-1 tables (nsym^2 entries per stream):
-//   x = rcp_freq, y = bias | freq<<13 | (rcp_shift-32)<<26.  x_max and cmpl_freq follow from
-// freq and the stream's precision, so shared memory holds twice as many streams.
-__device__ __forceinline__ uint2 enc_sym_pack(uint4 s, uint32_t freq) {
-    return make_uint2(s.y, s.z | (freq << 13) | ((s.w >> 16) << 26));
+// Compact 4-byte form for the order-1 tables (nsym^2 entries per stream):
+//   bias | freq << 13 | (rcp_shift - 32) << 26.
+// x_max and cmpl_freq follow from freq and the stream's precision; the 32-bit reciprocal
+// depends on freq alone and comes from a 4097-entry table in global memory that every
+// stream shares (L1-resident), so shared memory holds four times as many pairs as with full
+// 16-byte symbols and the order-1 kernels keep twice the warps resident.
+__device__ uint32_t g_rcp_freq[4097];
+__device__ __forceinline__ uint32_t enc_sym_pack(uint4 s, uint32_t freq) {
+    return s.z | (freq << 13) | ((s.w >> 16) << 26);
 }
-__device__ __forceinline__ uint4 enc_sym_unpack(uint2 c, uint32_t bits) {
-    uint32_t f = (c.y >> 13) & 0x1fff;
+__device__ __forceinline__ uint32_t rcp_of_freq(uint32_t f) {
+    uint32_t v;
+    asm("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(__cvta_generic_to_global(g_rcp_freq + f)));
+    return v;
+}
+__device__ __forceinline__ uint4 enc_sym_unpack(uint32_t c, uint32_t bits) {
+    uint32_t f = (c >> 13) & 0x1fff;
     uint4 s;
     s.x = (f << (31 - bits)) - 1;
-    s.y = c.x;
-    s.z = c.y & 0x1fff;
-    s.w = (((1u << bits) - f) & 0xffff) | ((c.y >> 26) << 16);
+    s.y = rcp_of_freq(f);
+    s.z = c & 0x1fff;
+    s.w = (((1u << bits) - f) & 0xffff) | ((c >> 26) << 16);
     return s;
 }
 
@@ -441,10 +450,12 @@ struct __align__(16) EncO1Smem {
     uint8_t  rank[256];
     uint8_t  sym[256];      // rank -> symbol
     uint16_t S[256];        // per-row stored total (rank space)
-    uint32_t rowlen[256];   // serialised row lengths / offsets (rank space)
     uint32_t pres[8];       // alphabet membership bitmap (symbol space)
     uint32_t pad_[4];
-    uint8_t  ring[ORING];   // output staging (OutRing)
+    union {                 // the model-building scratch is dead when the output ring starts
+        uint32_t rowlen[256];   // serialised row lengths / offsets (rank space), partition cursors
+        uint8_t  ring[ORING];   // output staging (OutRing)
+    };
 };                          // followed by dynamic storage: nsym*nsym pair counts when they fit
 
 // serialise one row against the alphabet (rANS_static16_int.h:278-306): every
@@ -475,10 +486,16 @@ __device__ __forceinline__ uint32_t rcp_freq_small(uint32_t freq, uint32_t sh) {
     uint32_t q2 = b / freq, r2 = b - q2 * freq;
     return (q1 << 12) + q2 + (r2 ? 1u : 0u);
 }
-__device__ __forceinline__ uint2 enc_sym_make8(uint32_t start, uint32_t freq, uint32_t bits) {
-    if (freq < 2) return make_uint2(~0u, (start + (1u << bits) - 1) | (freq << 13));
+__device__ __forceinline__ uint32_t enc_sym_make4(uint32_t start, uint32_t freq, uint32_t bits) {
+    if (freq < 2) return (start + (1u << bits) - 1) | (freq << 13);
     uint32_t sh = 32 - __clz(freq - 1);
-    return make_uint2(rcp_freq_small(freq, sh), start | (freq << 13) | ((sh - 1) << 26));
+    return start | (freq << 13) | ((sh - 1) << 26);
+}
+// fills g_rcp_freq (once per device): rcp of enc_sym_init for every possible frequency
+__global__ void rcp_table_kernel() {
+    uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f > 4096) return;
+    g_rcp_freq[f] = f < 2 ? ~0u : rcp_freq_small(f, 32 - __clz(f - 1));
 }
 
 // ------------------------------------------------------------------------
@@ -492,7 +509,7 @@ __device__ __forceinline__ uint2 enc_sym_make8(uint32_t start, uint32_t freq, ui
 // H rows are left normalised (as the per-row code leaves them).  Returns 0 ok, 1 fail.
 // ------------------------------------------------------------------------
 __device__ inline int enc_o1_rows_wide(uint32_t *H, uint32_t nsym, EncO1Smem &S, const uint8_t *in, uint32_t n,
-                                       uint8_t *out, uint32_t hdr, uint2 *symtab, int lane,
+                                       uint8_t *out, uint32_t hdr, uint32_t *symtab, int lane,
                                        uint32_t *shift_out, uint32_t *tl_out) {
     const uint32_t j0 = (uint32_t)lane * 8;
     const uint32_t last_rank = S.rank[in[n - 1]];
@@ -683,7 +700,7 @@ __device__ inline int enc_o1_rows_wide(uint32_t *H, uint32_t nsym, EncO1Smem &S,
         const uint32_t rowbytes = __shfl_sync(FULL, ex, 31) & 0xffff;
         ex -= tot8;
         uint32_t o = off + (ex & 0xffff), x = ex >> 16;
-        uint2 e8[8];
+        uint32_t e8[8];
 #pragma unroll
         for (int t = 0; t < 8; t++) {
             const uint32_t fs = f[t] << sh;
@@ -694,14 +711,13 @@ __device__ inline int enc_o1_rows_wide(uint32_t *H, uint32_t nsym, EncO1Smem &S,
                 } else { out[o] = 0; out[o + 1] = (uint8_t)(run[t] - 1); }
                 o += len[t];
             }
-            e8[t] = enc_sym_make8(x, fs, shift);
+            e8[t] = enc_sym_make4(x, fs, shift);
             x += fs;
         }
-        uint2 *srow = symtab + (size_t)i * nsym;
+        uint32_t *srow = symtab + (size_t)i * nsym;
         if (vec && j0 + 8 <= nsym) {
-#pragma unroll
-            for (int t = 0; t < 8; t += 2)
-                *(uint4 *)(srow + j0 + t) = make_uint4(e8[t].x, e8[t].y, e8[t + 1].x, e8[t + 1].y);
+            *(uint4 *)(srow + j0) = make_uint4(e8[0], e8[1], e8[2], e8[3]);
+            *(uint4 *)(srow + j0 + 4) = make_uint4(e8[4], e8[5], e8[6], e8[7]);
         } else {
 #pragma unroll
             for (int t = 0; t < 8; t++) if (j0 + t < nsym) srow[j0 + t] = e8[t];
@@ -855,7 +871,7 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
     const bool h_global = model != nullptr;
     const uint32_t h_bytes = h_global ? 0 : max((hw * 4 + 15) & ~15u, (uint32_t)sizeof(EncO0Smem));
     const bool h_smem = !h_global && h_bytes <= dyn_bytes;
-    const bool sym_smem = (h_global || h_smem) && h_bytes + hw * 8 <= dyn_bytes;
+    const bool sym_smem = (h_global || h_smem) && h_bytes + hw * 4 <= dyn_bytes;
     EncO0Smem *o0s = (EncO0Smem *)dyn;           // dead H, or not-yet-built symbols
     if (h_global) H = const_cast<uint32_t *>(model) + MODEL_HDR_WORDS;
     else if (h_smem) H = (uint32_t *)dyn;
@@ -914,9 +930,9 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
     // lanes 1..N-1 start in context 0 (rANS_static16_int.h:325-327)
     if (lane >= 1 && lane < N) atomicAdd(&H[S.rank[0] * nsym + S.rank[in[lane * seg]]], 1u);
     __syncwarp();
-    uint2 *symtab;
-    if (sym_smem) symtab = (uint2 *)(dyn + h_bytes);
-    else { symtab = (uint2 *)pool_alloc(pool, hw * 8, lane); if (!symtab) return 2; }
+    uint32_t *symtab;
+    if (sym_smem) symtab = (uint32_t *)(dyn + h_bytes);
+    else { symtab = (uint32_t *)pool_alloc(pool, hw * 4, lane); if (!symtab) return 2; }
     uint32_t shift = 12, tl = 0;
     const bool wide = nsym > 64;              // large alphabets: row-at-a-time, lanes across columns
     if (wide) {
@@ -1088,7 +1104,7 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
         uint32_t x = 0;
         for (uint32_t j = 0; j < nsym; j++) {
             uint32_t f = row[j] << sh;
-            symtab[i * nsym + j] = enc_sym_pack(enc_sym_init(x, f, shift), f);
+            symtab[i * nsym + j] = enc_sym_make4(x, f, shift);
             x += f;
         }
     }
@@ -1131,8 +1147,8 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
             return (w >> (8 * (b & 3))) & 0xff;
         };
         auto lds_sym = [&](uint32_t a) {
-            uint2 r;
-            asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a));
+            uint32_t r;
+            asm("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
             return enc_sym_unpack(r, shift);
         };
         auto rank_of = [&](uint32_t b) {
@@ -1143,7 +1159,7 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
         // the encoder symbol of the NEXT step is fetched (rank look-up, table look-up, unpack)
         // while the current step runs: none of it depends on the state
         uint32_t rc = rank_of(byte_of(cur, 14));
-        uint4 e = lds_sym(sym_s + (rc * nsym + rs) * 8);
+        uint4 e = lds_sym(sym_s + (rc * nsym + rs) * 4);
         for (uint32_t j = J - 1; j >= 1; j--) {
             uint4 nn = j >= 2 ? ldg_u128(v + j - 2) : make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -1151,7 +1167,7 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
                 // next step codes byte b-1 in the context of byte b-2 (crossing into nxt at the low end)
                 uint32_t nb = b >= 2 ? byte_of(cur, b - 2) : byte_of(nxt, 14 + b);
                 uint32_t rn = rank_of(nb);
-                uint4 en = lds_sym(sym_s + (rn * nsym + rc) * 8);
+                uint4 en = lds_sym(sym_s + (rn * nsym + rc) * 4);
                 if ((b & 3) == 3) w.maybe_flush(lane);
                 R = enc_step(R, true, e, w, lane);
                 e = en;
@@ -1164,7 +1180,7 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
 #pragma unroll
         for (int b = 15; b >= 1; b--) {                      // group 0: its byte 0 is the lane's first symbol
             uint32_t rn = b >= 2 ? rank_of(byte_of(cur, b - 2)) : 0;
-            uint4 en = b >= 2 ? lds_sym(sym_s + (rn * nsym + rc) * 8) : e;
+            uint4 en = b >= 2 ? lds_sym(sym_s + (rn * nsym + rc) * 4) : e;
             if ((b & 3) == 3) w.maybe_flush(lane);
             R = enc_step(R, true, e, w, lane);
             e = en;
@@ -1194,7 +1210,7 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
             rk[0] = j ? rank_of(prv.w >> 24) : (lead ? rank_of(g0[-1]) : rank0);
 #pragma unroll
             for (int b = 0; b < 16; b++) rk[b + 1] = rank_of((w4[b >> 2] >> (8 * (b & 3))) & 0xff);
-            uint2 ev[16];
+            uint32_t ev[16];
 #pragma unroll
             for (int b = 0; b < 16; b++) ev[b] = symtab[rk[b] * nsym + rk[b + 1]];      // (written by this kernel: no ld.nc)
 #pragma unroll
