@@ -31,6 +31,7 @@ EXPORTS = [
     "b200rans_uncompress_batch_dev", "b200rans_compress_batch_multi",
     "b200rans_uncompress_batch_multi", "b200rans_launch_count", "b200rans_version",
     "b200rans_set_profiling", "b200rans_last_kernel_ms",
+    "b200rans_compress_methods_batch", "b200rans_compress_methods", "b200rans_compress_trials",
 ]
 
 _lib = None
@@ -79,6 +80,10 @@ def lib():
         L.b200rans_uncompress_batch_dev.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.b200rans_compress_batch_multi.argtypes = [i32, i32, vp, vp, vp, vp, vp, sz, vp, vp]
         L.b200rans_uncompress_batch_multi.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
+        L.b200rans_compress_methods_batch.argtypes = [i32, vp, vp, i32, vp, vp, sz, vp, vp, vp, vp]
+        L.b200rans_compress_trials.argtypes = [i32, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp]
+        L.b200rans_compress_methods.argtypes = [vp, u32, i32, vp, pu32, pi32, vp]
+        L.b200rans_compress_methods.restype = vp
         L.b200rans_launch_count.restype = C.c_uint64
         L.b200rans_version.restype = C.c_char_p
         L.b200rans_set_profiling.argtypes = [i32]
@@ -204,6 +209,123 @@ def compress_batch(buf, offsets, sizes, orders, out=None, ngpu=1, block_of=None)
                                              _addr(out_off), _addr(out_size))
     _check(rc, "b200rans_compress_batch")
     return out, out_off, out_size
+
+
+# rANS members of fqzcomp5's method enum (fqzcomp5.c:120-131) -> `order` argument
+# (fqzcomp5.c:2005-2022); RANSXN1 needs the block's fixed read length.
+RANS_METHOD_ORDERS = {"RANS0": 0, "RANS1": 1, "RANS64": 64, "RANS65": 65,
+                      "RANS128": 128, "RANS129": 129, "RANS192": 192, "RANS193": 193}
+
+
+def ransxn1_order(fixed_len):
+    """fqzcomp5.c:2019: (fq->fixed_len << 8) + 9."""
+    return (int(fixed_len) << 8) + 9
+
+
+def compress_methods_batch(buf, offsets, sizes, methods, out=None):
+    """Method trial (fqzcomp5.c:1979-2119, rANS members): every slice of `buf` is encoded
+    under each `order` value in `methods`; the first smallest stream of each is returned.
+
+    Returns (out_array, out_off, out_size, best, csize) with best[k] the index into
+    `methods` and csize[k, j] the size under method j (0 = that call failed)."""
+    L = lib()
+    n = len(sizes)
+    M = len(methods)
+    ptrs = (np.asarray(offsets, np.uint64) + np.uint64(_addr(buf))).astype(np.uint64)
+    sizes = np.ascontiguousarray(sizes, np.uint32)
+    meth = np.ascontiguousarray(methods, np.int32)
+    if out is None:
+        cap = 256
+        for k in range(n):
+            cap += max(rans_compress_bound_4x16(int(sizes[k]), int(m)) for m in meth) + 32
+        out = np.empty(cap, np.uint8)
+    out_off = np.zeros(n, np.uint64)
+    out_size = np.zeros(n, np.uint32)
+    best = np.full(n, -1, np.int32)
+    csize = np.zeros((n, M), np.uint32)
+    rc = L.b200rans_compress_methods_batch(n, _addr(ptrs), _addr(sizes), M, _addr(meth), _addr(out), out.size,
+                                           _addr(out_off), _addr(out_size), _addr(best), _addr(csize))
+    _check(rc, "b200rans_compress_methods_batch")
+    return out, out_off, out_size, best, csize
+
+
+def compress_trials(buf, offsets, sizes, method_lists, out=None):
+    """Ragged method trial: slice k of `buf` is tried under method_lists[k] (a list of `order`
+    values).  Returns (out_array, out_off, out_size, best, csize_lists)."""
+    L = lib()
+    n = len(sizes)
+    ptrs = (np.asarray(offsets, np.uint64) + np.uint64(_addr(buf))).astype(np.uint64)
+    sizes = np.ascontiguousarray(sizes, np.uint32)
+    first = np.zeros(n + 1, np.uint32)
+    first[1:] = np.cumsum([len(m) for m in method_lists])
+    flat = np.ascontiguousarray([o for m in method_lists for o in m], np.int32)
+    if out is None:
+        cap = 256
+        for k in range(n):
+            cap += max(rans_compress_bound_4x16(int(sizes[k]), int(m)) for m in method_lists[k]) + 32
+        out = np.empty(cap, np.uint8)
+    out_off = np.zeros(n, np.uint64)
+    out_size = np.zeros(n, np.uint32)
+    best = np.full(n, -1, np.int32)
+    csize = np.zeros(len(flat), np.uint32)
+    rc = L.b200rans_compress_trials(n, _addr(ptrs), _addr(sizes), _addr(first), _addr(flat), _addr(out), out.size,
+                                    _addr(out_off), _addr(out_size), _addr(best), _addr(csize))
+    _check(rc, "b200rans_compress_trials")
+    return out, out_off, out_size, best, [csize[first[k]:first[k + 1]].tolist() for k in range(n)]
+
+
+# tok3's per-token-type method tables (tokenise_name3.c:1283-1357, rANS build: bit 0x04 cleared at
+# :1374-1375); levels 1-9 map to rows 0-4 by (level-1)//2.  Token types in enum order
+# (tokenise_name3.c:96-112): TYPE ALPHA CHAR DIGITS0 DZLEN DUP DIFF DIGITS DDELTA DDELTA0 MATCH NOP END.
+TOK3_TYPES = ["TYPE", "ALPHA", "CHAR", "DIGITS0", "DZLEN", "DUP", "DIFF", "DIGITS", "DDELTA", "DDELTA0",
+              "MATCH", "NOP", "END"]
+
+
+# R[level][type] of tokenise_name3.c:1283-1357, one row per level group (-1, -3, -5, -7, -9)
+TOK3_METHODS = [
+    [[128], [129], [0], [8], [0], [8], [8], [8], [0], [128], [0], [0], [0]],
+    [[192, 0], [129, 1], [0], [136, 0], [0], [200], [136], [200], [0], [128], [0], [0], [0]],
+    [[192, 0], [1, 128, 0, 129], [0], [200, 0], [0], [200], [192, 200], [132, 201], [0], [128], [0], [0], [0]],
+    [[193, 0, 1], [128, 1, 128, 0, 129], [1, 0], [200, 0], [0], [201], [192, 200], [132, 201], [0], [128], [0],
+     [0], [0]],
+    [[192, 0, 1, 65, 193, 132], [132, 1, 0, 129], [1, 0, 192], [201, 0, 192, 64], [0, 128, 1], [201],
+     [192, 201, 65], [132, 201, 1, 192, 129, 193], [1, 0, 192], [192, 1, 0], [0], [0], [0]],
+]
+
+
+def tok3_level_row(level):
+    """tokenise_name3.c:1275-1278: levels 1-9 -> rows 0-4."""
+    return min(4, max(0, (level - 1) // 2))
+
+
+def tok3_method_list(table_row, in_len):
+    """The candidate list tok3's compress() walks for one token stream: the row of its R[level][type]
+    table with X32 cleared (:1374-1375) and STRIPE entries dropped when in_len % 4 != 0 (:1377-1378)."""
+    out = []
+    for m in table_row:
+        m &= ~4
+        if in_len % 4 != 0 and (m & 8):
+            continue
+        out.append(m)
+    return out
+
+
+def compress_methods(data, methods):
+    """Single buffer, malloc()ed winner: (bytes or None, best, csize)."""
+    L = lib()
+    data = bytes(data)
+    src = C.create_string_buffer(data, max(len(data), 1))
+    meth = np.ascontiguousarray(methods, np.int32)
+    csize = np.zeros(len(meth), np.uint32)
+    sz = C.c_uint(0)
+    best = C.c_int(-1)
+    r = L.b200rans_compress_methods(C.addressof(src), len(data), len(meth), _addr(meth), C.byref(sz),
+                                    C.byref(best), _addr(csize))
+    if not r:
+        return None, best.value, csize
+    out = C.string_at(r, sz.value)
+    _libc.free(r)
+    return out, best.value, csize
 
 
 def uncompress_batch(comp, comp_off, comp_size, out, out_off, out_size, ngpu=1, block_of=None):

@@ -168,13 +168,26 @@ inline int effective_order(uint32_t in_size, int order) {
     return order;
 }
 
+// Method trial (compress_with_methods, fqzcomp5.c:1979-2119; tok3's compress(),
+// tokenise_name3.c:1268-1417): the n calls of an enc_core batch are groups of candidate
+// encodings of the same input, calls d_first[k] .. d_first[k+1]-1 belonging to input k.
+// Every candidate's size goes to d_csize, the first smallest of each group is kept and
+// d_out_off / d_out_size / d_best are per input.
+struct Trial {
+    uint32_t inputs;
+    const uint32_t *d_first;    // [inputs + 1]
+    uint32_t *d_csize;          // [n]
+    uint32_t *d_jobidx;         // [n] scratch
+    int32_t *d_best;            // [inputs]
+};
+
 // Build and run the encode of a batch whose inputs are already on the device.
 // On return (asynchronously on st): d_out holds the packed streams, d_out_off /
 // d_out_size / d_total describe them.
 int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, const uint64_t *in_off,
              const uint32_t *in_size, const int *order, const uint32_t *caps,
              uint8_t *d_out, size_t out_cap, uint64_t *d_out_off, uint32_t *d_out_size,
-             uint64_t *d_total) {
+             uint64_t *d_total, const Trial *trial = nullptr) {
     if (n <= 0) return 0;
     // ---- pass 1: count jobs and size scratch
     std::vector<StripePlan> stripes;
@@ -195,7 +208,7 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
     std::vector<EncJob> jobs(njobs);
     size_t o_jobs = L.take(njobs * sizeof(EncJob));
     size_t o_ctr = L.take(256);
-    uint32_t n_o0 = 0, n_o1 = 0, n_model = 0;
+    uint32_t n_o0 = 0, n_o1 = 0, n_o1w = 0, n_model = 0;
     size_t pool_bytes = 0;
     // ---- pass 2: place slots / work buffers
     auto place = [&](EncJob &J, const uint8_t *in, uint32_t isz, int ord, uint32_t cap, uint32_t item) {
@@ -212,7 +225,10 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
             n_model++;
         }
         if ((ord & 1) && isz >= 8) {
-            J.route = 1;                     // the order-1 kernel (larger shared memory per warp)
+            // the order-1 kernel (larger shared memory per warp); transformed streams get the launch
+            // with room for the partitioned pair count
+            J.route = (ord & (X_PACK | X_RLE)) ? ROUTE_O1_WIDE : ROUTE_O1;
+            if (J.route == ROUTE_O1_WIDE) n_o1w++;
             n_o1++;
             // symbol table (16 B/pair), pair counts (4 B/pair), coded table scratch
             // + 16-bit pair keys of the partitioned pair count (large alphabets without a model)
@@ -227,9 +243,10 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
             StripePlan &sp = stripes[si++];
             sp.o_transposed = L.take(in_size[k], 256);
             place(jobs[j], d_in + in_off[k], in_size[k], order[k], cap, (uint32_t)k);
+            if (jobs[j].route == ROUTE_O1_WIDE) n_o1w--;
             if (jobs[j].route) { n_o1--; pool_bytes -= 256 * 256 * 12 + 300 * 1024 + (jobs[j].model ? 0 : 2 * (size_t)in_size[k] + 2048); } else n_o0--;
             if (jobs[j].model) { jobs[j].model = nullptr; n_model--; }
-            jobs[j].route = 2;               // assembled by stripe_select, not coded
+            jobs[j].route = ROUTE_NONE;      // assembled by stripe_select, not coded
             jobs[j].stripe_n = sp.N;
             for (uint32_t s = 0; s < sp.nsub; s++) {
                 const StripeSub &ss = sp.sub[s];
@@ -279,14 +296,21 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
     if (n_model) { CK(launch_hist(d_jobs, (uint32_t)njobs, st)); C.launches++; }
     // ---- encode: order-0 streams on the lean kernel, the rest on the order-1 kernel
     if (C.prof) CK(cudaEventRecord(C.pe[0], st));
-    if (n_o0) { CK(launch_enc(d_jobs, (uint32_t)njobs, false, pool, st)); C.launches++; }
-    if (n_o1) { CK(launch_enc(d_jobs, (uint32_t)njobs, true, pool, st)); C.launches++; }
+    if (n_o0) { CK(launch_enc(d_jobs, (uint32_t)njobs, ROUTE_O0, pool, st)); C.launches++; }
+    if (n_o1 > n_o1w) { CK(launch_enc(d_jobs, (uint32_t)njobs, ROUTE_O1, pool, st)); C.launches++; }
+    if (n_o1w) { CK(launch_enc(d_jobs, (uint32_t)njobs, ROUTE_O1_WIDE, pool, st)); C.launches++; }
     if (C.prof) { CK(cudaEventRecord(C.pe[1], st)); C.pe_valid[0] = true; }
     CK(cudaEventRecord(S->ev, st)); S->busy = true;
     // ---- STRIPE: choose the smallest method per sub-stream and assemble the parent
     for (auto &sp : stripes) {
         CK(launch_stripe_select(d_jobs, sp.first_job, sp.N, sp.nmeth, st));
         C.launches++;
+    }
+    // ---- method trial: keep the first smallest candidate of each input
+    if (trial) {
+        CK(launch_trial_select(d_jobs, (uint32_t)njobs, trial->inputs, trial->d_first, trial->d_csize,
+                               trial->d_jobidx, trial->d_best, st));
+        C.launches += 2;
     }
     // ---- pack the finished streams of the caller's items (sub-streams carry no item)
     uint64_t *d_off = d_out_off ? d_out_off : (uint64_t *)(W + o_soff);
@@ -390,12 +414,19 @@ struct EncChunk {
     int k0 = 0, k1 = 0;
     Lane *L = nullptr;
     size_t o_in = 0, o_out = 0, o_off = 0, o_sz = 0, o_tot = 0, bound_total = 0;
+    size_t o_cs = 0, o_ji = 0, o_best = 0, o_first = 0;   // method trial: candidate sizes, job index scratch, winners, group offsets
     size_t base = 0;            // where this chunk's streams start in the caller's arena
 };
 
+// With mfirst != null this is the method trial: input k is encoded under
+// methods[mfirst[k] .. mfirst[k+1]), the first smallest stream is returned, best[k] is
+// its index in that list (-1: all failed) and csize[c] the size of candidate c (0: that
+// call failed).
 int compress_batch_impl(int n, const unsigned char *const *in, const unsigned int *in_size, const int *order,
                         const uint32_t *caps, unsigned char *out, size_t out_cap, size_t *out_off,
-                        unsigned int *out_size) {
+                        unsigned int *out_size, const uint32_t *mfirst = nullptr, const int *methods = nullptr,
+                        int *best = nullptr, unsigned int *csize = nullptr) {
+    const bool M = mfirst != nullptr;
     int err = 0;
     Ctx *C = get_ctx(&err);
     if (!C) return err;
@@ -406,7 +437,10 @@ int compress_batch_impl(int n, const unsigned char *const *in, const unsigned in
         EncChunk c;
         c.k0 = k;
         size_t acc = 0;
-        while (k < n && (k == c.k0 || ((acc + in_size[k] <= CHUNK_BYTES || k - c.k0 < CHUNK_MIN_STREAMS) && k - c.k0 < 16384)))
+        const size_t chunk_bytes = M ? CHUNK_BYTES / 2 : CHUNK_BYTES;      // a trial does several encodes per byte
+        auto streams = [&](int k1) { return M ? (int)(mfirst[k1] - mfirst[c.k0]) : k1 - c.k0; };
+        while (k < n && (k == c.k0 || ((acc + in_size[k] <= chunk_bytes || streams(k) < CHUNK_MIN_STREAMS) &&
+                                       streams(k) < 16384)))
             acc += in_size[k++];
         c.k1 = k;
         ch.push_back(c);
@@ -421,25 +455,57 @@ int compress_batch_impl(int n, const unsigned char *const *in, const unsigned in
         size_t in_total;
         place_spans(c.k0, c.k1, in, in_size, ioff.data(), &in_total);
         c.bound_total = 0;
-        for (int k = c.k0; k < c.k1; k++) c.bound_total += al(compress_bound(in_size[k], order[k]), 16) + 16;
+        for (int k = c.k0; k < c.k1; k++) {
+            size_t b = 0;
+            if (M) for (uint32_t c2 = mfirst[k]; c2 < mfirst[k + 1]; c2++)
+                b = std::max<size_t>(b, compress_bound(in_size[k], methods[c2]));
+            else b = compress_bound(in_size[k], order[k]);
+            c.bound_total += al(b, 16) + 16;
+        }
         Layout L;
         c.o_in = L.take(in_total); c.o_out = L.take(c.bound_total);
         c.o_off = L.take((size_t)m * 8); c.o_sz = L.take((size_t)m * 4); c.o_tot = L.take(8);
+        const size_t mm = M ? mfirst[c.k1] - mfirst[c.k0] : 0;      // candidate calls of this chunk
+        c.o_cs = L.take(mm * 4); c.o_ji = L.take(mm * 4); c.o_best = L.take((size_t)m * 4);
+        c.o_first = L.take((size_t)(m + 1) * 4);
         int r = Ln.io.ensure(L.off + 256);
         if (r) return r;
         uint8_t *D = Ln.io.p;
         std::vector<Span> sp(m);
         for (int k = c.k0; k < c.k1; k++) sp[k - c.k0] = Span{in[k], c.o_in + ioff[k], in_size[k]};
         if ((r = copy_spans(sp, D, true, Ln.st))) return r;
-        r = enc_core(*C, Ln, Ln.st, m, D + c.o_in, ioff.data() + c.k0, in_size + c.k0, order + c.k0,
-                     caps ? caps + c.k0 : nullptr, D + c.o_out, c.bound_total, (uint64_t *)(D + c.o_off),
-                     (uint32_t *)(D + c.o_sz), (uint64_t *)(D + c.o_tot));
+        if (M) {
+            // the input is staged once; its candidate calls share it
+            std::vector<uint64_t> xoff(mm);
+            std::vector<uint32_t> xsz(mm);
+            const uint32_t f0 = mfirst[c.k0];
+            Stage *SF;
+            if ((r = Ln.get_stage((size_t)(m + 1) * 4, &SF))) return r;
+            uint32_t *hf = (uint32_t *)SF->h.p;
+            for (int k = c.k0; k <= c.k1; k++) hf[k - c.k0] = mfirst[k] - f0;
+            for (int k = c.k0; k < c.k1; k++)
+                for (uint32_t c2 = mfirst[k]; c2 < mfirst[k + 1]; c2++) { xoff[c2 - f0] = ioff[k]; xsz[c2 - f0] = in_size[k]; }
+            CK(cudaMemcpyAsync(D + c.o_first, hf, (size_t)(m + 1) * 4, cudaMemcpyHostToDevice, Ln.st));
+            CK(cudaEventRecord(SF->ev, Ln.st)); SF->busy = true;
+            Trial T{(uint32_t)m, (const uint32_t *)(D + c.o_first), (uint32_t *)(D + c.o_cs),
+                    (uint32_t *)(D + c.o_ji), (int32_t *)(D + c.o_best)};
+            r = enc_core(*C, Ln, Ln.st, (int)mm, D + c.o_in, xoff.data(), xsz.data(), methods + f0, nullptr,
+                         D + c.o_out, c.bound_total, (uint64_t *)(D + c.o_off), (uint32_t *)(D + c.o_sz),
+                         (uint64_t *)(D + c.o_tot), &T);
+        } else
+            r = enc_core(*C, Ln, Ln.st, m, D + c.o_in, ioff.data() + c.k0, in_size + c.k0, order + c.k0,
+                         caps ? caps + c.k0 : nullptr, D + c.o_out, c.bound_total, (uint64_t *)(D + c.o_off),
+                         (uint32_t *)(D + c.o_sz), (uint64_t *)(D + c.o_tot));
         if (r) return r;
-        if ((r = Ln.hio.ensure((size_t)m * 12 + 32))) return r;
+        if ((r = Ln.hio.ensure((size_t)m * 16 + mm * 4 + 32))) return r;
         uint8_t *H = Ln.hio.p;
         CK(cudaMemcpyAsync(H, D + c.o_tot, 8, cudaMemcpyDeviceToHost, Ln.st));
         CK(cudaMemcpyAsync(H + 16, D + c.o_off, (size_t)m * 8, cudaMemcpyDeviceToHost, Ln.st));
         CK(cudaMemcpyAsync(H + 16 + (size_t)m * 8, D + c.o_sz, (size_t)m * 4, cudaMemcpyDeviceToHost, Ln.st));
+        if (M) {
+            CK(cudaMemcpyAsync(H + 16 + (size_t)m * 12, D + c.o_best, (size_t)m * 4, cudaMemcpyDeviceToHost, Ln.st));
+            CK(cudaMemcpyAsync(H + 16 + (size_t)m * 16, D + c.o_cs, mm * 4, cudaMemcpyDeviceToHost, Ln.st));
+        }
         return 0;
     };
     // sizes known: start the copy of exactly the bytes produced
@@ -457,6 +523,12 @@ int compress_batch_impl(int n, const unsigned char *const *in, const unsigned in
         for (int k = c.k0; k < c.k1; k++) {
             out_off[k] = out_base + (size_t)h_off[k - c.k0];
             out_size[k] = h_sz[k - c.k0];
+        }
+        if (M) {
+            const int32_t *h_best = (const int32_t *)(H + 16 + (size_t)m * 12);
+            const uint32_t *h_cs = (const uint32_t *)(H + 16 + (size_t)m * 16);
+            if (best) for (int k = c.k0; k < c.k1; k++) best[k] = h_best[k - c.k0];
+            if (csize) memcpy(csize + mfirst[c.k0], h_cs, (size_t)(mfirst[c.k1] - mfirst[c.k0]) * 4);
         }
         out_base += total;
         return 0;
@@ -738,6 +810,54 @@ API int b200rans_compress_batch(int n, const unsigned char *const *in, const uns
                                 unsigned int *out_size) {
     if (n < 0 || (n && (!in || !in_size || !order || !out || !out_off || !out_size))) return B200RANS_EINVAL;
     return compress_batch_impl(n, in, in_size, order, nullptr, out, out_cap, out_off, out_size);
+}
+
+API int b200rans_compress_trials(int n, const unsigned char *const *in, const unsigned int *in_size,
+                                 const unsigned int *method_first, const int *methods, unsigned char *out,
+                                 size_t out_cap, size_t *out_off, unsigned int *out_size, int *best,
+                                 unsigned int *csize) {
+    if (n < 0 || (n && (!in || !in_size || !method_first || !methods || !out || !out_off || !out_size)))
+        return B200RANS_EINVAL;
+    for (int k = 0; k < n; k++)
+        if (method_first[k + 1] <= method_first[k] || method_first[k + 1] - method_first[k] > 64) return B200RANS_EINVAL;
+    return compress_batch_impl(n, in, in_size, nullptr, nullptr, out, out_cap, out_off, out_size, method_first,
+                               methods, best, csize);
+}
+
+API int b200rans_compress_methods_batch(int n, const unsigned char *const *in, const unsigned int *in_size,
+                                        int n_methods, const int *methods, unsigned char *out, size_t out_cap,
+                                        size_t *out_off, unsigned int *out_size, int *best, unsigned int *csize) {
+    if (n < 0 || n_methods < 1 || n_methods > 64 || !methods) return B200RANS_EINVAL;
+    std::vector<uint32_t> first((size_t)n + 1);
+    std::vector<int> flat((size_t)n * n_methods);
+    for (int k = 0; k <= n; k++) first[k] = (uint32_t)k * (uint32_t)n_methods;
+    for (int k = 0; k < n; k++) memcpy(flat.data() + (size_t)k * n_methods, methods, sizeof(int) * n_methods);
+    return b200rans_compress_trials(n, in, in_size, first.data(), flat.data(), out, out_cap, out_off, out_size,
+                                    best, csize);
+}
+
+API unsigned char *b200rans_compress_methods(unsigned char *in, unsigned int in_size, int n_methods,
+                                             const int *methods, unsigned int *out_size, int *best,
+                                             unsigned int *csize) {
+    if (out_size) *out_size = 0;
+    if (!in || !out_size || n_methods < 1 || n_methods > 64 || !methods) return nullptr;
+    size_t cap = 0;
+    for (int j = 0; j < n_methods; j++) cap = std::max<size_t>(cap, compress_bound(in_size, methods[j]));
+    cap += 64;
+    unsigned char *out = (unsigned char *)malloc(cap);
+    if (!out) return nullptr;
+    const unsigned char *ins[1] = {in};
+    size_t off = 0;
+    unsigned int sz = 0;
+    int b = -1;
+    const uint32_t first[2] = {0, (uint32_t)n_methods};
+    int r = compress_batch_impl(1, ins, &in_size, nullptr, nullptr, out, cap, &off, &sz, first, methods, &b,
+                                csize);
+    if (best) *best = b;
+    if (r || !sz || b < 0) { free(out); return nullptr; }
+    if (off) memmove(out, out + off, sz);
+    *out_size = sz;
+    return out;
 }
 
 API int b200rans_uncompress_batch(int n, const unsigned char *const *in, const unsigned int *in_size,

@@ -35,11 +35,17 @@ struct EncJob {
     uint32_t item;          // index into the caller's arrays; 0xffffffff for STRIPE sub-streams
     uint32_t stripe_n;      // >0: STRIPE parent record; its tail is the chosen sub-streams,
                             //     whose job indices sit at (uint32_t*)(slot + STRIPE_LIST_OFF)
-    uint32_t route;         // 0: order-0 kernel, 1: order-1 kernel, 2: not coded (STRIPE parent)
+    uint32_t route;         // ROUTE_*: which launch codes this stream
     uint32_t pad_;
     uint32_t *model;        // counts precomputed by hist_kernel, or null (the coder counts itself):
                             //   [256] order-0 counts, [MODEL_HDR_WORDS..] order-1 pair counts in rank space
     uint64_t pad2_;
+};
+enum : uint32_t {
+    ROUTE_O0 = 0,           // order-0 kernel
+    ROUTE_O1 = 1,           // order-1 kernel
+    ROUTE_NONE = 2,         // not coded (STRIPE parent, assembled by stripe_select)
+    ROUTE_O1_WIDE = 3,      // order-1 kernel with more shared memory per stream (PACK / RLE in front)
 };
 constexpr uint32_t MODEL_HDR_WORDS = 260;   // 256 counts, nsym, 3 pad
 constexpr uint32_t STRIPE_LIST_OFF = 2048;   // header is < 7 + 5*255 bytes

@@ -178,11 +178,11 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
 
 template <bool O1>
 __global__ void __launch_bounds__((O1 ? ENC_WARPS_O1 : ENC_WARPS) * 32, O1 ? 11 : 1)   // O1: 22 warps per SM (<= 92 registers)
-enc_kernel(EncJob *jobs, uint32_t njobs, uint32_t warp_smem, Pool pool) {
+enc_kernel(EncJob *jobs, uint32_t njobs, uint32_t warp_smem, Pool pool, uint32_t route) {
     extern __shared__ __align__(16) uint8_t smem_all[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t j = blockIdx.x * (O1 ? ENC_WARPS_O1 : ENC_WARPS) + wid;
-    if (j >= njobs || jobs[j].route != (O1 ? 1u : 0u)) return;   // other kernel's stream, or a STRIPE parent
+    if (j >= njobs || jobs[j].route != route) return;   // another launch's stream, or a STRIPE parent
     enc_stream<O1>(jobs[j], smem_all + (size_t)wid * warp_smem, warp_smem, pool, lane);
 }
 
@@ -524,21 +524,24 @@ static cudaError_t ensure_rcp_table(cudaStream_t st) {
     return cudaSuccess;
 }
 
-cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStream_t st) {
+cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, uint32_t route, Pool pool, cudaStream_t st) {
     if (!n) return cudaSuccess;
+    const bool o1 = route != ROUTE_O0;
     if (o1) { cudaError_t e = ensure_rcp_table(st); if (e != cudaSuccess) return e; }
-    uint32_t ws = o1 ? ENC_SMEM_O1 : ENC_SMEM_O0;
+    uint32_t ws = route == ROUTE_O1_WIDE ? ENC_SMEM_O1_WIDE : o1 ? ENC_SMEM_O1 : ENC_SMEM_O0;
     if (o1) {                              // tuning knob: shared memory per order-1 stream
         static const char *e = getenv("B200RANS_ENC_O1_SMEM");
-        if (e && atoi(e) >= 8192 && atoi(e) <= 100000) ws = (uint32_t)atoi(e) & ~15u;
+        static const char *ew = getenv("B200RANS_ENC_O1_WIDE_SMEM");
+        const char *k = route == ROUTE_O1_WIDE ? ew : e;
+        if (k && atoi(k) >= 8192 && atoi(k) <= 100000) ws = (uint32_t)atoi(k) & ~15u;
     }
     size_t sm = (size_t)ws * (o1 ? ENC_WARPS_O1 : ENC_WARPS);
     if (o1) {
         cudaFuncSetAttribute(enc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        enc_kernel<true><<<cdiv(n, ENC_WARPS_O1), ENC_WARPS_O1 * 32, sm, st>>>(d_jobs, n, ws, pool);
+        enc_kernel<true><<<cdiv(n, ENC_WARPS_O1), ENC_WARPS_O1 * 32, sm, st>>>(d_jobs, n, ws, pool, route);
     } else {
         cudaFuncSetAttribute(enc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        enc_kernel<false><<<cdiv(n, ENC_WARPS), ENC_WARPS * 32, sm, st>>>(d_jobs, n, ws, pool);
+        enc_kernel<false><<<cdiv(n, ENC_WARPS), ENC_WARPS * 32, sm, st>>>(d_jobs, n, ws, pool, route);
     }
     return cudaGetLastError();
 }
@@ -558,6 +561,54 @@ cudaError_t launch_dec(DecJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStrea
         cudaFuncSetAttribute(dec_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         dec_kernel<false><<<cdiv(n, DEC_WARPS), DEC_WARPS * 32, sm, st>>>(d_jobs, n, ws, pool);
     }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------
+// Method trial (fqzcomp5.c:1979-2119, the rANS members of compress_with_methods):
+// the caller's items come in groups of candidate encodings of the same input, items
+// first[k] .. first[k+1]-1 belonging to input k.  trial_sizes records every candidate's size,
+// trial_pick keeps the first smallest of each group (fqzcomp5.c:2097 `best_sz >
+// out_len`, methods tried in list order) and renumbers it to item = input so that
+// the packing kernels deliver exactly one stream per input.
+// ------------------------------------------------------------------------
+__global__ void trial_sizes_kernel(const EncJob *jobs, uint32_t njobs, uint32_t *csize, uint32_t *jobidx) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= njobs) return;
+    const EncJob &J = jobs[j];
+    if (J.item == 0xffffffffu) return;
+    csize[J.item] = J.status == ST_OK ? J.head_len + J.tail_len : 0u;
+    jobidx[J.item] = j;
+}
+
+__global__ void trial_pick_kernel(EncJob *jobs, uint32_t ninputs, const uint32_t *first, const uint32_t *csize,
+                                  const uint32_t *jobidx, int32_t *best) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ninputs) return;
+    const uint32_t f0 = first[k], f1 = first[k + 1];
+    uint32_t best_sz = 0xffffffffu;
+    int32_t b = -1;
+    for (uint32_t c = f0; c < f1; c++) {
+        uint32_t sz = csize[c];
+        if (sz && best_sz > sz) { best_sz = sz; b = (int32_t)(c - f0); }
+    }
+    best[k] = b;
+    for (uint32_t c = f0; c < f1; c++) {
+        EncJob &J = jobs[jobidx[c]];
+        if ((int32_t)(c - f0) == b) J.item = k;
+        else J.item = 0xffffffffu;
+    }
+    if (b < 0 && f1 > f0) {  // every candidate failed: report a failed stream for this input
+        EncJob &J = jobs[jobidx[f0]];
+        J.item = k; J.status = ST_FAIL;
+    }
+}
+
+cudaError_t launch_trial_select(EncJob *d_jobs, uint32_t njobs, uint32_t ninputs, const uint32_t *d_first,
+                                uint32_t *d_csize, uint32_t *d_jobidx, int32_t *d_best, cudaStream_t st) {
+    if (!njobs || !ninputs) return cudaSuccess;
+    trial_sizes_kernel<<<cdiv(njobs, 256), 256, 0, st>>>(d_jobs, njobs, d_csize, d_jobidx);
+    trial_pick_kernel<<<cdiv(ninputs, 128), 128, 0, st>>>(d_jobs, ninputs, d_first, d_csize, d_jobidx, d_best);
     return cudaGetLastError();
 }
 

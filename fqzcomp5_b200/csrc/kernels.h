@@ -13,12 +13,18 @@ constexpr int DEC_WARPS_O1 = 2;
 // shared memory per warp (bytes)
 constexpr uint32_t ENC_SMEM_O0 = 6144;     // EncO0Smem: ring + 256 encoder symbols + histogram
 constexpr uint32_t ENC_SMEM_O1 = 9856;     // EncO1Smem header + 4-byte encoder symbols for <= 41 symbols (22 warps per SM)
+// order-1 streams that are PACKed / RLEd first (their alphabet is usually all 256 byte values):
+// room for the 8 x 256 counters of the partitioned pair count behind the EncO1Smem header
+constexpr uint32_t ENC_SMEM_O1_WIDE = 11520;
 constexpr uint32_t DEC_SMEM_O0 = 8192;     // DecO0Smem, 8 KiB aligned
 constexpr uint32_t DEC_SMEM_O1 = 8192;     // DecO1Smem header + 16-bit cumulative rows + 64-bucket index for <= 41 symbols (26 warps per SM: measured 1.35x over 15 KiB / 256 buckets)
 
 cudaError_t launch_hist(EncJob *d_jobs, uint32_t n, cudaStream_t st);
-cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStream_t st);
+cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, uint32_t route, Pool pool, cudaStream_t st);
 cudaError_t launch_dec(DecJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStream_t st);
+// method trial: items first[k]..first[k+1]-1 are the candidates of input k -> sizes of all, first smallest kept
+cudaError_t launch_trial_select(EncJob *d_jobs, uint32_t njobs, uint32_t ninputs, const uint32_t *d_first,
+                                uint32_t *d_csize, uint32_t *d_jobidx, int32_t *d_best, cudaStream_t st);
 cudaError_t launch_pack(const EncJob *d_jobs, uint32_t n, uint64_t *d_off, uint32_t *d_size,
                         uint64_t *d_total, uint8_t *d_out, uint64_t out_cap, cudaStream_t st);
 

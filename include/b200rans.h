@@ -103,6 +103,48 @@ int b200rans_compress_batch(int n,
                             unsigned char *out, size_t out_cap,
                             size_t *out_off, unsigned int *out_size);
 
+/* Batched method trial: the rANS members of fqzcomp5's compress_with_methods
+ * (fqzcomp5.c:1979-2119: RANS0..RANS193 = orders {0,1,64,65,128,129,192,193} at
+ * :2005-2011, RANSXN1 = (fixed_len<<8)+9 at :2013-2022) and of the learner that
+ * consumes their sizes (metrics_update, fqzcomp5.c:1950-1958).  Every input is
+ * staged once and encoded under each of methods[0..n_methods) -- `order` values
+ * as rans_compress_to_4x16 takes them -- in one launch; only the winner leaves
+ * the device.
+ *   best[k]                index into methods[] of the first smallest stream, as
+ *                          the reference's `if (best_sz > out_len)` walk in list
+ *                          order keeps it (fqzcomp5.c:2097-2106); -1 if every
+ *                          method failed (then out_size[k] == 0)
+ *   csize[k*n_methods+j]   size under method j (what metrics_update receives);
+ *                          0 = that call failed.  May be NULL.
+ *   out, out_off, out_size the winning stream of input k, byte-identical to
+ *                          rans_compress_4x16(in[k], in_size[k], ., methods[best[k]])
+ * A failed method is never selected (the reference would keep a NULL buffer of
+ * size 0 in that case; no caller relies on it). */
+int b200rans_compress_methods_batch(int n,
+                                    const unsigned char *const *in, const unsigned int *in_size,
+                                    int n_methods, const int *methods,
+                                    unsigned char *out, size_t out_cap,
+                                    size_t *out_off, unsigned int *out_size,
+                                    int *best, unsigned int *csize);
+
+/* The same with a private method list per input -- the shape of tok3's compress()
+ * (tokenise_name3.c:1268-1417), which brute-forces each token stream over the
+ * 1-6 `order` values its type and level select: input k is tried under
+ * methods[method_first[k] .. method_first[k+1]) (1-64 entries each); best[k]
+ * indexes that sub-list and csize[] is laid out like methods[]. */
+int b200rans_compress_trials(int n,
+                             const unsigned char *const *in, const unsigned int *in_size,
+                             const unsigned int *method_first, const int *methods,
+                             unsigned char *out, size_t out_cap,
+                             size_t *out_off, unsigned int *out_size,
+                             int *best, unsigned int *csize);
+
+/* One input, malloc()ed winner (caller free()s), NULL on failure: the shape of
+ * the rANS arm of compress_with_methods for a single section buffer. */
+unsigned char *b200rans_compress_methods(unsigned char *in, unsigned int in_size,
+                                         int n_methods, const int *methods,
+                                         unsigned int *out_size, int *best, unsigned int *csize);
+
 /* Host buffers in, caller-placed outputs.
  *   out[k]        destination of stream k (must not be NULL)
  *   out_size[k]   in: capacity (exact length for NOSZ streams); out: bytes

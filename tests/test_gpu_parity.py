@@ -262,3 +262,104 @@ def test_randomised_differential(gpu_codec, checker):
     out = subprocess.run([sys.executable, os.path.join(root, "scripts", "gpu_fuzz.py"), "400", "99"],
                          capture_output=True, text=True, timeout=600).stdout
     assert "cases 400 mismatches 0" in out, out[-2000:]
+
+
+# ---------------------------------------------------------------- method trial
+def _cpu_trial(checker, data, methods):
+    """compress_with_methods restated on the CPU checker (fqzcomp5.c:1989-2106, rANS members):
+    try the methods in list order, keep the first strictly smaller stream."""
+    best, best_out, sizes = -1, None, []
+    for j, order in enumerate(methods):
+        out = checker.compress_malloc(data, order)
+        sizes.append(len(out) if out else 0)
+        if out and (best_out is None or len(best_out) > len(out)):
+            best, best_out = j, out
+    return best, best_out, sizes
+
+
+def test_method_trial_batch(gpu_codec, checker):
+    """fqzcomp5 -3 / -5 method sets for the seq and qual sections, many inputs per call."""
+    qual_methods = [0, 1, 129, 193, gpu_codec.ransxn1_order(150)]         # fqzcomp5.c:4893-4900 + RANSXN1
+    seq_methods = [0, 1, 64, 65, 128, 129, 192, 193]                      # fqzcomp5.c:2005
+    cases = [
+        (qual_methods, [("illumina_qual", 150 * 400, 1), ("binned_qual", 150 * 700, 2), ("ont_qual", 90000, 3),
+                        ("const", 30000, 1), ("runs", 60000, 4), ("illumina_qual", 150 * 7, 5),
+                        ("illumina_qual", 0, 1), ("random", 40000, 6), ("nsym4", 19, 1)]),
+        (seq_methods, [("illumina_seq", 200000, 1), ("nsym4", 50000, 2), ("nsym16", 50000, 3),
+                       ("nsym17", 50000, 4), ("text", 70000, 5), ("wide", 120000, 6), ("random", 1000, 7)]),
+    ]
+    for methods, items in cases:
+        parts = [np.frombuffer(corpus.make(g, n, s), np.uint8) for g, n, s in items]
+        sizes = [p.size for p in parts]
+        offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64)
+        buf = np.concatenate(parts)
+        out, ooff, osz, best, csize = gpu_codec.compress_methods_batch(buf, offs, sizes, methods)
+        for k, (g, n, s) in enumerate(items):
+            wb, wout, wsizes = _cpu_trial(checker, parts[k].tobytes(), methods)
+            assert list(csize[k]) == wsizes, (g, n, list(csize[k]), wsizes)
+            assert best[k] == wb, (g, n, best[k], wb)
+            got = out[int(ooff[k]):int(ooff[k]) + int(osz[k])].tobytes()
+            assert got == wout, (g, n)
+            assert gpu_codec.rans_uncompress_4x16(got) == parts[k].tobytes()
+
+
+def test_method_trial_single(gpu_codec, checker):
+    data = corpus.make("illumina_qual", 150 * 2000, 9)
+    for methods in ([0, 1, 129, 193], [1], [193, 129, 1, 0], [gpu_codec.ransxn1_order(150), 1]):
+        wb, wout, wsizes = _cpu_trial(checker, data, methods)
+        got, best, csize = gpu_codec.compress_methods(data, methods)
+        assert (got, best, list(csize)) == (wout, wb, wsizes), methods
+
+
+def test_method_trial_many_inputs(gpu_codec, checker):
+    """More inputs than one pipeline chunk holds; winners differ between inputs."""
+    gens = ["illumina_qual", "binned_qual", "runs", "random", "ont_qual", "const"]
+    methods = [4, 5, 0x84, 0x45, 0xc5]
+    parts = [np.frombuffer(corpus.make(gens[i % len(gens)], 20000 + 997 * (i % 13), i), np.uint8) for i in range(700)]
+    sizes = [p.size for p in parts]
+    offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64)
+    buf = np.concatenate(parts)
+    out, ooff, osz, best, csize = gpu_codec.compress_methods_batch(buf, offs, sizes, methods)
+    assert len(set(best.tolist())) > 1
+    for k in range(0, 700, 7):
+        wb, wout, wsizes = _cpu_trial(checker, parts[k].tobytes(), methods)
+        assert best[k] == wb and list(csize[k]) == wsizes
+        assert out[int(ooff[k]):int(ooff[k]) + int(osz[k])].tobytes() == wout
+
+
+def test_tok3_stream_trials(gpu_codec, checker):
+    """tok3's compress() (tokenise_name3.c:1268-1417) as one ragged trial: every token stream of a
+    block brute-forced over the method list of its type and level; 4-lane streams, STRIPE N=4,
+    PACK and RLE candidates, first smallest kept."""
+    rng = np.random.default_rng(11)
+    # token-stream-like payloads: type bytes, small deltas, little-endian 32-bit digits, text
+    def payload(t, n):
+        if t in (0, 10, 11, 12):
+            return rng.choice(np.array([1, 7, 8, 9, 10], np.uint8), n, p=[.05, .6, .2, .1, .05])
+        if t in (3, 5, 6, 7):
+            v = (rng.integers(0, 50000, n // 4 + 1).astype("<u4") + np.arange(n // 4 + 1, dtype="<u4") * 3)
+            return v.view(np.uint8)[:n]
+        if t in (8, 9, 4):
+            return rng.choice(np.array([0, 1, 2, 3, 255], np.uint8), n, p=[.1, .7, .1, .05, .05])
+        return np.frombuffer(corpus.make("text", n, int(rng.integers(1, 99))), np.uint8)
+    for level in (1, 3, 5, 7, 9):
+        row = gpu_codec.TOK3_METHODS[gpu_codec.tok3_level_row(level)]
+        parts, lists = [], []
+        for t in range(13):
+            for n in (0, 3, 40, 1000, 4001, 24000):
+                if n == 0 and t:
+                    continue
+                lst = gpu_codec.tok3_method_list(row[t], n)
+                if not lst:
+                    continue
+                parts.append(np.ascontiguousarray(payload(t, n)))
+                lists.append(lst)
+        sizes = [p.size for p in parts]
+        offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64)
+        buf = np.concatenate(parts)
+        out, ooff, osz, best, cs = gpu_codec.compress_trials(buf, offs, sizes, lists)
+        for k in range(len(parts)):
+            wb, wout, wsizes = _cpu_trial(checker, parts[k].tobytes(), lists[k])
+            assert cs[k] == wsizes, (level, k, lists[k], cs[k], wsizes)
+            assert best[k] == wb
+            assert out[int(ooff[k]):int(ooff[k]) + int(osz[k])].tobytes() == wout
