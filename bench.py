@@ -143,6 +143,42 @@ def cpu_roundtrip(codec, buf, slices, order, threads):
     return te, td, sum(csz)
 
 
+def cpu_fastq(sample, nrec):
+    """Reference load_seqs / output_fastq (oracle/_ref/libref_fqz.so, else the oracle port) on one thread
+    over `sample` (uint8 array of FASTQ text): (split seconds, join seconds, kind).  Used by
+    scripts/fastq_timing.py; raw C calls, no Python copies inside the timed regions."""
+    import ctypes as C
+    from oracle.pyoracle import FastqChecker, fastq_available, _libc, FqInfo
+    if fastq_available("ref"):
+        chk = FastqChecker("ref")
+        last = C.c_int(0)
+        t0 = time.perf_counter()
+        fq = chk.lib.load_seqs(sample.ctypes.data, int(sample.size), C.byref(last))
+        t1 = time.perf_counter()
+        assert fq and fq.contents.num_records == nrec
+        qb = np.ctypeslib.as_array(C.cast(fq.contents.qual_buf, C.POINTER(C.c_ubyte)), (fq.contents.qual_len,))
+        fp = _libc.fopen(b"/dev/null", b"wb")
+        t2 = time.perf_counter()
+        qb += 33                                                   # fqzcomp5.c:2532-2533
+        chk.lib.output_fastq(fp, fq, 0)
+        t3 = time.perf_counter()
+        _libc.fclose(fp)
+        chk.lib.fastq_free(fq)
+        return t1 - t0, t3 - t2, "reference"
+    chk = FastqChecker("oracle")
+    nm, sq, ql = (np.empty(sample.size, np.uint8) for _ in range(3))
+    ln, fl = np.empty(sample.size // 4, np.uint32), np.empty(sample.size // 4, np.uint32)
+    oi = FqInfo()
+    t0 = time.perf_counter()
+    chk.lib.fqo_split(sample.ctypes.data, int(sample.size), nm.ctypes.data, sq.ctypes.data, ql.ctypes.data,
+                      ln.ctypes.data, fl.ctypes.data, C.byref(oi))
+    t1 = time.perf_counter()
+    out = np.empty(sample.size + 64, np.uint8)
+    chk.lib.fqo_join(nm.ctypes.data, sq.ctypes.data, ql.ctypes.data, ln.ctypes.data, oi.num_records, 0,
+                     out.ctypes.data)
+    return t1 - t0, time.perf_counter() - t1, "port"
+
+
 def kind_name(codec):
     return "reference" if codec.kind.startswith("ref") else "port"
 

@@ -32,6 +32,8 @@ EXPORTS = [
     "b200rans_uncompress_batch_multi", "b200rans_launch_count", "b200rans_version",
     "b200rans_set_profiling", "b200rans_last_kernel_ms",
     "b200rans_compress_methods_batch", "b200rans_compress_methods", "b200rans_compress_trials",
+    "b200fq_split", "b200fq_join", "b200fq_split_dev", "b200fq_join_dev",
+    "b200fq_split_scratch_bytes", "b200fq_join_scratch_bytes",
 ]
 
 _lib = None
@@ -84,6 +86,14 @@ def lib():
         L.b200rans_compress_trials.argtypes = [i32, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp]
         L.b200rans_compress_methods.argtypes = [vp, u32, i32, vp, pu32, pi32, vp]
         L.b200rans_compress_methods.restype = vp
+        L.b200fq_split.argtypes = [vp, u32, vp, u32, vp, vp, u32, vp, vp, u32, vp]
+        L.b200fq_join.argtypes = [vp, u32, vp, vp, u32, vp, u32, i32, vp, u32, vp]
+        L.b200fq_split_scratch_bytes.argtypes = [u32, u32]
+        L.b200fq_split_scratch_bytes.restype = sz
+        L.b200fq_join_scratch_bytes.argtypes = [u32, u32]
+        L.b200fq_join_scratch_bytes.restype = sz
+        L.b200fq_split_dev.argtypes = [vp, vp, u32, vp, u32, vp, vp, u32, vp, vp, vp, vp, u32, vp, sz, vp]
+        L.b200fq_join_dev.argtypes = [vp, vp, u32, vp, vp, vp, u32, i32, vp, u32, vp, sz, vp]
         L.b200rans_launch_count.restype = C.c_uint64
         L.b200rans_version.restype = C.c_char_p
         L.b200rans_set_profiling.argtypes = [i32]
@@ -399,3 +409,60 @@ def set_profiling(on):
 def last_kernel_ms(which):
     """which: 0 = encode coder kernel, 1 = decode coder kernel of the last batch call."""
     return float(lib().b200rans_last_kernel_ms(which))
+
+
+# ---------------------------------------------------------------- FASTQ split / join (SURVEY 8f-3)
+class FqInfo(C.Structure):
+    """b200fq_info (include/b200rans.h)."""
+    _fields_ = [("status", C.c_int32), ("num_records", C.c_uint32), ("name_len", C.c_uint32),
+                ("seq_len", C.c_uint32), ("qual_len", C.c_uint32), ("fixed_len", C.c_int32),
+                ("consumed", C.c_uint32), ("text_len", C.c_uint32)]
+
+
+def load_seqs(text, max_records=None):
+    """The reference's load_seqs (fqzcomp5.c:279-410) on the GPU: a block of FASTQ text ->
+    dict(num_records, name, seq, qual, len, flag, fixed_len, consumed), or None where the
+    reference returns NULL.  `text`: bytes or a uint8 numpy array (pinned for full PCIe rate)."""
+    L = lib()
+    t = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray)) else text
+    n = int(t.size)
+    mr = int(max_records) if max_records is not None else n // 24 + 64
+    while True:
+        name = np.empty(n + 16, np.uint8); seq = np.empty(n + 16, np.uint8); qual = np.empty(n + 16, np.uint8)
+        ln = np.empty(mr + 1, np.uint32); fl = np.empty(mr + 1, np.uint32)
+        info = FqInfo()
+        rc = L.b200fq_split(_addr(t) if n else None, n, _addr(name), n + 16, _addr(seq), _addr(qual), n + 16,
+                            _addr(ln), _addr(fl), mr, C.addressof(info))
+        _check(rc, "b200fq_split")
+        if info.status == 2 and max_records is None and mr < n // 4 + 64:
+            mr = n // 4 + 64            # more records than guessed: the smallest record is 6 bytes... retry
+            continue
+        break
+    if info.status:
+        if info.status == 2:
+            raise B200RansError("b200fq_split: max_records too small")
+        return None
+    R = info.num_records
+    return dict(num_records=R, name=name[:info.name_len].tobytes(), seq=seq[:info.seq_len].tobytes(),
+                qual=qual[:info.qual_len].tobytes(), len=ln[:R].tolist(), flag=fl[:R].tolist(),
+                fixed_len=info.fixed_len, consumed=info.consumed)
+
+
+def output_fastq(name, seq, qual, lens, plus_name=0):
+    """The reference's output_fastq (fqzcomp5.c:3440-3480) with the decoder's +33 on the
+    qualities (fqzcomp5.c:2532-2533), on the GPU.  Returns the FASTQ text as bytes."""
+    L = lib()
+    nb = np.frombuffer(bytes(name), np.uint8); sb = np.frombuffer(bytes(seq), np.uint8)
+    qb = np.frombuffer(bytes(qual), np.uint8)
+    ln = np.ascontiguousarray(lens, np.uint32)
+    R = int(ln.size)
+    cap = 2 * nb.size + 2 * sb.size + 6 * R + 64
+    out = np.empty(cap, np.uint8)
+    info = FqInfo()
+    rc = L.b200fq_join(_addr(nb) if nb.size else None, nb.size, _addr(sb) if sb.size else None,
+                       _addr(qb) if qb.size else None, sb.size, _addr(ln) if R else None, R, int(plus_name),
+                       _addr(out), cap, C.addressof(info))
+    _check(rc, "b200fq_join")
+    if info.status:
+        return None
+    return out[:info.text_len].tobytes()

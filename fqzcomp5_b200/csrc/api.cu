@@ -15,6 +15,7 @@
 #include "../../include/b200rans.h"
 #include "kernels.h"
 #include "stripe.h"
+#include "fastq.h"
 
 using namespace b200;
 
@@ -63,6 +64,9 @@ constexpr int NSTAGE = 4;
 constexpr int NPIPE = 4;                  // chunks in flight in the host-buffer API
 constexpr size_t CHUNK_BYTES = 48u << 20; // uncompressed bytes per pipeline chunk ...
 constexpr int CHUNK_MIN_STREAMS = 256;    // ... but at least this many streams: a chunk of few streams is latency bound
+constexpr int CHUNK_MIN_STREAMS_SLOW = 1536;  // PACK / RLE streams take several ms each whatever their number: a
+                                              // chunk should fill most of the GPU's stream slots
+constexpr int CHUNK_MAX_STREAMS = 16384;
 struct Stage { Arena h; cudaEvent_t ev = nullptr; bool busy = false; };
 
 // One pipeline lane: a stream plus the arenas a chunk of work needs.  Chunks of a
@@ -432,15 +436,21 @@ int compress_batch_impl(int n, const unsigned char *const *in, const unsigned in
     if (!C) return err;
     if (n <= 0) return 0;
     // ---- split into pipeline chunks of ~CHUNK_BYTES of input
+    bool slow = false;
+    {
+        const int *o = M ? methods : order;
+        const size_t no = M ? mfirst[n] : (size_t)n;
+        for (size_t i = 0; i < no && !slow; i++) slow = (o[i] & (X_PACK | X_RLE)) != 0;
+    }
+    const int min_streams = slow ? CHUNK_MIN_STREAMS_SLOW : CHUNK_MIN_STREAMS;
     std::vector<EncChunk> ch;
     for (int k = 0; k < n;) {
         EncChunk c;
         c.k0 = k;
         size_t acc = 0;
-        const size_t chunk_bytes = M ? CHUNK_BYTES / 2 : CHUNK_BYTES;      // a trial does several encodes per byte
         auto streams = [&](int k1) { return M ? (int)(mfirst[k1] - mfirst[c.k0]) : k1 - c.k0; };
-        while (k < n && (k == c.k0 || ((acc + in_size[k] <= chunk_bytes || streams(k) < CHUNK_MIN_STREAMS) &&
-                                       streams(k) < 16384)))
+        while (k < n && (k == c.k0 || ((acc + in_size[k] <= CHUNK_BYTES || streams(k) < min_streams) &&
+                                       streams(k) < CHUNK_MAX_STREAMS)))
             acc += in_size[k++];
         c.k1 = k;
         ch.push_back(c);
@@ -587,6 +597,7 @@ int uncompress_batch_impl(int n, const unsigned char *const *in, const unsigned 
     {
         DecChunk c;
         size_t acc = 0;
+        int dec_min_streams = CHUNK_MIN_STREAMS;
         for (int k = 0; k < n; k++) {
             DecItem &it = items[k];
             int flag = 0, hdr = 0;
@@ -615,7 +626,8 @@ int uncompress_batch_impl(int n, const unsigned char *const *in, const unsigned 
             }
             it.njobs = (uint32_t)jin.size() - it.first_job;
             acc += ocap[k];
-            if ((acc >= CHUNK_BYTES && k - c.k0 + 1 >= CHUNK_MIN_STREAMS) || k - c.k0 + 1 >= 16384 || k == n - 1) {
+            if (it.njobs && (jflag.back() & (X_PACK | X_RLE))) dec_min_streams = CHUNK_MIN_STREAMS_SLOW;
+            if ((acc >= CHUNK_BYTES && k - c.k0 + 1 >= dec_min_streams) || k - c.k0 + 1 >= CHUNK_MAX_STREAMS || k == n - 1) {
                 c.k1 = k + 1; c.j1 = (int)jin.size();
                 ch.push_back(c);
                 c = DecChunk(); c.k0 = k + 1; c.j0 = (int)jin.size();
@@ -908,6 +920,134 @@ API int b200rans_uncompress_batch_dev(void *stream, int n, const unsigned char *
     Lane &Ln = C->lane[0];
     cudaStream_t st = stream ? (cudaStream_t)stream : Ln.st;
     return dec_core(*C, Ln, st, n, d_in, in_off, in_size, flags, d_out, out_off, out_size, d_out_size, d_status);
+}
+
+// ---------------------------------------------------------------- FASTQ split / join
+static_assert(sizeof(b200fq_info) == sizeof(FqInfo), "b200fq_info mirrors FqInfo");
+
+API size_t b200fq_split_scratch_bytes(uint32_t n, uint32_t max_records) {
+    return fq_split_scratch_bytes(n, max_records);
+}
+API size_t b200fq_join_scratch_bytes(uint32_t name_len, uint32_t num_records) {
+    return fq_join_scratch_bytes(name_len, num_records);
+}
+
+API int b200fq_split_dev(void *stream, const unsigned char *d_text, uint32_t n, unsigned char *d_name,
+                         uint32_t name_cap, unsigned char *d_seq, unsigned char *d_qual, uint32_t seq_cap,
+                         uint32_t *d_len, uint32_t *d_flag, uint32_t *d_name_off, uint32_t *d_seq_off,
+                         uint32_t max_records, void *d_scratch, size_t scratch_bytes, b200fq_info *d_info) {
+    int err = 0;
+    Ctx *C = get_ctx(&err);
+    if (!C) return err;
+    if (!d_text || !d_name || !d_seq || !d_qual || !d_len || !d_flag || !d_name_off || !d_seq_off || !d_scratch ||
+        !d_info || n > 0x7fffffffu || ((uintptr_t)d_text & 15) || ((uintptr_t)d_scratch & 255) ||
+        scratch_bytes < fq_split_scratch_bytes(n, max_records))
+        return B200RANS_EINVAL;
+    int l = 0;
+    CK(fq_split_launch(d_text, n, d_name, d_seq, d_qual, name_cap, seq_cap, d_len, d_flag, d_name_off, d_seq_off,
+                       max_records, (uint8_t *)d_scratch, (FqInfo *)d_info,
+                       stream ? (cudaStream_t)stream : C->lane[0].st, &l));
+    C->launches += l;
+    return 0;
+}
+
+API int b200fq_join_dev(void *stream, const unsigned char *d_name, uint32_t name_len, const unsigned char *d_seq,
+                        const unsigned char *d_qual, const uint32_t *d_len, uint32_t num_records, int plus_name,
+                        unsigned char *d_text, uint32_t text_cap, void *d_scratch, size_t scratch_bytes,
+                        b200fq_info *d_info) {
+    int err = 0;
+    Ctx *C = get_ctx(&err);
+    if (!C) return err;
+    if (!d_name || !d_seq || !d_qual || !d_len || !d_text || !d_scratch || !d_info || ((uintptr_t)d_name & 15) ||
+        ((uintptr_t)d_scratch & 255) || scratch_bytes < fq_join_scratch_bytes(name_len, num_records))
+        return B200RANS_EINVAL;
+    int l = 0;
+    CK(fq_join_launch(d_name, name_len, d_seq, d_qual, d_len, num_records, plus_name, d_text, text_cap,
+                      (uint8_t *)d_scratch, (FqInfo *)d_info, stream ? (cudaStream_t)stream : C->lane[0].st, &l));
+    C->launches += l;
+    return 0;
+}
+
+API int b200fq_split(const unsigned char *text, uint32_t n, unsigned char *name, uint32_t name_cap,
+                     unsigned char *seq, unsigned char *qual, uint32_t seq_cap, uint32_t *len, uint32_t *flag,
+                     uint32_t max_records, b200fq_info *info) {
+    int err = 0;
+    Ctx *C = get_ctx(&err);
+    if (!C) return err;
+    if ((n && !text) || !name || !seq || !qual || !len || !flag || !info || n > 0x7fffffffu) return B200RANS_EINVAL;
+    Lane &Ln = C->lane[0];
+    cudaStream_t st = Ln.st;
+    const size_t mr = max_records;
+    Layout L;
+    size_t o_text = L.take((size_t)n + 64), o_name = L.take((size_t)name_cap + 64);
+    size_t o_seq = L.take((size_t)seq_cap + 64), o_qual = L.take((size_t)seq_cap + 64);
+    size_t o_len = L.take(mr * 4 + 4), o_flag = L.take(mr * 4 + 4), o_no = L.take(mr * 4 + 4), o_so = L.take(mr * 4 + 4);
+    size_t o_info = L.take(sizeof(FqInfo));
+    size_t sb = fq_split_scratch_bytes(n, max_records);
+    size_t o_scr = L.take(sb);
+    int r = Ln.io.ensure(L.off + 256);
+    if (r) return r;
+    if ((r = Ln.hio.ensure(256))) return r;
+    uint8_t *D = Ln.io.p;
+    if (n) CK(cudaMemcpyAsync(D + o_text, text, n, cudaMemcpyHostToDevice, st));
+    int l = 0;
+    CK(fq_split_launch(D + o_text, n, D + o_name, D + o_seq, D + o_qual, name_cap, seq_cap, (uint32_t *)(D + o_len),
+                       (uint32_t *)(D + o_flag), (uint32_t *)(D + o_no), (uint32_t *)(D + o_so), max_records,
+                       D + o_scr, (FqInfo *)(D + o_info), st, &l));
+    C->launches += l;
+    CK(cudaMemcpyAsync(Ln.hio.p, D + o_info, sizeof(FqInfo), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(info, Ln.hio.p, sizeof(FqInfo));
+    if (info->status) return 0;                 // the reference returns NULL; nothing to read back
+    const size_t R = info->num_records;
+    if (info->name_len) CK(cudaMemcpyAsync(name, D + o_name, info->name_len, cudaMemcpyDeviceToHost, st));
+    if (info->seq_len) CK(cudaMemcpyAsync(seq, D + o_seq, info->seq_len, cudaMemcpyDeviceToHost, st));
+    if (info->qual_len) CK(cudaMemcpyAsync(qual, D + o_qual, info->qual_len, cudaMemcpyDeviceToHost, st));
+    if (R) {
+        CK(cudaMemcpyAsync(len, D + o_len, R * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(flag, D + o_flag, R * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+API int b200fq_join(const unsigned char *name, uint32_t name_len, const unsigned char *seq,
+                    const unsigned char *qual, uint32_t seq_len, const uint32_t *len, uint32_t num_records,
+                    int plus_name, unsigned char *text, uint32_t text_cap, b200fq_info *info) {
+    int err = 0;
+    Ctx *C = get_ctx(&err);
+    if (!C) return err;
+    if (!text || !info || (name_len && !name) || (seq_len && (!seq || !qual)) || (num_records && !len))
+        return B200RANS_EINVAL;
+    Lane &Ln = C->lane[0];
+    cudaStream_t st = Ln.st;
+    Layout L;
+    size_t o_name = L.take((size_t)name_len + 64), o_seq = L.take((size_t)seq_len + 64);
+    size_t o_qual = L.take((size_t)seq_len + 64), o_len = L.take((size_t)num_records * 4 + 4);
+    size_t o_text = L.take((size_t)text_cap + 64), o_info = L.take(sizeof(FqInfo));
+    size_t sb = fq_join_scratch_bytes(name_len, num_records);
+    size_t o_scr = L.take(sb);
+    int r = Ln.io.ensure(L.off + 256);
+    if (r) return r;
+    if ((r = Ln.hio.ensure(256))) return r;
+    uint8_t *D = Ln.io.p;
+    if (name_len) CK(cudaMemcpyAsync(D + o_name, name, name_len, cudaMemcpyHostToDevice, st));
+    if (seq_len) {
+        CK(cudaMemcpyAsync(D + o_seq, seq, seq_len, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(D + o_qual, qual, seq_len, cudaMemcpyHostToDevice, st));
+    }
+    if (num_records) CK(cudaMemcpyAsync(D + o_len, len, (size_t)num_records * 4, cudaMemcpyHostToDevice, st));
+    int l = 0;
+    CK(fq_join_launch(D + o_name, name_len, D + o_seq, D + o_qual, (const uint32_t *)(D + o_len), num_records,
+                      plus_name, D + o_text, text_cap, D + o_scr, (FqInfo *)(D + o_info), st, &l));
+    C->launches += l;
+    CK(cudaMemcpyAsync(Ln.hio.p, D + o_info, sizeof(FqInfo), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(info, Ln.hio.p, sizeof(FqInfo));
+    if (info->status) return 0;
+    if (info->text_len) CK(cudaMemcpyAsync(text, D + o_text, info->text_len, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
 }
 
 API uint64_t b200rans_launch_count(void) { return tls_ctx ? tls_ctx->launches : 0; }

@@ -201,6 +201,65 @@ int b200rans_uncompress_batch_multi(int ngpu, int n,
                                     unsigned char *const *out, unsigned int *out_size,
                                     int *status);
 
+/* ------------------------------------------------------------------------
+ * Part 3: the step either side of the codec -- a block of 4-line
+ * FASTQ text split into the name / seq / qual buffers the codec is fed with,
+ * and joined back, on the device.
+ *
+ * b200fq_split* restates load_seqs (fqzcomp5.c:279-410): names without '@',
+ * NUL separated; bases and qualities concatenated without separators, the
+ * qualities shifted by -33 (:375); len[] and flag[] per record (FQZ_FREAD2 = 128
+ * when the name ends in "/2" or repeats the previous one, :319-327); fixed_len
+ * as fq->fixed_len (:344-348); `consumed` is *last_offset: the record the block
+ * ends in is not taken, and a last record whose qualities do not match its
+ * bases yet is held back when it ends on the block's final byte (:382-386).
+ * status 1 = the reference returns NULL (a record not starting with '@', a
+ * third line not starting with '+', base / quality lengths differing); blocks
+ * holding NUL bytes are also reported malformed (the reference would read a NUL
+ * as a line end).  status 2 = max_records or a buffer capacity was too small.
+ * n <= INT_MAX as in the reference (`int blk_size`).
+ *
+ * b200fq_join* is output_fastq (fqzcomp5.c:3440-3480) with the +33 of
+ * fqzcomp5.c:2532-2533 folded in: "@name\nseq\n+[name]\nqual\n" per record.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+    int32_t  status;        /* 0 ok, 1 malformed, 2 capacity */
+    uint32_t num_records;
+    uint32_t name_len, seq_len, qual_len;   /* bytes used in the three buffers */
+    int32_t  fixed_len;     /* -1 nothing seen, L > 0 every read L long, else 0 */
+    uint32_t consumed;      /* split: offset of the first byte not consumed */
+    uint32_t text_len;      /* join: bytes of text produced */
+} b200fq_info;
+
+/* Host buffers (pinned for full PCIe rate).  name_cap / seq_cap bytes are
+ * available in name / seq and qual; n bytes each are always enough.  len and
+ * flag hold max_records entries. */
+int b200fq_split(const unsigned char *text, uint32_t n,
+                 unsigned char *name, uint32_t name_cap,
+                 unsigned char *seq, unsigned char *qual, uint32_t seq_cap,
+                 uint32_t *len, uint32_t *flag, uint32_t max_records, b200fq_info *info);
+int b200fq_join(const unsigned char *name, uint32_t name_len,
+                const unsigned char *seq, const unsigned char *qual, uint32_t seq_len,
+                const uint32_t *len, uint32_t num_records, int plus_name,
+                unsigned char *text, uint32_t text_cap, b200fq_info *info);
+
+/* Device-resident forms, asynchronous on `stream` (NULL = the context's).  All
+ * pointers are device memory; d_text / d_name 16-byte aligned, d_scratch 256-byte
+ * aligned and *_scratch_bytes() large; d_name_off / d_seq_off receive the offset
+ * of every record in the name and seq/qual buffers (fq->name[], fq->seq[]). */
+size_t b200fq_split_scratch_bytes(uint32_t n, uint32_t max_records);
+int b200fq_split_dev(void *stream, const unsigned char *d_text, uint32_t n,
+                     unsigned char *d_name, uint32_t name_cap,
+                     unsigned char *d_seq, unsigned char *d_qual, uint32_t seq_cap,
+                     uint32_t *d_len, uint32_t *d_flag, uint32_t *d_name_off, uint32_t *d_seq_off,
+                     uint32_t max_records, void *d_scratch, size_t scratch_bytes, b200fq_info *d_info);
+size_t b200fq_join_scratch_bytes(uint32_t name_len, uint32_t num_records);
+int b200fq_join_dev(void *stream, const unsigned char *d_name, uint32_t name_len,
+                    const unsigned char *d_seq, const unsigned char *d_qual,
+                    const uint32_t *d_len, uint32_t num_records, int plus_name,
+                    unsigned char *d_text, uint32_t text_cap,
+                    void *d_scratch, size_t scratch_bytes, b200fq_info *d_info);
+
 /* Number of kernel launches issued by this thread's context so far. */
 uint64_t b200rans_launch_count(void);
 

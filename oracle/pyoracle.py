@@ -120,3 +120,122 @@ class Codec:
         sz = C.c_uint(ulen)
         r = self._dec(src_addr, n, dst_addr, C.byref(sz))
         return sz.value if r else -1
+
+
+# ---------------------------------------------------------------- FASTQ split / join checkers
+_FQ_LIBS = {
+    "oracle": os.path.join(HERE, "liboracle_fastq.so"),
+    "ref": os.path.join(HERE, "_ref", "libref_fqz.so"),
+}
+
+
+def fastq_available(kind):
+    return os.path.exists(_FQ_LIBS[kind])
+
+
+class FqInfo(C.Structure):
+    _fields_ = [("status", C.c_int32), ("num_records", C.c_uint32), ("name_len", C.c_uint32),
+                ("seq_len", C.c_uint32), ("qual_len", C.c_uint32), ("fixed_len", C.c_int32),
+                ("consumed", C.c_uint32), ("text_len", C.c_uint32)]
+
+
+class _RefFastq(C.Structure):          # `fastq`, fqzcomp5.c:235-249
+    _fields_ = [("num_records", C.c_int), ("name_buf", C.c_void_p), ("seq_buf", C.c_void_p),
+                ("qual_buf", C.c_void_p), ("name", C.POINTER(C.c_int)), ("seq", C.POINTER(C.c_int)),
+                ("qual", C.POINTER(C.c_int)), ("len", C.POINTER(C.c_uint)), ("flag", C.POINTER(C.c_uint)),
+                ("name_len", C.c_int), ("seq_len", C.c_int), ("qual_len", C.c_int),
+                ("name_sz", C.c_int), ("seq_sz", C.c_int), ("qual_sz", C.c_int),
+                ("fixed_len", C.c_int), ("is_fasta", C.c_int)]
+
+
+class FastqChecker:
+    """split(text) -> dict or None (the reference returns NULL); join(...) -> bytes.
+
+    kind "oracle": oracle/fastq_oracle.c.  kind "ref": the reference's own load_seqs /
+    output_fastq (fqzcomp5.c:279-410, :3440-3480) from oracle/_ref/libref_fqz.so; the
+    +33 the decoder applies before output_fastq (fqzcomp5.c:2532-2533) is applied here."""
+
+    def __init__(self, kind="oracle"):
+        path = _FQ_LIBS[kind]
+        if not os.path.exists(path) and (kind == "oracle" or os.path.isdir(REFERENCE_ROOT)):
+            build()
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.kind = kind
+        self.lib = L = C.CDLL(path)
+        if kind == "oracle":
+            L.fqo_split.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 5 + [C.POINTER(FqInfo)]
+            L.fqo_join.argtypes = [C.c_void_p] * 4 + [C.c_uint32, C.c_int, C.c_void_p]
+            L.fqo_join.restype = C.c_uint32
+        else:
+            L.load_seqs.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+            L.load_seqs.restype = C.POINTER(_RefFastq)
+            L.fastq_free.argtypes = [C.POINTER(_RefFastq)]
+            L.output_fastq.argtypes = [C.c_void_p, C.POINTER(_RefFastq), C.c_int]
+            _libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+            _libc.fopen.restype = C.c_void_p
+            _libc.fclose.argtypes = [C.c_void_p]
+
+    def split(self, text):
+        import numpy as np
+        text = bytes(text)
+        n = len(text)
+        src = C.create_string_buffer(text, max(n, 1))
+        if self.kind == "oracle":
+            name = np.zeros(n + 16, np.uint8); seq = np.zeros(n + 16, np.uint8); qual = np.zeros(n + 16, np.uint8)
+            ln = np.zeros(n // 4 + 16, np.uint32); fl = np.zeros(n // 4 + 16, np.uint32)
+            info = FqInfo()
+            self.lib.fqo_split(C.addressof(src), n, name.ctypes.data, seq.ctypes.data, qual.ctypes.data,
+                               ln.ctypes.data, fl.ctypes.data, C.byref(info))
+            if info.status:
+                return None
+            R = info.num_records
+            return dict(num_records=R, name=name[:info.name_len].tobytes(), seq=seq[:info.seq_len].tobytes(),
+                        qual=qual[:info.qual_len].tobytes(), len=ln[:R].tolist(), flag=fl[:R].tolist(),
+                        fixed_len=info.fixed_len, consumed=info.consumed)
+        last = C.c_int(0)
+        devnull = os.open(os.devnull, os.O_WRONLY)       # load_seqs reports errors on stderr
+        saved = os.dup(2)
+        os.dup2(devnull, 2)
+        try:
+            fq = self.lib.load_seqs(C.addressof(src), n, C.byref(last))
+        finally:
+            os.dup2(saved, 2); os.close(saved); os.close(devnull)
+        if not fq:
+            return None
+        f = fq.contents
+        R = f.num_records
+        out = dict(num_records=R, name=C.string_at(f.name_buf, f.name_len), seq=C.string_at(f.seq_buf, f.seq_len),
+                   qual=C.string_at(f.qual_buf, f.qual_len), len=[f.len[i] for i in range(R)],
+                   flag=[f.flag[i] for i in range(R)], fixed_len=f.fixed_len, consumed=last.value)
+        self.lib.fastq_free(fq)
+        return out
+
+    def join(self, name, seq, qual, lens, plus_name=0):
+        import numpy as np
+        import tempfile
+        R = len(lens)
+        ln = np.ascontiguousarray(lens, np.uint32)
+        nb = C.create_string_buffer(bytes(name), max(len(name), 1))
+        sb = C.create_string_buffer(bytes(seq), max(len(seq), 1))
+        if self.kind == "oracle":
+            qb = C.create_string_buffer(bytes(qual), max(len(qual), 1))
+            out = np.zeros(2 * len(name) + 2 * len(seq) + 6 * R + 16, np.uint8)
+            k = self.lib.fqo_join(C.addressof(nb), C.addressof(sb), C.addressof(qb), ln.ctypes.data, R, plus_name,
+                                  out.ctypes.data)
+            return out[:k].tobytes()
+        q33 = bytes((b + 33) & 0xff for b in bytes(qual))           # fqzcomp5.c:2532-2533
+        qb = C.create_string_buffer(q33, max(len(q33), 1))
+        fq = _RefFastq()
+        fq.num_records = R
+        fq.name_buf, fq.seq_buf, fq.qual_buf = C.addressof(nb), C.addressof(sb), C.addressof(qb)
+        fq.len = ln.ctypes.data_as(C.POINTER(C.c_uint))
+        fq.name_len, fq.seq_len, fq.qual_len = len(name), len(seq), len(qual)
+        with tempfile.NamedTemporaryFile(delete=False) as t:
+            path = t.name
+        fp = _libc.fopen(path.encode(), b"wb")
+        self.lib.output_fastq(fp, C.byref(fq), plus_name)
+        _libc.fclose(fp)
+        data = open(path, "rb").read()
+        os.unlink(path)
+        return data

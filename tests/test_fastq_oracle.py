@@ -1,0 +1,64 @@
+"""The FASTQ split / join oracle (oracle/fastq_oracle.c) against the unmodified reference's
+load_seqs() / output_fastq() and against the committed vectors generated from them."""
+import hashlib
+import json
+import os
+import sys
+
+import pytest
+
+import corpus_fastq
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+from make_golden_fastq import describe  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def fq_oracle():
+    from oracle.pyoracle import FastqChecker
+    return FastqChecker("oracle")
+
+
+@pytest.fixture(scope="module")
+def fq_ref():
+    from oracle.pyoracle import FastqChecker, fastq_available, REFERENCE_ROOT
+    if not fastq_available("ref") and not os.path.isdir(REFERENCE_ROOT):
+        pytest.skip("oracle/_ref/libref_fqz.so not built and /root/reference absent")
+    return FastqChecker("ref")
+
+
+@pytest.fixture(scope="module")
+def fq_golden():
+    with open(os.path.join(ROOT, "tests", "golden", "fastq_vectors.json")) as f:
+        return {v["label"]: v for v in json.load(f)["vectors"]}
+
+
+def test_oracle_matches_golden_vectors(fq_oracle, fq_golden):
+    cases = corpus_fastq.edge_cases()
+    assert len(cases) == len(fq_golden)
+    for label, text in cases:
+        r = fq_oracle.split(text)
+        v = describe(label, text, r)
+        if r is not None:
+            v["join0_sha256"] = hashlib.sha256(fq_oracle.join(r["name"], r["seq"], r["qual"], r["len"], 0)).hexdigest()
+            v["join1_sha256"] = hashlib.sha256(fq_oracle.join(r["name"], r["seq"], r["qual"], r["len"], 1)).hexdigest()
+        assert v == fq_golden[label], label
+
+
+def test_oracle_matches_reference(fq_oracle, fq_ref):
+    for label, text in corpus_fastq.edge_cases() + [("big", corpus_fastq.illumina(3000, 150, seed=9, paired=True)),
+                                                     ("ont", corpus_fastq.long_reads(40, seed=10))]:
+        a, b = fq_oracle.split(text), fq_ref.split(text)
+        assert a == b, label
+        if a is not None:
+            for p in (0, 1):
+                assert fq_oracle.join(a["name"], a["seq"], a["qual"], a["len"], p) == \
+                    fq_ref.join(a["name"], a["seq"], a["qual"], a["len"], p), label
+
+
+def test_join_inverts_split(fq_oracle):
+    text = corpus_fastq.illumina(500, 100, seed=12)
+    r = fq_oracle.split(text)
+    assert r["consumed"] == len(text) and r["fixed_len"] == 100
+    assert fq_oracle.join(r["name"], r["seq"], r["qual"], r["len"], 0) == text
