@@ -2,13 +2,14 @@
 //
 // Split restates load_seqs (fqzcomp5.c:279-410) as data-parallel passes over a block of
 // 4-line FASTQ text already in HBM:
-//   1. count_kernel      newlines per 8 KiB tile                        (reads the text)
+//   1. count_kernel      newlines per 16 KiB tile                        (reads the text)
 //   2. scan_small        exclusive scan of the tile counts
 //   3. mark_kernel       position of every newline, in order            (reads the text)
 //   4. records_kernel    one thread per record: field lengths, '@' / '+' / length checks,
 //                        the trailing partial record's rules, fixed_len
 //   5. scan (3 kernels)  offsets of every record in the name and seq/qual buffers
-//   6. scatter_kernel    one warp per record: name + NUL, seq, qual - 33, READ2 flag
+//   6. scatter_kernel    one CTA per 32 records, their text staged in shared memory: name + NUL,
+//                        seq, qual - 33, READ2 flag, '@' / '+' checks
 //                                                                       (reads the text, writes the buffers)
 //   7. finalize_kernel   the block's totals
 // Join is output_fastq (fqzcomp5.c:3440-3480) the other way round, with the +33 of
@@ -22,8 +23,10 @@
 namespace b200 {
 namespace {
 
-constexpr uint32_t TILE = 8192;          // bytes per CTA in the byte-search passes
-constexpr uint32_t TPB = 256;            // 32 bytes per thread
+constexpr uint32_t TILE = 16384;         // bytes per CTA in the byte-search passes
+constexpr uint32_t TPB = 512;            // 32 bytes per thread
+constexpr uint32_t GREC = 32;            // records per CTA in the copy kernels
+constexpr uint32_t SPAN_CAP = 24576;     // bytes of a group's text staged in shared memory
 constexpr uint32_t STILE = 2048;         // elements per CTA in the offset scan (8 per thread)
 constexpr uint32_t FREAD2 = 128;         // FQZ_FREAD2, htscodecs/fqzcomp_qual.h:45
 
@@ -156,26 +159,24 @@ records_kernel(const uint8_t *__restrict__ text, uint32_t n, const uint32_t *__r
     uint32_t R = total >> 2;
     if (R > max_records) { capped = true; R = max_records; }
     if (capped && r == 0) atomicOr(&W->err, 2u);
-    auto note_len = [&](uint32_t l) {            // fqzcomp5.c:344-348
-        atomicMax(&W->not_minlen, ~l);
-        atomicMax(&W->maxlen, l);
-        W->have_len = 1;
-    };
+    // length statistics for fixed_len (fqzcomp5.c:344-348), reduced per warp before the atomics
+    uint32_t not_mn = 0, mx = 0, have = 0, e = 0;
+    auto note_len = [&](uint32_t l) { not_mn = max(not_mn, ~l); mx = max(mx, l); have = 1; };
     if (r < R) {
         const uint32_t a = r ? nl[4 * r - 1] + 1 : 0;
         const uint32_t n0 = nl[4 * r], n1 = nl[4 * r + 1], n2 = nl[4 * r + 2], n3 = nl[4 * r + 3];
         const uint32_t sl = n1 - n0 - 1, ql = n3 - n2 - 1;
         nlen1[r] = n0 - a;                       // name without '@', plus its NUL
         len[r] = sl;
-        uint32_t e = 0;
-        if (text[a] != '@') e = 1;               // :302-304
-        if (text[n1 + 1] != '+') e = 1;          // :351-352
         note_len(sl);
         if (sl != ql) {                          // :382-386
-            if (r == R - 1 && n3 == n - 1) W->drop_last = 1;
-            else e = 1;
+            if (r == R - 1 && n3 == n - 1) {
+                // held back, not an error; scatter_kernel will not see it, so its '@' and '+'
+                // (:302-304, :351-352) are judged here
+                W->drop_last = 1;
+                if (text[a] != '@' || text[n1 + 1] != '+') e = 1;
+            } else e = 1;
         }
-        if (e) atomicOr(&W->err, 1u);
     } else if (r == R && !capped) {
         // the record the block ends in (no fourth newline): the checks load_seqs makes
         // before it notices the end of the block.  (A held-back last record ends on the
@@ -183,7 +184,6 @@ records_kernel(const uint8_t *__restrict__ text, uint32_t n, const uint32_t *__r
         const uint32_t start = R ? nl[4 * R - 1] + 1 : 0;
         const uint32_t k = total - 4 * R;        // complete lines of the partial record
         if (start < n) {
-            uint32_t e = 0;
             if (text[start] != '@') e = 1;       // :302-304
             // the sequence line counts once its newline is inside the block and not its last
             // byte (:339-340 breaks first otherwise): length noted (:344-348), '+' checked (:351)
@@ -191,8 +191,22 @@ records_kernel(const uint8_t *__restrict__ text, uint32_t n, const uint32_t *__r
                 note_len(nl[4 * R + 1] - nl[4 * R] - 1);
                 if (text[nl[4 * R + 1] + 1] != '+') e = 1;
             }
-            if (e) atomicOr(&W->err, 1u);
         }
+    }
+    not_mn = __reduce_max_sync(FULL, not_mn);
+    mx = __reduce_max_sync(FULL, mx);
+    have = __reduce_max_sync(FULL, have);
+    e = __reduce_max_sync(FULL, e);
+    if ((threadIdx.x & 31) == 0) {
+        // the statistics only grow: look before touching them (same-address atomics serialise in L2,
+        // and with fixed-length reads every warp would send the same two values)
+        volatile FqWork *V = W;
+        if (have) {
+            if (not_mn > V->not_minlen) atomicMax(&W->not_minlen, not_mn);
+            if (mx > V->maxlen) atomicMax(&W->maxlen, mx);
+            if (!V->have_len) W->have_len = 1;
+        }
+        if (e) atomicOr(&W->err, 1u);
     }
 }
 
@@ -258,7 +272,7 @@ scan_apply(const uint32_t *__restrict__ v0, const uint32_t *__restrict__ v1, con
 // ---------------------------------------------------------------- copies
 // warp-cooperative copy with a byte-wise add (0, -33 or +33 mod 256), any alignment:
 // 4-byte stores assembled from aligned 4-byte loads.  Reads stay inside the aligned
-// words that hold src[0 .. n).
+// words that hold src[0 .. n).  src may be global or shared memory.
 __device__ __forceinline__ void warp_copy_add(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, uint32_t n,
                                               uint32_t add4, int lane) {
     if (!n) return;
@@ -273,51 +287,106 @@ __device__ __forceinline__ void warp_copy_add(uint8_t *__restrict__ dst, const u
     uint32_t *dw = (uint32_t *)dst;
     if (sh == 0) {
 #pragma unroll 4
-        for (uint32_t i = lane; i < nw; i += 32) dw[i] = __vadd4(__ldg(sw + i), add4);
+        for (uint32_t i = lane; i < nw; i += 32) dw[i] = __vadd4(sw[i], add4);
     } else {
 #pragma unroll 4
         for (uint32_t i = lane; i < nw; i += 32)
-            dw[i] = __vadd4(__funnelshift_r(__ldg(sw + i), __ldg(sw + i + 1), sh), add4);
+            dw[i] = __vadd4(__funnelshift_r(sw[i], sw[i + 1], sh), add4);
     }
     for (uint32_t i = (nw << 2) + lane; i < n; i += 32) dst[i] = (uint8_t)(src[i] + add);
 }
 
+// The staged fast path: source bytes in shared memory (32-bit shared addresses), one byte per
+// lane and round.  Far fewer instructions than the word path for the 25-150 byte fields of short
+// reads; the 32 bytes a warp stores per round are contiguous and merge in L2.
+__device__ __forceinline__ uint32_t lds_b(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void smem_copy_add(uint8_t *__restrict__ dst, uint32_t saddr, uint32_t n, uint32_t add,
+                                              int lane) {
+    uint8_t *d = dst + lane;
+    saddr += lane;
+    for (uint32_t i = lane; i < n; i += 32, saddr += 32, d += 32) *d = (uint8_t)(lds_b(saddr) + add);
+}
+
+// cooperative copy of text[lo, hi) into shared memory at its position relative to `base`
+// (base <= lo, 16-byte aligned); 16-byte loads where the text allows
+__device__ __forceinline__ void stage_span(uint8_t *s, const uint8_t *__restrict__ g, uint32_t base, uint32_t hi,
+                                           uint32_t n) {
+    const uint32_t nv = (hi - base + 15) >> 4;
+    for (uint32_t i = threadIdx.x; i < nv; i += blockDim.x) {
+        const uint32_t p = base + 16 * i;
+        if (p + 16 <= n) ((uint4 *)s)[i] = __ldg((const uint4 *)(g + p));
+        else for (uint32_t q = p; q < n; q++) s[q - base] = g[q];
+    }
+}
+
+// One CTA per GREC consecutive records: their text is one contiguous span, staged in shared
+// memory with coalesced 16-byte loads when it fits (reads of 150-byte fields straight from
+// HBM are latency bound); each warp then writes whole records.  Groups whose span exceeds
+// SPAN_CAP (long reads) copy from global memory.
 __global__ void __launch_bounds__(256)
 scatter_kernel(const uint8_t *__restrict__ text, uint32_t n, const uint32_t *__restrict__ nl, uint32_t cap_nl,
                uint32_t max_records, const uint32_t *__restrict__ name_off, const uint32_t *__restrict__ seq_off,
                uint8_t *__restrict__ name, uint8_t *__restrict__ seq, uint8_t *__restrict__ qual, uint32_t name_cap,
                uint32_t seq_cap, uint32_t *__restrict__ flag, FqWork *W) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t total = min(W->total, cap_nl);
-    uint32_t R = min(total >> 2, max_records) - W->drop_last;
-    if (r >= R) return;
-    const uint32_t a = r ? nl[4 * r - 1] + 1 : 0;
-    const uint32_t n0 = nl[4 * r], n1 = nl[4 * r + 1], n2 = nl[4 * r + 2];
-    const uint32_t L = n0 - a - 1, sl = n1 - n0 - 1;
-    const uint32_t no = name_off[r], so = seq_off[r];
-    if ((uint64_t)no + L + 1 > name_cap || (uint64_t)so + sl > seq_cap) {
-        if (lane == 0) atomicOr(&W->err, 2u);
-        return;
-    }
-    warp_copy_add(name + no, text + a + 1, L, 0, lane);
-    if (lane == 0) name[no + L] = 0;
-    warp_copy_add(seq + so, text + n0 + 1, sl, 0, lane);
-    warp_copy_add(qual + so, text + n2 + 1, sl, 0xdfdfdfdfu, lane);          // - 33 (fqzcomp5.c:375)
-    // READ2: name ends in "/2" (the reference tests the running buffer offset, :320-323), or
-    // repeats the previous record's name (:324-326)
-    bool f = L >= 2 && no + L + 1 > 3 && text[n0 - 1] == '2' && text[n0 - 2] == '/';
-    if (!f && r) {
-        const uint32_t pa = r > 1 ? nl[4 * r - 5] + 1 : 0, pn0 = nl[4 * r - 4];
-        bool same = pn0 - pa - 1 == L;
-        if (same) {
-            bool eq = true;
-            for (uint32_t i = lane; i < L; i += 32) eq = eq && text[a + 1 + i] == text[pa + 1 + i];
-            same = __all_sync(FULL, eq);
+    __shared__ uint32_t s_nl[4 * GREC + 1];      // newline in front of the group, then the group's own
+    __shared__ uint32_t s_no[GREC], s_so[GREC];
+    __shared__ __align__(16) uint8_t s_text[SPAN_CAP + 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t total = min(W->total, cap_nl);
+    const uint32_t R = min(total >> 2, max_records) - W->drop_last;
+    const uint32_t r0 = blockIdx.x * GREC;
+    if (r0 >= R) return;
+    const uint32_t g = min(GREC, R - r0);
+    for (uint32_t i = threadIdx.x; i < 4 * g + 1; i += blockDim.x)
+        s_nl[i] = (r0 == 0 && i == 0) ? 0xffffffffu : nl[4 * r0 - 1 + i];
+    for (uint32_t i = threadIdx.x; i < g; i += blockDim.x) { s_no[i] = name_off[r0 + i]; s_so[i] = seq_off[r0 + i]; }
+    __syncthreads();
+    const uint32_t lo = s_nl[0] + 1, hi = s_nl[4 * g] + 1, base = lo & ~15u;
+    const bool staged = hi - base <= SPAN_CAP;
+    if (staged) stage_span(s_text, text, base, hi, n);
+    __syncthreads();
+    // position p of the text: shared address sa0 + p when staged
+    const uint32_t sa0 = (uint32_t)__cvta_generic_to_shared(s_text) - base;
+    auto byte_at = [&](uint32_t p) -> uint32_t { return staged ? lds_b(sa0 + p) : (uint32_t)text[p]; };
+    auto copy = [&](uint8_t *dst, uint32_t p, uint32_t len, uint32_t add4) {
+        if (staged) smem_copy_add(dst, sa0 + p, len, add4 & 0xff, lane);
+        else warp_copy_add(dst, text + p, len, add4, lane);
+    };
+    uint32_t err = 0;
+    for (uint32_t j = wid; j < g; j += blockDim.x >> 5) {
+        const uint32_t r = r0 + j;
+        const uint32_t a = s_nl[4 * j] + 1, n0 = s_nl[4 * j + 1], n1 = s_nl[4 * j + 2], n2 = s_nl[4 * j + 3];
+        const uint32_t L = n0 - a - 1, sl = n1 - n0 - 1;
+        const uint32_t no = s_no[j], so = s_so[j];
+        if (byte_at(a) != '@' || byte_at(n1 + 1) != '+') err |= 1u;           // fqzcomp5.c:302-304, :351-352
+        if ((uint64_t)no + L + 1 > name_cap || (uint64_t)so + sl > seq_cap) { err |= 2u; continue; }
+        copy(name + no, a + 1, L, 0);
+        if (lane == 0) name[no + L] = 0;
+        copy(seq + so, n0 + 1, sl, 0);
+        copy(qual + so, n2 + 1, sl, 0xdfdfdfdfu);                             // - 33 (fqzcomp5.c:375)
+        // READ2: name ends in "/2" (the reference tests the running buffer offset, :320-323), or
+        // repeats the previous record's name (:324-326)
+        bool f = L >= 2 && no + L + 1 > 3 && byte_at(n0 - 1) == '2' && byte_at(n0 - 2) == '/';
+        if (!f && r) {
+            uint32_t pa, pn0;
+            if (j) { pa = s_nl[4 * j - 4] + 1; pn0 = s_nl[4 * j - 3]; }
+            else { pa = r > 1 ? nl[4 * r - 5] + 1 : 0; pn0 = nl[4 * r - 4]; }      // previous group's last
+            bool same = pn0 - pa - 1 == L;
+            if (same) {
+                bool eq = true;
+                if (j && staged) for (uint32_t i = lane; i < L; i += 32) eq = eq && lds_b(sa0 + a + 1 + i) == lds_b(sa0 + pa + 1 + i);
+                else for (uint32_t i = lane; i < L; i += 32) eq = eq && text[a + 1 + i] == text[pa + 1 + i];
+                same = __all_sync(FULL, eq);
+            }
+            f = same;
         }
-        f = same;
+        if (lane == 0) flag[r] = f ? FREAD2 : 0u;
     }
-    if (lane == 0) flag[r] = f ? FREAD2 : 0u;
+    if (err && lane == 0) atomicOr(&W->err, err);
 }
 
 __global__ void split_finalize(const uint32_t *nl, uint32_t cap_nl, uint32_t max_records, const uint32_t *name_off,
@@ -336,33 +405,63 @@ __global__ void split_finalize(const uint32_t *nl, uint32_t cap_nl, uint32_t max
 }
 
 // ---------------------------------------------------------------- join
+// One CTA per GREC consecutive records: their names, bases and qualities are three contiguous
+// spans, staged in shared memory when they fit; each warp writes whole records of text.
+constexpr uint32_t JN_CAP = 4096, JS_CAP = 10240;
 __global__ void __launch_bounds__(256)
-gather_kernel_fq(const uint8_t *__restrict__ name, const uint32_t *__restrict__ nul, const uint8_t *__restrict__ seq,
-                 const uint8_t *__restrict__ qual, const uint32_t *__restrict__ len,
+gather_kernel_fq(const uint8_t *__restrict__ name, uint32_t name_len, const uint32_t *__restrict__ nul,
+                 const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual, const uint32_t *__restrict__ len,
                  const uint32_t *__restrict__ seq_off, uint32_t R, int plus_name, uint8_t *__restrict__ text,
                  uint32_t text_cap, FqWork *W, FqInfo *info) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= R || W->total != R) return;
-    const uint32_t no = r ? nul[r - 1] + 1 : 0, L = nul[r] - no, sl = len[r], so = seq_off[r];
-    // bytes in front of record r: names (without NULs), two copies of the bases' count, 6 per record
-    uint64_t o = (uint64_t)(no - r) * (plus_name ? 2 : 1) + 2ull * so + 6ull * r;
-    const uint64_t sz = (uint64_t)L * (plus_name ? 2 : 1) + 2ull * sl + 6;
-    if (r == R - 1 && lane == 0) info->text_len = (uint32_t)(o + sz);
-    if (o + sz > text_cap) { if (lane == 0) atomicOr(&W->err, 2u); return; }
-    uint8_t *p = text + o;
-    if (lane == 0) p[0] = '@';
-    warp_copy_add(p + 1, name + no, L, 0, lane);
-    p += 1 + L;
-    if (lane == 0) p[0] = '\n';
-    warp_copy_add(p + 1, seq + so, sl, 0, lane);
-    p += 1 + sl;
-    if (lane == 0) { p[0] = '\n'; p[1] = '+'; }
-    p += 2;
-    if (plus_name) { warp_copy_add(p, name + no, L, 0, lane); p += L; }
-    if (lane == 0) p[0] = '\n';
-    warp_copy_add(p + 1, qual + so, sl, 0x21212121u, lane);                  // + 33 (fqzcomp5.c:2532-2533)
-    if (lane == 0) p[1 + sl] = '\n';
+    __shared__ uint32_t s_nul[GREC + 1], s_so[GREC], s_len[GREC];
+    __shared__ __align__(16) uint8_t s_name[JN_CAP + 32], s_seq[JS_CAP + 32], s_qual[JS_CAP + 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t r0 = blockIdx.x * GREC;
+    if (r0 >= R || W->total != R) return;
+    const uint32_t g = min(GREC, R - r0);
+    for (uint32_t i = threadIdx.x; i < g + 1; i += blockDim.x)
+        s_nul[i] = (r0 == 0 && i == 0) ? 0xffffffffu : nul[r0 - 1 + i];
+    for (uint32_t i = threadIdx.x; i < g; i += blockDim.x) { s_so[i] = seq_off[r0 + i]; s_len[i] = len[r0 + i]; }
+    __syncthreads();
+    const uint32_t nlo = s_nul[0] + 1, nhi = s_nul[g] + 1, nbase = nlo & ~15u;
+    const uint32_t slo = s_so[0], shi = s_so[g - 1] + s_len[g - 1], sbase = slo & ~15u;
+    const bool staged = nhi - nbase <= JN_CAP && shi - sbase <= JS_CAP;
+    if (staged) {
+        // the spans end inside the buffers; the last 16-byte load may not, so bound it by the span
+        stage_span(s_name, name, nbase, nhi, nhi);
+        stage_span(s_seq, seq, sbase, shi, shi);
+        stage_span(s_qual, qual, sbase, shi, shi);
+    }
+    __syncthreads();
+    const uint32_t na0 = (uint32_t)__cvta_generic_to_shared(s_name) - nbase;
+    const uint32_t sa0 = (uint32_t)__cvta_generic_to_shared(s_seq) - sbase;
+    const uint32_t qa0 = (uint32_t)__cvta_generic_to_shared(s_qual) - sbase;
+    auto copy = [&](uint8_t *dst, uint32_t sa, const uint8_t *gsrc, uint32_t len, uint32_t add4) {
+        if (staged) smem_copy_add(dst, sa, len, add4 & 0xff, lane);
+        else warp_copy_add(dst, gsrc, len, add4, lane);
+    };
+    for (uint32_t j = wid; j < g; j += blockDim.x >> 5) {
+        const uint32_t r = r0 + j;
+        const uint32_t no = s_nul[j] + 1, L = s_nul[j + 1] - no, sl = s_len[j], so = s_so[j];
+        // bytes in front of record r: names (without NULs), two copies of the bases' count, 6 per record
+        uint64_t o = (uint64_t)(no - r) * (plus_name ? 2 : 1) + 2ull * so + 6ull * r;
+        const uint64_t sz = (uint64_t)L * (plus_name ? 2 : 1) + 2ull * sl + 6;
+        if (r == R - 1 && lane == 0) info->text_len = (uint32_t)(o + sz);
+        if (o + sz > text_cap) { if (lane == 0) atomicOr(&W->err, 2u); continue; }
+        uint8_t *p = text + o;
+        if (lane == 0) p[0] = '@';
+        copy(p + 1, na0 + no, name + no, L, 0);
+        p += 1 + L;
+        if (lane == 0) p[0] = '\n';
+        copy(p + 1, sa0 + so, seq + so, sl, 0);
+        p += 1 + sl;
+        if (lane == 0) { p[0] = '\n'; p[1] = '+'; }
+        p += 2;
+        if (plus_name) { copy(p, na0 + no, name + no, L, 0); p += L; }
+        if (lane == 0) p[0] = '\n';
+        copy(p + 1, qa0 + so, qual + so, sl, 0x21212121u);                    // + 33 (fqzcomp5.c:2532-2533)
+        if (lane == 0) p[1 + sl] = '\n';
+    }
 }
 
 __global__ void join_finalize(uint32_t R, FqWork *W, FqInfo *info) {
@@ -422,7 +521,7 @@ cudaError_t fq_split_launch(const uint8_t *d_text, uint32_t n, uint8_t *d_name, 
     scan_reduce<<<L.stiles, 256, 0, st>>>(nlen1, d_len, &W->tot[0], max_records, sums0, sums1);
     scan_small<<<1, 1024, 0, st>>>(sums0, toff0, nullptr, sums1, toff1, nullptr, 0, &W->tot[0], max_records, STILE);
     scan_apply<<<L.stiles, 256, 0, st>>>(nlen1, d_len, &W->tot[0], max_records, toff0, toff1, d_name_off, d_seq_off);
-    scatter_kernel<<<cdivu(max_records ? max_records : 1, 8), 256, 0, st>>>(
+    scatter_kernel<<<cdivu(max_records ? max_records : 1, GREC), 256, 0, st>>>(
         d_text, n, nl, L.cap_nl, max_records, d_name_off, d_seq_off, d_name, d_seq, d_qual, name_cap, seq_cap,
         d_flag, W);
     split_finalize<<<1, 1, 0, st>>>(nl, L.cap_nl, max_records, d_name_off, d_seq_off, nlen1, d_len, W, d_info);
@@ -473,7 +572,7 @@ cudaError_t fq_join_launch(const uint8_t *d_name, uint32_t name_len, const uint8
     scan_reduce<<<L.stiles, 256, 0, st>>>(d_len, nullptr, cnt, R, sums0, nullptr);
     scan_small<<<1, 1024, 0, st>>>(sums0, toff0, nullptr, nullptr, nullptr, nullptr, 0, cnt, R, STILE);
     scan_apply<<<L.stiles, 256, 0, st>>>(d_len, nullptr, cnt, R, toff0, nullptr, seq_off, nullptr);
-    gather_kernel_fq<<<cdivu(R ? R : 1, 8), 256, 0, st>>>(d_name, nul, d_seq, d_qual, d_len, seq_off, R, plus_name,
+    gather_kernel_fq<<<cdivu(R ? R : 1, GREC), 256, 0, st>>>(d_name, name_len, nul, d_seq, d_qual, d_len, seq_off, R, plus_name,
                                                           d_text, text_cap, W, d_info);
     join_finalize<<<1, 1, 0, st>>>(R, W, d_info);
     if (launches) *launches += 9;
