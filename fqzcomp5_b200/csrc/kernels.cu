@@ -177,7 +177,7 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
 }
 
 template <bool O1>
-__global__ void __launch_bounds__((O1 ? ENC_WARPS_O1 : ENC_WARPS) * 32, O1 ? 11 : 1)   // O1: 22 warps per SM (<= 92 registers)
+__global__ void __launch_bounds__((O1 ? ENC_WARPS_O1 : ENC_WARPS) * 32, O1 ? 11 : 7)   // O1: 22 warps per SM (<= 92 registers); O0: 28 warps (<= 72) so that the 3815 streams of a 1 GB block are one wave (unbounded the compiler takes 179 registers and residency collapses)
 enc_kernel(EncJob *jobs, uint32_t njobs, uint32_t warp_smem, Pool pool, uint32_t route) {
     extern __shared__ __align__(16) uint8_t smem_all[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
