@@ -348,8 +348,11 @@ struct __align__(16) EncO0Smem {
 
 // Writes the frequency table at `out` (forwards) and the payload below
 // `out_end` (backwards).  Returns 0 ok; *tab_len, *ptr_out give the two pieces.
+// Not inlined: it is called from three places (payload, RLE meta-data, self-compressed order-1
+// tables), and as a function of its own its hot loop gets a register allocation that does not
+// depend on what surrounds the call.
 template <int N>
-__device__ int enc_o0(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_end,
+__device__ __noinline__ int enc_o0(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_end,
                       uint32_t *tab_len, uint8_t **ptr_out, EncO0Smem &S, int lane,
                       const uint32_t *model = nullptr) {
     *tab_len = 0;
