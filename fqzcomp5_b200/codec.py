@@ -34,6 +34,7 @@ EXPORTS = [
     "b200rans_compress_methods_batch", "b200rans_compress_methods", "b200rans_compress_trials",
     "b200fq_split", "b200fq_join", "b200fq_split_dev", "b200fq_join_dev",
     "b200fq_split_scratch_bytes", "b200fq_join_scratch_bytes",
+    "b200fqz_crc32", "b200fqz_crc32_dev", "b200fqz_assemble_block_dev",
 ]
 
 _lib = None
@@ -94,6 +95,9 @@ def lib():
         L.b200fq_join_scratch_bytes.restype = sz
         L.b200fq_split_dev.argtypes = [vp, vp, u32, vp, u32, vp, vp, u32, vp, vp, vp, vp, u32, vp, sz, vp]
         L.b200fq_join_dev.argtypes = [vp, vp, u32, vp, vp, vp, u32, i32, vp, u32, vp, sz, vp]
+        L.b200fqz_crc32.argtypes = [u32, vp, C.c_uint64, pu32]
+        L.b200fqz_crc32_dev.argtypes = [vp, vp, C.c_uint64, u32, vp]
+        L.b200fqz_assemble_block_dev.argtypes = [vp, u32, i32, vp, vp, C.c_uint64, pu32]
         L.b200rans_launch_count.restype = C.c_uint64
         L.b200rans_version.restype = C.c_char_p
         L.b200rans_set_profiling.argtypes = [i32]
@@ -466,3 +470,28 @@ def output_fastq(name, seq, qual, lens, plus_name=0):
     if info.status:
         return None
     return out[:info.text_len].tobytes()
+
+
+# ---------------------------------------------------------------- CRC-32 and block framing
+class FqzPiece(C.Structure):
+    """b200fqz_piece (include/b200rans.h)."""
+    _fields_ = [("ptr", C.c_void_p), ("len", C.c_uint32), ("on_device", C.c_int)]
+
+
+def crc32(data, crc_in=0):
+    """zlib's crc32(crc_in, data) computed on the GPU (host buffer in)."""
+    b = np.frombuffer(bytes(data), np.uint8) if not isinstance(data, np.ndarray) else data
+    out = C.c_uint(0)
+    _check(lib().b200fqz_crc32(crc_in, _addr(b) if b.size else None, b.size, C.byref(out)), "b200fqz_crc32")
+    return out.value
+
+
+def assemble_block_dev(stream, num_records, pieces, d_block_ptr, block_cap):
+    """pieces: list of (address, length, on_device).  Returns the block length."""
+    arr = (FqzPiece * max(len(pieces), 1))()
+    for i, (ptr, ln, dev) in enumerate(pieces):
+        arr[i].ptr, arr[i].len, arr[i].on_device = ptr, ln, int(dev)
+    n = C.c_uint(0)
+    _check(lib().b200fqz_assemble_block_dev(stream, num_records, len(pieces), C.addressof(arr), d_block_ptr,
+                                            block_cap, C.byref(n)), "b200fqz_assemble_block_dev")
+    return n.value

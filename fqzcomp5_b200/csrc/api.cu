@@ -16,6 +16,7 @@
 #include "kernels.h"
 #include "stripe.h"
 #include "fastq.h"
+#include "crc32.h"
 
 using namespace b200;
 
@@ -1047,6 +1048,76 @@ API int b200fq_join(const unsigned char *name, uint32_t name_len, const unsigned
     if (info->status) return 0;
     if (info->text_len) CK(cudaMemcpyAsync(text, D + o_text, info->text_len, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---------------------------------------------------------------- CRC-32 and block framing
+API int b200fqz_crc32_dev(void *stream, const unsigned char *d_buf, uint64_t n, uint32_t crc_in, uint32_t *d_crc) {
+    int err = 0;
+    Ctx *C = get_ctx(&err);
+    if (!C) return err;
+    if ((n && !d_buf) || !d_crc) return B200RANS_EINVAL;
+    Lane &Ln = C->lane[0];
+    cudaStream_t st = stream ? (cudaStream_t)stream : Ln.st;
+    int r = Ln.work.ensure(crc32_scratch_bytes(n) + 256);
+    if (r) return r;
+    int l = 0;
+    CK(crc32_launch(d_buf, n, crc_in, d_crc, nullptr, 0, Ln.work.p, st, &l));
+    C->launches += l;
+    return 0;
+}
+
+API int b200fqz_crc32(uint32_t crc_in, const unsigned char *buf, uint64_t n, uint32_t *crc_out) {
+    int err = 0;
+    Ctx *C = get_ctx(&err);
+    if (!C) return err;
+    if ((n && !buf) || !crc_out) return B200RANS_EINVAL;
+    Lane &Ln = C->lane[0];
+    int r = Ln.io.ensure(n + 512);
+    if (r) return r;
+    if ((r = Ln.hio.ensure(256))) return r;
+    if (n) CK(cudaMemcpyAsync(Ln.io.p + 256, buf, n, cudaMemcpyHostToDevice, Ln.st));
+    if ((r = b200fqz_crc32_dev(Ln.st, Ln.io.p + 256, n, crc_in, (uint32_t *)Ln.io.p))) return r;
+    CK(cudaMemcpyAsync(Ln.hio.p, Ln.io.p, 4, cudaMemcpyDeviceToHost, Ln.st));
+    CK(cudaStreamSynchronize(Ln.st));
+    *crc_out = *(uint32_t *)Ln.hio.p;
+    return 0;
+}
+
+API int b200fqz_assemble_block_dev(void *stream, uint32_t num_records, int n_pieces, const b200fqz_piece *pieces,
+                                   unsigned char *d_block, uint64_t block_cap, uint32_t *block_len) {
+    int err = 0;
+    Ctx *C = get_ctx(&err);
+    if (!C) return err;
+    if (n_pieces < 0 || (n_pieces && !pieces) || !d_block || !block_len) return B200RANS_EINVAL;
+    uint64_t total = 12;
+    for (int i = 0; i < n_pieces; i++) {
+        if (pieces[i].len && !pieces[i].ptr) return B200RANS_EINVAL;
+        total += pieces[i].len;
+    }
+    if (total > block_cap || total > 0xffffffffull) return B200RANS_ESPACE;
+    Lane &Ln = C->lane[0];
+    cudaStream_t st = stream ? (cudaStream_t)stream : Ln.st;
+    int r = Ln.work.ensure(crc32_scratch_bytes(total) + 256);
+    if (r) return r;
+    Stage *S;
+    if ((r = Ln.get_stage(16, &S))) return r;
+    // [block size][num_records][crc]: size and CRC are patched in by the finishing kernel
+    uint32_t *h = (uint32_t *)S->h.p;
+    h[0] = 0; h[1] = num_records; h[2] = 0;
+    CK(cudaMemcpyAsync(d_block, h, 12, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(S->ev, st)); S->busy = true;
+    uint64_t o = 12;
+    for (int i = 0; i < n_pieces; i++) {
+        if (pieces[i].len)
+            CK(cudaMemcpyAsync(d_block + o, pieces[i].ptr, pieces[i].len,
+                               pieces[i].on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        o += pieces[i].len;
+    }
+    int l = 0;
+    CK(crc32_launch(d_block + 12, total - 12, 0, nullptr, d_block, (uint32_t)(total - 4), Ln.work.p, st, &l));
+    C->launches += l;
+    *block_len = (uint32_t)total;
     return 0;
 }
 

@@ -260,6 +260,31 @@ int b200fq_join_dev(void *stream, const unsigned char *d_name, uint32_t name_len
                     unsigned char *d_text, uint32_t text_cap,
                     void *d_scratch, size_t scratch_bytes, b200fq_info *d_info);
 
+/* ------------------------------------------------------------------------
+ * Part 4: the step after the codec -- fqzcomp5's block framing
+ * (encode_block, fqzcomp5.c:2147-2280) with its CRC-32 computed on the device.
+ *
+ * b200fqz_crc32* is zlib's crc32(crc_in, buf, n) (the reference links zlib for
+ * it: fqzcomp5.c:2268-2269, :2310-2311), any alignment, n up to 2^32-1 bytes.
+ * b200fqz_assemble_block_dev builds
+ *     [u32 block size = total-4][u32 num_records][u32 crc][piece 0][piece 1]...
+ * in d_block, the CRC taken over everything after the CRC field (:2266-2274),
+ * so a finished block leaves the GPU in one copy.  Pieces are the sections as
+ * encode_block appends them (name stream; length bytes; 9-byte meta + seq
+ * stream; 9-byte meta + qual stream) and may live in host or device memory.
+ * Asynchronous on `stream`; *block_len (host) is known at once.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+    const void *ptr;
+    uint32_t len;
+    int on_device;          /* 0: host memory, 1: device memory */
+} b200fqz_piece;
+
+int b200fqz_crc32(uint32_t crc_in, const unsigned char *buf, uint64_t n, uint32_t *crc_out);
+int b200fqz_crc32_dev(void *stream, const unsigned char *d_buf, uint64_t n, uint32_t crc_in, uint32_t *d_crc);
+int b200fqz_assemble_block_dev(void *stream, uint32_t num_records, int n_pieces, const b200fqz_piece *pieces,
+                               unsigned char *d_block, uint64_t block_cap, uint32_t *block_len);
+
 /* Number of kernel launches issued by this thread's context so far. */
 uint64_t b200rans_launch_count(void);
 

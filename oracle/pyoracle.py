@@ -239,3 +239,31 @@ class FastqChecker:
         data = open(path, "rb").read()
         os.unlink(path)
         return data
+
+
+# ---------------------------------------------------------------- CRC-32 / block framing checker
+class Crc32Oracle:
+    """oracle/crc32_oracle.c: crc32(data, crc) and frame_block(num_records, pieces)."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "liboracle_crc32.so")
+        if not os.path.exists(path):
+            build()
+        self.lib = L = C.CDLL(path)
+        L.orc_crc32.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64]
+        L.orc_crc32.restype = C.c_uint32
+        L.orc_frame_block.argtypes = [C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_frame_block.restype = C.c_uint32
+
+    def crc32(self, data, crc=0):
+        data = bytes(data)
+        b = C.create_string_buffer(data, max(len(data), 1))
+        return int(self.lib.orc_crc32(crc, C.addressof(b), len(data)))
+
+    def frame_block(self, num_records, pieces):
+        bufs = [C.create_string_buffer(bytes(p), max(len(p), 1)) for p in pieces]
+        ptrs = (C.c_void_p * max(len(bufs), 1))(*[C.addressof(b) for b in bufs])
+        lens = (C.c_uint32 * max(len(bufs), 1))(*[len(p) for p in pieces])
+        out = C.create_string_buffer(12 + sum(len(p) for p in pieces) + 16)
+        n = self.lib.orc_frame_block(num_records, len(pieces), C.addressof(ptrs), C.addressof(lens), C.addressof(out))
+        return out.raw[:n]

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_functions():
     h = open(os.path.join(ROOT, "include", "b200rans.h")).read()
     h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:rans|b200rans|b200fq)_\w+)\s*\(", h)))
+    return sorted(set(re.findall(r"\b((?:rans|b200rans|b200fqz|b200fq)_\w+)\s*\(", h)))
 
 
 def test_library_exports_every_declared_symbol():
