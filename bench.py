@@ -218,7 +218,7 @@ def run_reference(args, gen, order, total, S):
                                    % (len(sl), S, sample / 1e6, codec.kind, cores)},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------ GPU arm
@@ -406,7 +406,7 @@ def run_b200(args, gen, order, total, S):
                 "sample": "first %d slices of %d B (%.0f MB) of the same block, %s build, %d threads"
                           % (k, S, sb / 1e6, codec.kind, cores),
                 "enc_gbs": sb / te / 1e9, "dec_gbs": sb / td / 1e9}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -416,7 +416,34 @@ def synth_seed(gen):
     return {"illumina_qual": 2, "binned_qual": 22, "illumina_seq": 3, "ont_qual": 4}[gen]
 
 
+class QuietStdout:
+    """Route everything libraries print on fd 1 (e.g. NCCL's version banner) to stderr, so that
+    stdout carries exactly one JSON line; emit() writes to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.real, (text + "\n").encode())
+
+
+OUT = None
+
+
+def emit(obj):
+    line = json.dumps(obj)
+    if OUT is not None:
+        OUT.emit(line)
+    else:
+        print(line)
+
+
 def main():
+    global OUT
+    OUT = QuietStdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
