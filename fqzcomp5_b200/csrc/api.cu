@@ -62,13 +62,26 @@ struct Layout {
 };
 
 constexpr int NSTAGE = 4;
-constexpr int NPIPE = 4;                  // chunks in flight in the host-buffer API
-constexpr size_t CHUNK_BYTES = 48u << 20; // uncompressed bytes per pipeline chunk ...
-constexpr int CHUNK_MIN_STREAMS = 256;    // ... but at least this many streams: a chunk of few streams is latency bound
+constexpr int NPIPE = 6;                  // lanes: chunks in flight in the host-buffer API
+// a pipeline chunk is ~chunk_bytes() of uncompressed data but at least chunk_min_streams() streams
+// (a chunk of few streams is latency bound); see the knobs below
 constexpr int CHUNK_MIN_STREAMS_SLOW = 1536;  // PACK / RLE streams take several ms each whatever their number: a
                                               // chunk should fill most of the GPU's stream slots
 constexpr int CHUNK_MAX_STREAMS = 16384;
 struct Stage { Arena h; cudaEvent_t ev = nullptr; bool busy = false; };
+
+// Tuning knobs of the host-buffer pipeline (environment overrides are for measurement only).
+inline int env_int(const char *name, int dflt, int lo, int hi) {
+    const char *e = getenv(name);
+    if (!e) return dflt;
+    int v = atoi(e);
+    return v < lo ? lo : v > hi ? hi : v;
+}
+// chunks submitted (copy in + kernels queued) ahead of the chunk whose results are being read back:
+// the host blocks on that chunk's kernels, and without work queued behind it the copy engines idle
+inline int pipe_depth() { static int v = env_int("B200RANS_PIPE_DEPTH", 2, 1, NPIPE - 1); return v; }
+inline size_t chunk_bytes() { static size_t v = (size_t)env_int("B200RANS_CHUNK_MB", 48, 1, 1024) << 20; return v; }
+inline int chunk_min_streams() { static int v = env_int("B200RANS_CHUNK_STREAMS", 256, 1, 16384); return v; }
 
 // One pipeline lane: a stream plus the arenas a chunk of work needs.  Chunks of a
 // large host-buffer batch rotate over NPIPE lanes so that the H2D copy of one
@@ -436,21 +449,21 @@ int compress_batch_impl(int n, const unsigned char *const *in, const unsigned in
     Ctx *C = get_ctx(&err);
     if (!C) return err;
     if (n <= 0) return 0;
-    // ---- split into pipeline chunks of ~CHUNK_BYTES of input
+    // ---- split into pipeline chunks of ~chunk_bytes() of input
     bool slow = false;
     {
         const int *o = M ? methods : order;
         const size_t no = M ? mfirst[n] : (size_t)n;
         for (size_t i = 0; i < no && !slow; i++) slow = (o[i] & (X_PACK | X_RLE)) != 0;
     }
-    const int min_streams = slow ? CHUNK_MIN_STREAMS_SLOW : CHUNK_MIN_STREAMS;
+    const int min_streams = slow ? CHUNK_MIN_STREAMS_SLOW : chunk_min_streams();
     std::vector<EncChunk> ch;
     for (int k = 0; k < n;) {
         EncChunk c;
         c.k0 = k;
         size_t acc = 0;
         auto streams = [&](int k1) { return M ? (int)(mfirst[k1] - mfirst[c.k0]) : k1 - c.k0; };
-        while (k < n && (k == c.k0 || ((acc + in_size[k] <= CHUNK_BYTES || streams(k) < min_streams) &&
+        while (k < n && (k == c.k0 || ((acc + in_size[k] <= chunk_bytes() || streams(k) < min_streams) &&
                                        streams(k) < CHUNK_MAX_STREAMS)))
             acc += in_size[k++];
         c.k1 = k;
@@ -547,13 +560,14 @@ int compress_batch_impl(int n, const unsigned char *const *in, const unsigned in
     auto finish = [&](EncChunk &c) -> int { CK(cudaStreamSynchronize(c.L->st)); return 0; };
 
     int nc = (int)ch.size();
+    const int depth = pipe_depth();
     for (int c = 0; c < nc && !rc; c++) {
         ch[c].L = &C->lane[c % NPIPE];
-        rc = submit(ch[c]);
-        if (!rc && c >= 1) rc = readback(ch[c - 1]);
-        if (!rc && c >= NPIPE - 1) rc = finish(ch[c - (NPIPE - 1)]);      // frees the lane chunk c+1 will use
+        if (c >= NPIPE) rc = finish(ch[c - NPIPE]);                  // the lane's previous chunk has left
+        if (!rc) rc = submit(ch[c]);
+        if (!rc && c >= depth) rc = readback(ch[c - depth]);
     }
-    if (!rc) rc = readback(ch[nc - 1]);
+    for (int c = nc > depth ? nc - depth : 0; c < nc && !rc; c++) rc = readback(ch[c]);
     for (auto &l : C->lane) cudaStreamSynchronize(l.st);
     return rc;
 }
@@ -598,7 +612,7 @@ int uncompress_batch_impl(int n, const unsigned char *const *in, const unsigned 
     {
         DecChunk c;
         size_t acc = 0;
-        int dec_min_streams = CHUNK_MIN_STREAMS;
+        int dec_min_streams = chunk_min_streams();
         for (int k = 0; k < n; k++) {
             DecItem &it = items[k];
             int flag = 0, hdr = 0;
@@ -628,7 +642,7 @@ int uncompress_batch_impl(int n, const unsigned char *const *in, const unsigned 
             it.njobs = (uint32_t)jin.size() - it.first_job;
             acc += ocap[k];
             if (it.njobs && (jflag.back() & (X_PACK | X_RLE))) dec_min_streams = CHUNK_MIN_STREAMS_SLOW;
-            if ((acc >= CHUNK_BYTES && k - c.k0 + 1 >= dec_min_streams) || k - c.k0 + 1 >= CHUNK_MAX_STREAMS || k == n - 1) {
+            if ((acc >= chunk_bytes() && k - c.k0 + 1 >= dec_min_streams) || k - c.k0 + 1 >= CHUNK_MAX_STREAMS || k == n - 1) {
                 c.k1 = k + 1; c.j1 = (int)jin.size();
                 ch.push_back(c);
                 c = DecChunk(); c.k0 = k + 1; c.j0 = (int)jin.size();
@@ -720,13 +734,14 @@ int uncompress_batch_impl(int n, const unsigned char *const *in, const unsigned 
     auto finish = [&](DecChunk &c) -> int { CK(cudaStreamSynchronize(c.L->st)); return 0; };
 
     int nc = (int)ch.size();
+    const int depth = pipe_depth();
     for (int c = 0; c < nc && !rc; c++) {
         ch[c].L = &C->lane[c % NPIPE];
-        rc = submit(ch[c]);
-        if (!rc && c >= 1) rc = readback(ch[c - 1]);
-        if (!rc && c >= NPIPE - 1) rc = finish(ch[c - (NPIPE - 1)]);
+        if (c >= NPIPE) rc = finish(ch[c - NPIPE]);
+        if (!rc) rc = submit(ch[c]);
+        if (!rc && c >= depth) rc = readback(ch[c - depth]);
     }
-    if (!rc && nc) rc = readback(ch[nc - 1]);
+    for (int c = nc > depth ? nc - depth : 0; c < nc && !rc; c++) rc = readback(ch[c]);
     for (auto &l : C->lane) cudaStreamSynchronize(l.st);
     return rc;
 }
