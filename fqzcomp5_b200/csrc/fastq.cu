@@ -4,7 +4,8 @@
 // 4-line FASTQ text already in HBM:
 //   1. count_kernel      newlines per 16 KiB tile                        (reads the text)
 //   2. scan_small        exclusive scan of the tile counts
-//   3. mark_kernel       position of every newline, in order            (reads the text)
+//   3. mark_kernel       position of every newline, in order            (reads the n/8 bytes of match
+//                        masks pass 1 left behind)
 //   4. records_kernel    one thread per record: field lengths, '@' / '+' / length checks,
 //                        the trailing partial record's rules, fixed_len
 //   5. scan (3 kernels)  offsets of every record in the name and seq/qual buffers
@@ -16,7 +17,7 @@
 // fqzcomp5.c:2532-2533 folded into the copy.
 //
 // Algorithmic bytes: split reads n and writes ~n (names, bases, qualities, 8 bytes per
-// record); join the same.  The text is re-read by passes 1 and 3 (2 n extra reads).
+// record); join the same.  The text is read twice (passes 1 and 6).
 #include "fastq.h"
 #include "common.cuh"
 
@@ -74,11 +75,13 @@ __device__ __forceinline__ uint32_t match32(const uint8_t *text, uint32_t n, uin
 template <bool CHECK_NUL>
 __global__ void __launch_bounds__(TPB)
 count_kernel(const uint8_t *__restrict__ text, uint32_t n, uint32_t B, uint32_t *__restrict__ tile_count,
-             FqWork *W) {
+             uint32_t *__restrict__ masks, FqWork *W) {
     __shared__ uint32_t ws[TPB / 32];
     const uint32_t base = blockIdx.x * TILE + threadIdx.x * 32;
     bool nul = false;
-    uint32_t c = __popc(match32<CHECK_NUL>(text, n, base, B, &nul));
+    const uint32_t m = match32<CHECK_NUL>(text, n, base, B, &nul);
+    masks[blockIdx.x * TPB + threadIdx.x] = m;       // mark_kernel reads n/8 bytes of masks instead of the text again
+    uint32_t c = __popc(m);
     c = warp_sum(c);
     if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
     if (CHECK_NUL && __any_sync(FULL, nul) && (threadIdx.x & 31) == 0) atomicOr(&W->err, 1u);
@@ -126,13 +129,12 @@ scan_small(const uint32_t *in0, uint32_t *out0, uint32_t *tot0, const uint32_t *
 }
 
 __global__ void __launch_bounds__(TPB)
-mark_kernel(const uint8_t *__restrict__ text, uint32_t n, uint32_t B, const uint32_t *__restrict__ tile_off,
+mark_kernel(const uint32_t *__restrict__ masks, const uint32_t *__restrict__ tile_off,
             uint32_t *__restrict__ pos, uint32_t cap) {
     __shared__ uint32_t ws[TPB / 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t base = blockIdx.x * TILE + threadIdx.x * 32;
-    bool nul;
-    uint32_t m = match32<false>(text, n, base, B, &nul);
+    uint32_t m = masks[blockIdx.x * TPB + threadIdx.x];
     uint32_t c = __popc(m);
     uint32_t incl = warp_incl_scan(c, lane);
     if (lane == 31) ws[wid] = incl;
@@ -476,7 +478,7 @@ inline uint32_t cdivu(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct SplitLayout {
-    size_t work, tile_cnt, tile_off, nl, nlen1, sums0, sums1, toff0, toff1, total;
+    size_t work, tile_cnt, tile_off, masks, nl, nlen1, sums0, sums1, toff0, toff1, total;
     uint32_t ntiles, cap_nl, stiles;
     SplitLayout(uint32_t n, uint32_t max_records) {
         ntiles = cdivu(n ? n : 1, TILE);
@@ -486,6 +488,7 @@ struct SplitLayout {
         work = o; o += al256(sizeof(FqWork));
         tile_cnt = o; o += al256((size_t)ntiles * 4);
         tile_off = o; o += al256((size_t)ntiles * 4);
+        masks = o; o += al256((size_t)ntiles * TPB * 4);
         nl = o; o += al256((size_t)cap_nl * 4);
         nlen1 = o; o += al256((size_t)max_records * 4 + 4);
         sums0 = o; o += al256((size_t)stiles * 4);
@@ -512,9 +515,10 @@ cudaError_t fq_split_launch(const uint8_t *d_text, uint32_t n, uint8_t *d_name, 
     uint32_t *toff0 = (uint32_t *)(S + L.toff0), *toff1 = (uint32_t *)(S + L.toff1);
     cudaError_t e = cudaMemsetAsync(W, 0, sizeof(FqWork), st);
     if (e != cudaSuccess) return e;
-    count_kernel<true><<<L.ntiles, TPB, 0, st>>>(d_text, n, '\n', tile_cnt, W);
+    uint32_t *masks = (uint32_t *)(S + L.masks);
+    count_kernel<true><<<L.ntiles, TPB, 0, st>>>(d_text, n, '\n', tile_cnt, masks, W);
     scan_small<<<1, 1024, 0, st>>>(tile_cnt, tile_off, &W->total, nullptr, nullptr, nullptr, L.ntiles, nullptr, 0, 1);
-    mark_kernel<<<L.ntiles, TPB, 0, st>>>(d_text, n, '\n', tile_off, nl, L.cap_nl);
+    mark_kernel<<<L.ntiles, TPB, 0, st>>>(masks, tile_off, nl, L.cap_nl);
     records_kernel<<<cdivu(max_records + 1, 256), 256, 0, st>>>(d_text, n, nl, L.cap_nl, max_records, nlen1, d_len, W);
     // element count of the offset scans (a held-back last record is scanned too, harmlessly)
     set_count<<<1, 1, 0, st>>>(W, L.cap_nl, max_records);
@@ -531,7 +535,7 @@ cudaError_t fq_split_launch(const uint8_t *d_text, uint32_t n, uint8_t *d_name, 
 
 namespace {
 struct JoinLayout {
-    size_t work, tile_cnt, tile_off, nul, seq_off, sums0, toff0, cnt, total;
+    size_t work, tile_cnt, tile_off, masks, nul, seq_off, sums0, toff0, cnt, total;
     uint32_t ntiles, stiles;
     JoinLayout(uint32_t name_len, uint32_t R) {
         ntiles = cdivu(name_len ? name_len : 1, TILE);
@@ -540,6 +544,7 @@ struct JoinLayout {
         work = o; o += al256(sizeof(FqWork));
         tile_cnt = o; o += al256((size_t)ntiles * 4);
         tile_off = o; o += al256((size_t)ntiles * 4);
+        masks = o; o += al256((size_t)ntiles * TPB * 4);
         nul = o; o += al256((size_t)R * 4 + 4);
         seq_off = o; o += al256((size_t)R * 4 + 4);
         sums0 = o; o += al256((size_t)stiles * 4);
@@ -565,9 +570,10 @@ cudaError_t fq_join_launch(const uint8_t *d_name, uint32_t name_len, const uint8
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(d_info, 0, sizeof(FqInfo), st);
     if (e != cudaSuccess) return e;
-    count_kernel<false><<<L.ntiles, TPB, 0, st>>>(d_name, name_len, 0, tile_cnt, W);
+    uint32_t *masks = (uint32_t *)(S + L.masks);
+    count_kernel<false><<<L.ntiles, TPB, 0, st>>>(d_name, name_len, 0, tile_cnt, masks, W);
     scan_small<<<1, 1024, 0, st>>>(tile_cnt, tile_off, &W->total, nullptr, nullptr, nullptr, L.ntiles, nullptr, 0, 1);
-    mark_kernel<<<L.ntiles, TPB, 0, st>>>(d_name, name_len, 0, tile_off, nul, R);
+    mark_kernel<<<L.ntiles, TPB, 0, st>>>(masks, tile_off, nul, R);
     set_u32<<<1, 1, 0, st>>>(cnt, R);
     scan_reduce<<<L.stiles, 256, 0, st>>>(d_len, nullptr, cnt, R, sums0, nullptr);
     scan_small<<<1, 1024, 0, st>>>(sums0, toff0, nullptr, nullptr, nullptr, nullptr, 0, cnt, R, STILE);
