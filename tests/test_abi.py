@@ -54,6 +54,35 @@ def test_no_cpu_fallback_without_gpu(capfd):
     buf = np.frombuffer(b"abcabcabc" * 100, np.uint8)
     with pytest.raises(codec.B200RansError):
         codec.compress_batch(buf, [0], [buf.size], [0])
+    # the rows around the codec fail the same way: method trials, FASTQ split / join, CRC, framing
+    with pytest.raises(codec.B200RansError):
+        codec.compress_methods_batch(buf, [0], [buf.size], [0, 1])
+    with pytest.raises(codec.B200RansError):
+        codec.compress_trials(buf, [0], [buf.size], [[0, 1]])
+    assert codec.compress_methods(b"hello world" * 10, [0, 1])[0] is None
+    with pytest.raises(codec.B200RansError):
+        codec.load_seqs(b"@r\nAC\n+\nII\n")
+    with pytest.raises(codec.B200RansError):
+        codec.output_fastq(b"r\0", b"AC", b"((", [2])
+    with pytest.raises(codec.B200RansError):
+        codec.crc32(b"123456789")
+
+
+def test_new_entry_points_reject_bad_arguments_before_touching_a_device():
+    """Argument validation that needs no GPU: NULL pointers and empty method lists are EINVAL / ENODEV,
+    never a crash."""
+    import ctypes as C
+    from fqzcomp5_b200 import codec
+    L = codec.lib()
+    assert L.b200rans_compress_methods_batch(1, None, None, 0, None, None, 0, None, None, None, None) < 0
+    assert L.b200rans_compress_trials(1, None, None, None, None, None, 0, None, None, None, None) < 0
+    assert L.b200fq_split(None, 5, None, 0, None, None, 0, None, None, 0, None) < 0
+    assert L.b200fq_join(None, 0, None, None, 0, None, 0, 0, None, 0, None) < 0
+    assert L.b200fqz_crc32(0, None, 9, None) < 0
+    n = C.c_uint(0)
+    assert L.b200fqz_assemble_block_dev(None, 0, 1, None, None, 0, C.byref(n)) < 0
+    assert L.b200fq_split_scratch_bytes(1 << 20, 1000) > 1000 * 16
+    assert L.b200fq_join_scratch_bytes(1 << 20, 1000) > 1000 * 8
 
 
 def test_product_never_imports_the_oracle():
