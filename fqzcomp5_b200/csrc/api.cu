@@ -88,6 +88,8 @@ inline int chunk_min_streams() { static int v = env_int("B200RANS_CHUNK_STREAMS"
 // chunk, the kernels of the previous and the D2H copy of the one before overlap.
 struct Lane {
     cudaStream_t st = nullptr;
+    cudaStream_t aux[2] = {nullptr, nullptr};   // side streams: coder launches of different routes run side by side
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
     Arena work;                 // device: jobs, slots, scratch, pool
     Arena io;                   // device: staged inputs / outputs of the host-buffer API
     Arena hio;                  // pinned: results read back
@@ -96,6 +98,9 @@ struct Lane {
 
     int init() {
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        for (auto &a : aux) CK(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        for (auto &j : join) CK(cudaEventCreateWithFlags(&j, cudaEventDisableTiming));
         hio.pinned = true;
         for (auto &s : stage) { s.h.pinned = true; CK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming)); }
         return 0;
@@ -114,6 +119,9 @@ struct Lane {
         if (st) cudaStreamSynchronize(st);
         work.release(); io.release(); hio.release();
         for (auto &s : stage) { s.h.release(); if (s.ev) cudaEventDestroy(s.ev); }
+        for (auto &a : aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); a = nullptr; }
+        if (fork) cudaEventDestroy(fork);
+        for (auto &j : join) if (j) cudaEventDestroy(j);
         if (st) cudaStreamDestroy(st);
         st = nullptr;
     }
@@ -314,9 +322,24 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
     if (n_model) { CK(launch_hist(d_jobs, (uint32_t)njobs, st)); C.launches++; }
     // ---- encode: order-0 streams on the lean kernel, the rest on the order-1 kernel
     if (C.prof) CK(cudaEventRecord(C.pe[0], st));
-    if (n_o0) { CK(launch_enc(d_jobs, (uint32_t)njobs, ROUTE_O0, pool, st)); C.launches++; }
-    if (n_o1 > n_o1w) { CK(launch_enc(d_jobs, (uint32_t)njobs, ROUTE_O1, pool, st)); C.launches++; }
-    if (n_o1w) { CK(launch_enc(d_jobs, (uint32_t)njobs, ROUTE_O1_WIDE, pool, st)); C.launches++; }
+    {
+        // streams of different routes are independent: their launches go to side streams so that the
+        // few long PACK / RLE order-1 streams of a mixed batch (a method trial) overlap the rest
+        const uint32_t routes[3] = {ROUTE_O1_WIDE, ROUTE_O1, ROUTE_O0};        // longest first
+        const bool have[3] = {n_o1w != 0, n_o1 > n_o1w, n_o0 != 0};
+        const int nr = (int)have[0] + have[1] + have[2];
+        if (nr > 1) CK(cudaEventRecord(Ln.fork, st));
+        int used = 0;
+        for (int i = 0; i < 3; i++) {
+            if (!have[i]) continue;
+            cudaStream_t s2 = used == 0 ? st : Ln.aux[used - 1];
+            if (used) CK(cudaStreamWaitEvent(s2, Ln.fork, 0));
+            CK(launch_enc(d_jobs, (uint32_t)njobs, routes[i], pool, s2));
+            C.launches++;
+            if (used) { CK(cudaEventRecord(Ln.join[used - 1], s2)); CK(cudaStreamWaitEvent(st, Ln.join[used - 1], 0)); }
+            used++;
+        }
+    }
     if (C.prof) { CK(cudaEventRecord(C.pe[1], st)); C.pe_valid[0] = true; }
     CK(cudaEventRecord(S->ev, st)); S->busy = true;
     // ---- STRIPE: choose the smallest method per sub-stream and assemble the parent
@@ -377,8 +400,18 @@ int dec_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
     CK(cudaMemsetAsync(W + o_ctr, 0, 256, st));
     Pool pool{W + o_pool, pool_bytes, (unsigned long long *)(W + o_ctr)};
     if (C.prof) CK(cudaEventRecord(C.pe[2], st));
-    if (n_o0) { CK(launch_dec(d_jobs, (uint32_t)n, false, pool, st)); C.launches++; }
-    if (n_o1) { CK(launch_dec(d_jobs, (uint32_t)n, true, pool, st)); C.launches++; }
+    if (n_o0 && n_o1) {           // independent streams: the two launches run side by side
+        CK(cudaEventRecord(Ln.fork, st));
+        CK(cudaStreamWaitEvent(Ln.aux[0], Ln.fork, 0));
+        CK(launch_dec(d_jobs, (uint32_t)n, true, pool, st));
+        CK(launch_dec(d_jobs, (uint32_t)n, false, pool, Ln.aux[0]));
+        CK(cudaEventRecord(Ln.join[0], Ln.aux[0]));
+        CK(cudaStreamWaitEvent(st, Ln.join[0], 0));
+        C.launches += 2;
+    } else {
+        if (n_o0) { CK(launch_dec(d_jobs, (uint32_t)n, false, pool, st)); C.launches++; }
+        if (n_o1) { CK(launch_dec(d_jobs, (uint32_t)n, true, pool, st)); C.launches++; }
+    }
     if (C.prof) { CK(cudaEventRecord(C.pe[3], st)); C.pe_valid[1] = true; }
     CK(cudaEventRecord(S->ev, st)); S->busy = true;
     CK(launch_dec_results(d_jobs, (uint32_t)n, d_osz, d_status, st));
