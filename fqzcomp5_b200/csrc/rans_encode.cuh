@@ -421,6 +421,43 @@ __device__ __noinline__ int enc_o0(const uint8_t *in, uint32_t n, uint8_t *out, 
         R = enc_step(R, act, e2, w, lane);
         R = enc_step(R, act, e3, w, lane);
     };
+    if (N == 32 && i >= 4 * 512) {
+        // 32 lanes: the symbols of 16 steps are 512 consecutive bytes.  The warp brings them in
+        // with one coalesced 16-byte load per lane, a whole chunk ahead of their use, and parks them
+        // in shared memory (the histogram is dead by now: S.F holds two chunks); a step then takes
+        // its byte from there.  One global load per 16 steps instead of one per step, and no
+        // state-chain instruction ever waits on global memory.
+        const uint32_t st_s = (uint32_t)__cvta_generic_to_shared(S.F);
+        while (i & 511) {                                    // steps above the highest chunk boundary
+            w.maybe_flush(lane);
+            R = enc_step(R, act, S.sym[q[i - N]], w, lane);
+            i -= N;
+        }
+        const bool al16 = (((uintptr_t)in) & 15) == 0;
+        auto load16 = [&](uint32_t at) -> uint4 {            // plain loads: `in` may be PACK / RLE output
+            const uint8_t *p = in + at + 16 * lane;
+            return al16 ? *(const uint4 *)p : ld16_any(p);
+        };
+        uint4 nxt = load16(i - 512);
+        uint32_t buf = 0;
+        while (i >= 512) {
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(st_s + buf * 512 + 16 * lane), "r"(nxt.x),
+                         "r"(nxt.y), "r"(nxt.z), "r"(nxt.w) : "memory");
+            __syncwarp();
+            if (i >= 1024) nxt = load16(i - 1024);
+            const uint32_t b = st_s + buf * 512 + lane;
+#pragma unroll
+            for (int gi = 3; gi >= 0; gi--) {
+                uint32_t s4[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(s4[u]) : "r"(b + 32 * (4 * gi + 3 - u)));
+                group(s4);
+            }
+            i -= 512;
+            buf ^= 1;
+        }
+    }
     if (i >= 24 * N) {
         fetch(sA, i); fetch(sB, i - 4 * N); fetch(sC, i - 8 * N);
         for (; i >= 24 * N; i -= 12 * N) {
