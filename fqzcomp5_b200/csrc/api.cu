@@ -80,6 +80,13 @@ inline int env_int(const char *name, int dflt, int lo, int hi) {
 // chunks submitted (copy in + kernels queued) ahead of the chunk whose results are being read back:
 // the host blocks on that chunk's kernels, and without work queued behind it the copy engines idle
 inline int pipe_depth() { static int v = env_int("B200RANS_PIPE_DEPTH", 2, 1, NPIPE - 1); return v; }
+// plain streams of at least this many bytes get their counts from hist_kernel (one CTA per stream)
+// instead of counting inside the coder warp
+inline uint32_t hist_min_bytes(bool o1) {
+    static uint32_t v0 = (uint32_t)env_int("B200RANS_HIST_MIN_O0", 4096, 0, 0x7fffffff);
+    static uint32_t v1 = (uint32_t)env_int("B200RANS_HIST_MIN_O1", 4096, 0, 0x7fffffff);
+    return o1 ? v1 : v0;
+}
 inline size_t chunk_bytes() { static size_t v = (size_t)env_int("B200RANS_CHUNK_MB", 48, 1, 1024) << 20; return v; }
 inline int chunk_min_streams() { static int v = env_int("B200RANS_CHUNK_STREAMS", 256, 1, 16384); return v; }
 
@@ -244,7 +251,7 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
         J.slot_cap = slot_cap;
         J.slot = (uint8_t *)L.take(slot_cap, 256);
         if (ord & (X_PACK | X_RLE)) J.work = (uint8_t *)L.take((size_t)isz * 4 + isz / 4 + 8192, 256);
-        else if (isz >= 4096) {
+        else if (isz >= hist_min_bytes((ord & 1) != 0)) {
             // big plain streams: counts come from hist_kernel (order-1: up to (isz+1)^2 or 256^2 pairs)
             size_t pairs = ((ord & 1) && isz >= 8) ? std::min<size_t>(65536, ((size_t)isz + 1) * (isz + 1)) : 0;
             J.model = (uint32_t *)(L.take((MODEL_HDR_WORDS + pairs) * 4, 256) + 1);   // +1: null stays null
