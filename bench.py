@@ -412,6 +412,46 @@ def run_b200(args, gen, order, total, S):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------ rows around the codec
+EXTRA = {
+    "fastq_split": "FASTQ block split (load_seqs) GB/s of text on one B200",
+    "fastq_join": "FASTQ block join (output_fastq) GB/s of text on one B200",
+    "crc32": "CRC-32 of a compressed block GB/s on one B200",
+}
+
+
+def run_extra(args):
+    """The steps either side of the codec, measured by scripts/fastq_timing.py and
+    scripts/crc32_timing.py (CUDA events on the launching stream, inputs resident in HBM, several GB of
+    distinct data per timed loop so nothing is served from L2), reported in this file's JSON shape."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    if args.workload == "crc32":
+        import crc32_timing
+        r = crc32_timing.main(["crc32_timing"] + ([str(args.bytes)] if args.bytes else []))
+        value, ms, roof = r["gbs"], r["ms"], r["roofline"]
+        e2e = None
+        cpu = {"value": r["cpu_baseline"]["gbs"], "unit": "GB/s", "cores": 1, "kind": "reference",
+               "sample": r["cpu_baseline"]["kind"] + ", the whole buffer"}
+        launches = r["launches"]
+    else:
+        import fastq_timing
+        r = fastq_timing.main(["fastq_timing"] + ([str(args.bytes // 331)] if args.bytes else []))
+        k = "split" if args.workload == "fastq_split" else "join"
+        value, ms, roof = r[k]["gbs_text"], r[k]["ms"], r[k]["roofline"]
+        e2e = {"value": r["e2e"][k + "_gbs"], "unit": "GB/s", "note": r["e2e"]["note"]}
+        cpu = {"value": r["cpu_baseline"][k + "_gbs"], "unit": "GB/s", "cores": 1, "kind": r["cpu_baseline"]["kind"],
+               "sample": r["cpu_baseline"]["sample"]}
+        launches = r[k]["launches"]
+    roof = dict(roof, traffic=None)
+    emit({"metric": EXTRA[args.workload], "value": value, "unit": "GB/s", "n_gpus": 1, "steps": 10, "warmup": 3,
+          "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+          "data": "synthetic", "config": {"workload": args.workload, "description": r["workload"],
+                                          "l2": "inputs exceed the 126 MB L2"},
+          "e2e": e2e, "gpu_launches": launches * 10, "roofline": roof, "cpu_baseline": cpu})
+
+
 def synth_seed(gen):
     return {"illumina_qual": 2, "binned_qual": 22, "illumina_seq": 3, "ont_qual": 4}[gen]
 
@@ -449,11 +489,18 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="illumina_qual_o0", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="illumina_qual_o0", choices=sorted(WORKLOADS) + sorted(EXTRA))
     ap.add_argument("--bytes", type=int, default=0, help="block size per GPU (default: the config's 1 GB)")
     ap.add_argument("--slice", type=int, default=256 << 10, help="bytes per rans_compress_to_4x16 call")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    if args.workload in EXTRA:
+        if args.impl == "reference":
+            if int(os.environ.get("RANK", "0")) == 0:
+                emit({"impl": "reference", "unavailable": "the CPU leg of %s is reported inside the b200 arm's "
+                      "cpu_baseline (one thread: the reference runs this step on one thread)" % args.workload})
+            return
+        return run_extra(args)
     gen, order, total, _ = WORKLOADS[args.workload]
     if args.bytes:
         total = args.bytes
