@@ -99,6 +99,8 @@ struct Lane {
     cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
     Arena work;                 // device: jobs, slots, scratch, pool
     Arena io;                   // device: staged inputs / outputs of the host-buffer API
+    Arena crc;                  // device: CRC-32 tables and tile values (kept apart from `work`, which an
+                                // encode still in flight on another stream may be using)
     Arena hio;                  // pinned: results read back
     Stage stage[NSTAGE];        // pinned: job descriptors in flight
     int next_stage = 0;
@@ -124,7 +126,7 @@ struct Lane {
     }
     void destroy() {
         if (st) cudaStreamSynchronize(st);
-        work.release(); io.release(); hio.release();
+        work.release(); io.release(); crc.release(); hio.release();
         for (auto &s : stage) { s.h.release(); if (s.ev) cudaEventDestroy(s.ev); }
         for (auto &a : aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); a = nullptr; }
         if (fork) cudaEventDestroy(fork);
@@ -1114,10 +1116,10 @@ API int b200fqz_crc32_dev(void *stream, const unsigned char *d_buf, uint64_t n, 
     if ((n && !d_buf) || !d_crc) return B200RANS_EINVAL;
     Lane &Ln = C->lane[0];
     cudaStream_t st = stream ? (cudaStream_t)stream : Ln.st;
-    int r = Ln.work.ensure(crc32_scratch_bytes(n) + 256);
+    int r = Ln.crc.ensure(crc32_scratch_bytes(n) + 256);
     if (r) return r;
     int l = 0;
-    CK(crc32_launch(d_buf, n, crc_in, d_crc, nullptr, 0, Ln.work.p, st, &l));
+    CK(crc32_launch(d_buf, n, crc_in, d_crc, nullptr, 0, Ln.crc.p, st, &l));
     C->launches += l;
     return 0;
 }
@@ -1153,7 +1155,7 @@ API int b200fqz_assemble_block_dev(void *stream, uint32_t num_records, int n_pie
     if (total > block_cap || total > 0xffffffffull) return B200RANS_ESPACE;
     Lane &Ln = C->lane[0];
     cudaStream_t st = stream ? (cudaStream_t)stream : Ln.st;
-    int r = Ln.work.ensure(crc32_scratch_bytes(total) + 256);
+    int r = Ln.crc.ensure(crc32_scratch_bytes(total) + 256);
     if (r) return r;
     Stage *S;
     if ((r = Ln.get_stage(16, &S))) return r;
@@ -1170,7 +1172,7 @@ API int b200fqz_assemble_block_dev(void *stream, uint32_t num_records, int n_pie
         o += pieces[i].len;
     }
     int l = 0;
-    CK(crc32_launch(d_block + 12, total - 12, 0, nullptr, d_block, (uint32_t)(total - 4), Ln.work.p, st, &l));
+    CK(crc32_launch(d_block + 12, total - 12, 0, nullptr, d_block, (uint32_t)(total - 4), Ln.crc.p, st, &l));
     C->launches += l;
     *block_len = (uint32_t)total;
     return 0;

@@ -272,7 +272,9 @@ int b200fq_join_dev(void *stream, const unsigned char *d_name, uint32_t name_len
  * so a finished block leaves the GPU in one copy.  Pieces are the sections as
  * encode_block appends them (name stream; length bytes; 9-byte meta + seq
  * stream; 9-byte meta + qual stream) and may live in host or device memory.
- * Asynchronous on `stream`; *block_len (host) is known at once.
+ * Asynchronous on `stream`; *block_len (host) is known at once.  Like every
+ * `_dev` entry point it uses scratch owned by the calling thread's context: keep
+ * the device-resident calls of one thread on one stream (or order them yourself).
  * ---------------------------------------------------------------------- */
 typedef struct {
     const void *ptr;
