@@ -68,3 +68,23 @@ def test_two_rank_partition_over_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [1000 + 7 * b for b in range(nblocks)] and tmax == 2.0
+
+
+def test_tok3_method_lists_follow_the_reference_filters():
+    """tokenise_name3.c:1268-1417: levels 1-9 map to table rows 0-4; the rANS build clears X32 (0x04)
+    from every entry; STRIPE entries are skipped unless the stream length is a multiple of 4."""
+    from fqzcomp5_b200 import codec
+    assert [codec.tok3_level_row(l) for l in (0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 12)] == [0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4]
+    assert len(codec.TOK3_METHODS) == 5 and all(len(r) == len(codec.TOK3_TYPES) == 13 for r in codec.TOK3_METHODS)
+    row9 = codec.TOK3_METHODS[4]
+    digits = row9[codec.TOK3_TYPES.index("DIGITS")]                  # {132, 201, 1, 192, 129, 193}
+    assert codec.tok3_method_list(digits, 4000) == [128, 201, 1, 192, 129, 193]      # 132 -> 128 (X32 cleared)
+    assert codec.tok3_method_list(digits, 4001) == [128, 1, 192, 129, 193]           # 201 has STRIPE: skipped
+    assert codec.tok3_method_list(codec.TOK3_METHODS[0][codec.TOK3_TYPES.index("DUP")], 7) == []   # {8}, len % 4
+    assert codec.ransxn1_order(150) == (150 << 8) + 9                                # fqzcomp5.c:2019
+
+
+def test_bench_extra_workloads_are_registered():
+    import bench
+    assert set(bench.EXTRA) == {"fastq_split", "fastq_join", "crc32"}
+    assert "illumina_qual_o0" in bench.WORKLOADS and bench.METRIC.startswith("rANS32x16")
