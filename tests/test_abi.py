@@ -93,3 +93,22 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "pyoracle" not in txt and "liboracle" not in txt and "oracle/" not in txt, f
+
+
+def test_header_is_valid_c_and_the_example_links(tmp_path):
+    """include/b200rans.h is a C header (the reference is C): the example in examples/ compiles as
+    strict C99 and links against the library; without a GPU it fails loudly instead of falling back."""
+    import subprocess
+    import torch
+    from fqzcomp5_b200 import build, codec
+    build.build()
+    exe = str(tmp_path / "block_pipeline")
+    libdir = os.path.dirname(codec.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "block_pipeline.c"), "-L" + libdir, "-lb200rans",
+                    "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "sample.fastq")], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and "identical to" in r.stdout, r.stdout + r.stderr
+    else:
+        assert r.returncode != 0 and "no CPU path" in r.stderr
