@@ -62,3 +62,34 @@ def test_join_inverts_split(fq_oracle):
     r = fq_oracle.split(text)
     assert r["consumed"] == len(text) and r["fixed_len"] == 100
     assert fq_oracle.join(r["name"], r["seq"], r["qual"], r["len"], 0) == text
+
+
+def test_oracle_matches_reference_on_random_texts(fq_oracle, fq_ref):
+    """Random record soups, cut anywhere, damaged in one byte, with NUL bytes (which load_seqs reads as
+    line ends -- the one point where the GPU path deliberately differs and reports a malformed block)."""
+    import numpy as np
+    rng = np.random.default_rng(77)
+    n_null = 0
+    for it in range(400):
+        recs = []
+        for i in range(int(rng.integers(0, 60))):
+            n = int(rng.integers(0, 120))
+            nm = bytes(rng.integers(33, 127, int(rng.integers(0, 30))).astype(np.uint8))
+            if recs and rng.random() < 0.2:
+                nm = recs[-1][0]
+            if rng.random() < 0.2:
+                nm += b"/2"
+            recs.append((nm, bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), n)),
+                         bytes((rng.integers(0, 60, n) + 33).astype(np.uint8))))
+        t = b"".join(b"@" + a + b"\n" + s + b"\n+\n" + q + b"\n" for a, s, q in recs)
+        r = rng.random()
+        if r < 0.4 and t:
+            t = t[:int(rng.integers(0, len(t) + 1))]
+        elif r < 0.7 and len(t) > 4:
+            b = bytearray(t)
+            b[int(rng.integers(0, len(b)))] = int(rng.choice([0, 10, 43, 64, 65]))
+            t = bytes(b)
+        a, b = fq_oracle.split(t), fq_ref.split(t)
+        assert a == b, (it, t[:80])
+        n_null += a is None
+    assert 0 < n_null < 400
