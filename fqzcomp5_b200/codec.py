@@ -35,6 +35,10 @@ EXPORTS = [
     "b200fq_split", "b200fq_join", "b200fq_split_dev", "b200fq_join_dev",
     "b200fq_split_scratch_bytes", "b200fq_join_scratch_bytes",
     "b200fqz_crc32", "b200fqz_crc32_dev", "b200fqz_assemble_block_dev",
+    "b200rans_compress_slots_bound", "b200rans_compress_batch_dev2", "b200rans_compress_trials_dev",
+    "b200rans_tok3_methods",
+    "b200fqz_block_bound", "b200fqz_encode_block", "b200fqz_decode_block",
+    "b200fqz_encode_blocks_multi", "b200fqz_decode_blocks_multi",
 ]
 
 _lib = None
@@ -98,6 +102,17 @@ def lib():
         L.b200fqz_crc32.argtypes = [u32, vp, C.c_uint64, pu32]
         L.b200fqz_crc32_dev.argtypes = [vp, vp, C.c_uint64, u32, vp]
         L.b200fqz_assemble_block_dev.argtypes = [vp, u32, i32, vp, vp, C.c_uint64, pu32]
+        L.b200rans_compress_slots_bound.argtypes = [i32, vp, vp]
+        L.b200rans_compress_slots_bound.restype = sz
+        L.b200rans_compress_batch_dev2.argtypes = [vp, i32, vp, vp, vp, vp, vp, sz, vp, vp, u32]
+        L.b200rans_compress_trials_dev.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, sz, u32, vp, vp, vp, vp]
+        L.b200rans_tok3_methods.argtypes = [i32, i32, u32, vp]
+        L.b200fqz_block_bound.argtypes = [u32]
+        L.b200fqz_block_bound.restype = sz
+        L.b200fqz_encode_block.argtypes = [vp, u32, vp, vp, sz, vp]
+        L.b200fqz_decode_block.argtypes = [vp, u32, i32, vp, sz, vp]
+        L.b200fqz_encode_blocks_multi.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
+        L.b200fqz_decode_blocks_multi.argtypes = [i32, i32, vp, vp, i32, vp, vp, vp]
         L.b200rans_launch_count.restype = C.c_uint64
         L.b200rans_version.restype = C.c_char_p
         L.b200rans_set_profiling.argtypes = [i32]
@@ -196,7 +211,7 @@ def _addr(a):
     return a.ctypes.data
 
 
-def compress_batch(buf, offsets, sizes, orders, out=None, ngpu=1, block_of=None):
+def compress_batch(buf, offsets, sizes, orders, out=None, ngpu=1, block_of=None, multi=False):
     """Compress n slices of one host array.
 
     buf: uint8 numpy array (pinned for full PCIe speed); offsets/sizes/orders: per stream.
@@ -213,7 +228,7 @@ def compress_batch(buf, offsets, sizes, orders, out=None, ngpu=1, block_of=None)
         out = np.empty(cap, np.uint8)
     out_off = np.zeros(n, np.uint64)
     out_size = np.zeros(n, np.uint32)
-    if ngpu == 1:
+    if ngpu == 1 and not multi:
         rc = L.b200rans_compress_batch(n, _addr(ptrs), _addr(sizes), _addr(orders), _addr(out), out.size,
                                        _addr(out_off), _addr(out_size))
     else:
@@ -342,7 +357,7 @@ def compress_methods(data, methods):
     return out, best.value, csize
 
 
-def uncompress_batch(comp, comp_off, comp_size, out, out_off, out_size, ngpu=1, block_of=None):
+def uncompress_batch(comp, comp_off, comp_size, out, out_off, out_size, ngpu=1, block_of=None, multi=False):
     """Decompress n streams held in one host array into slices of `out`.
 
     out_size[k] is the capacity (exact length for NOSZ streams).  Returns (sizes, status)."""
@@ -353,7 +368,7 @@ def uncompress_batch(comp, comp_off, comp_size, out, out_off, out_size, ngpu=1, 
     isz = np.ascontiguousarray(comp_size, np.uint32)
     osz = np.array(out_size, np.uint32)
     status = np.zeros(n, np.int32)
-    if ngpu == 1:
+    if ngpu == 1 and not multi:
         rc = L.b200rans_uncompress_batch(n, _addr(iptr), _addr(isz), _addr(optr), _addr(osz), _addr(status))
     else:
         bo = None if block_of is None else np.ascontiguousarray(block_of, np.int32)
@@ -394,6 +409,52 @@ def uncompress_batch_dev(stream, d_in_ptr, in_off, in_size, d_out_ptr, out_off, 
                                              d_out_ptr, _addr(out_off), _addr(out_size), d_out_size_ptr,
                                              d_status_ptr)
     _check(rc, "b200rans_uncompress_batch_dev")
+
+
+OUT_IN_SLOT = 1
+
+
+def compress_slots_bound(in_size, orders):
+    """d_out bytes b200rans_compress_batch_dev2 needs with OUT_IN_SLOT (one bound-sized slot per call)."""
+    in_size = np.ascontiguousarray(in_size, np.uint32)
+    orders = np.ascontiguousarray(orders, np.int32)
+    return int(lib().b200rans_compress_slots_bound(len(in_size), _addr(in_size), _addr(orders)))
+
+
+def compress_batch_dev2(stream, d_in_ptr, in_off, in_size, orders, d_out_ptr, out_cap, d_out_off_ptr,
+                        d_out_size_ptr, flags=0):
+    """As compress_batch_dev; flags=OUT_IN_SLOT leaves every stream in its own slot of d_out."""
+    in_off = np.ascontiguousarray(in_off, np.uint64)
+    in_size = np.ascontiguousarray(in_size, np.uint32)
+    orders = np.ascontiguousarray(orders, np.int32)
+    rc = lib().b200rans_compress_batch_dev2(stream, len(in_size), d_in_ptr, _addr(in_off), _addr(in_size),
+                                            _addr(orders), d_out_ptr, out_cap, d_out_off_ptr, d_out_size_ptr, flags)
+    _check(rc, "b200rans_compress_batch_dev2")
+
+
+def compress_trials_dev(stream, d_in_ptr, in_off, in_size, method_lists, d_out_ptr, out_cap, pack_align,
+                        d_out_off_ptr, d_out_size_ptr, d_best_ptr=None, d_csize_ptr=None):
+    """Ragged method trial with inputs and outputs in HBM (b200rans_compress_trials_dev)."""
+    in_off = np.ascontiguousarray(in_off, np.uint64)
+    in_size = np.ascontiguousarray(in_size, np.uint32)
+    n = len(in_size)
+    first = np.zeros(n + 1, np.uint32)
+    first[1:] = np.cumsum([len(m) for m in method_lists])
+    flat = np.ascontiguousarray([o for m in method_lists for o in m], np.int32)
+    rc = lib().b200rans_compress_trials_dev(stream, n, d_in_ptr, _addr(in_off), _addr(in_size), _addr(first),
+                                            _addr(flat), d_out_ptr, out_cap, pack_align, d_out_off_ptr,
+                                            d_out_size_ptr, d_best_ptr, d_csize_ptr)
+    _check(rc, "b200rans_compress_trials_dev")
+    return first
+
+
+def tok3_methods(level, token_type, in_len):
+    """b200rans_tok3_methods: the candidate list tok3's compress() walks (C-side tables)."""
+    out = np.zeros(8, np.int32)
+    n = lib().b200rans_tok3_methods(level, token_type, in_len, _addr(out))
+    if n < 0:
+        raise B200RansError("b200rans_tok3_methods: bad arguments")
+    return out[:n].tolist()
 
 
 def compress_bound_batch(in_size, orders):
@@ -495,3 +556,109 @@ def assemble_block_dev(stream, num_records, pieces, d_block_ptr, block_cap):
     _check(lib().b200fqz_assemble_block_dev(stream, num_records, len(pieces), C.addressof(arr), d_block_ptr,
                                             block_cap, C.byref(n)), "b200fqz_assemble_block_dev")
     return n.value
+
+
+# ---------------------------------------------------------------- one call per fqzcomp5 block (part 5)
+RANSXN1 = -1            # B200FQZ_RANSXN1: (fixed_len << 8) + 9, skipped for variable-length reads
+STRAT_SLICED = 0xB2
+MAX_METHODS = 16
+NAME_CODER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_ubyte), C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32,
+                         C.POINTER(C.c_void_p), C.POINTER(C.c_uint32))
+
+
+class BlockOpts(C.Structure):
+    """b200fqz_block_opts."""
+    _fields_ = [("slice_bytes", C.c_uint32), ("n_name_methods", C.c_int), ("n_seq_methods", C.c_int),
+                ("n_qual_methods", C.c_int), ("name_methods", C.c_int * MAX_METHODS),
+                ("seq_methods", C.c_int * MAX_METHODS), ("qual_methods", C.c_int * MAX_METHODS),
+                ("name_coder", NAME_CODER), ("name_user", C.c_void_p)]
+
+
+class BlockReport(C.Structure):
+    """b200fqz_block_report."""
+    _fields_ = [("status", C.c_int32), ("num_records", C.c_uint32), ("consumed", C.c_uint32),
+                ("fixed_len", C.c_int32), ("ulen", C.c_uint32 * 3), ("clen", C.c_uint32 * 3),
+                ("nslices", C.c_uint32 * 3), ("csize", (C.c_uint64 * MAX_METHODS) * 3),
+                ("wins", (C.c_uint32 * MAX_METHODS) * 3), ("block_len", C.c_uint32), ("crc", C.c_uint32)]
+
+
+# fqzcomp5 -3 (fqzcomp5.c:4893-4900), the rANS members of its seq / qual method sets; names: the codec half
+# of TLZP3 (order 5).  x32=True ORs RANS_ORDER_X32 into every method (SURVEY F2).
+def block_opts(slice_bytes=262144, seq=(0, 1, 129, 193), qual=(0, 1, 129, 193, RANSXN1), names=(5,), x32=False,
+               name_coder=None):
+    o = BlockOpts()
+    o.slice_bytes = slice_bytes
+    fix = lambda m: m if m == RANSXN1 or not x32 else (m | RANS_ORDER_X32)
+    for lst, arr, cnt in ((names, o.name_methods, "n_name_methods"), (seq, o.seq_methods, "n_seq_methods"),
+                          (qual, o.qual_methods, "n_qual_methods")):
+        for i, m in enumerate(lst):
+            arr[i] = fix(m)
+        setattr(o, cnt, len(lst))
+    if name_coder is not None:
+        o.name_coder = name_coder
+    return o
+
+
+def resolve_methods(lst, fixed_len, x32=False):
+    """The `order` values a method list stands for in a block whose reads are fixed_len long."""
+    out = []
+    for m in lst:
+        if m == RANSXN1:
+            if fixed_len <= 0:
+                continue
+            out.append((fixed_len << 8) + 9)
+        else:
+            out.append(m | (RANS_ORDER_X32 if x32 else 0))
+    return out
+
+
+def encode_block(text, opts, out=None):
+    """b200fqz_encode_block: FASTQ text (bytes or uint8 array) -> (block bytes view, BlockReport)."""
+    t = np.frombuffer(text, np.uint8) if isinstance(text, (bytes, bytearray)) else text
+    n = int(t.size)
+    cap = int(lib().b200fqz_block_bound(n))
+    if out is None:
+        out = np.empty(cap, np.uint8)
+    rep = BlockReport()
+    rc = lib().b200fqz_encode_block(_addr(t) if n else None, n, C.addressof(opts), _addr(out), out.size,
+                                    C.addressof(rep))
+    _check(rc, "b200fqz_encode_block")
+    return out[:rep.block_len], rep
+
+
+def decode_block(block, text_cap, plus_name=0, out=None):
+    """b200fqz_decode_block -> (text bytes view or None, BlockReport)."""
+    b = np.frombuffer(block, np.uint8) if isinstance(block, (bytes, bytearray)) else block
+    if out is None:
+        out = np.empty(text_cap, np.uint8)
+    rep = BlockReport()
+    rc = lib().b200fqz_decode_block(_addr(b), int(b.size), plus_name, _addr(out), out.size, C.addressof(rep))
+    _check(rc, "b200fqz_decode_block")
+    return (out[:rep.block_len] if rep.status == 0 else None), rep
+
+
+def encode_blocks_multi(ngpu, texts, opts, outs):
+    """texts / outs: lists of uint8 arrays (pinned for full PCIe rate).  Returns the list of BlockReport."""
+    nb = len(texts)
+    tp = np.array([_addr(t) for t in texts], np.uint64)
+    tn = np.array([t.size for t in texts], np.uint32)
+    bp = np.array([_addr(b) for b in outs], np.uint64)
+    bc = np.array([b.size for b in outs], np.uint64)
+    reps = (BlockReport * max(nb, 1))()
+    rc = lib().b200fqz_encode_blocks_multi(ngpu, nb, _addr(tp), _addr(tn), C.addressof(opts), _addr(bp), _addr(bc),
+                                           C.addressof(reps))
+    _check(rc, "b200fqz_encode_blocks_multi")
+    return [reps[i] for i in range(nb)]
+
+
+def decode_blocks_multi(ngpu, blocks, lens, outs, plus_name=0):
+    nb = len(blocks)
+    bp = np.array([_addr(b) for b in blocks], np.uint64)
+    bl = np.array(lens, np.uint32)
+    tp = np.array([_addr(t) for t in outs], np.uint64)
+    tc = np.array([t.size for t in outs], np.uint64)
+    reps = (BlockReport * max(nb, 1))()
+    rc = lib().b200fqz_decode_blocks_multi(ngpu, nb, _addr(bp), _addr(bl), plus_name, _addr(tp), _addr(tc),
+                                           C.addressof(reps))
+    _check(rc, "b200fqz_decode_blocks_multi")
+    return [reps[i] for i in range(nb)]

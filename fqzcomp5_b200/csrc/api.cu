@@ -12,167 +12,24 @@
 #include <mutex>
 #include <atomic>
 
-#include "../../include/b200rans.h"
-#include "kernels.h"
-#include "stripe.h"
+#include "runtime.h"
 #include "fastq.h"
 #include "crc32.h"
 
 using namespace b200;
+using namespace b200rt;
 
 #define API extern "C" __attribute__((visibility("default")))
 
-namespace {
-
-bool cuda_ok(cudaError_t e, const char *what) {
-    if (e == cudaSuccess) return true;
-    fprintf(stderr, "libb200rans: %s failed: %s\n", what, cudaGetErrorString(e));
-    return false;
-}
-#define CK(call) do { if (!cuda_ok((call), #call)) return B200RANS_ECUDA; } while (0)
-
-inline size_t al(size_t v, size_t a = 256) { return (v + a - 1) & ~(a - 1); }
-
-struct Arena {
-    uint8_t *p = nullptr;
-    size_t cap = 0;
-    bool pinned = false;
-    int ensure(size_t need) {
-        if (need <= cap) return 0;
-        size_t want = need + need / 4 + (1 << 20);
-        if (p) { if (pinned) cudaFreeHost(p); else cudaFree(p); p = nullptr; cap = 0; }
-        cudaError_t e = pinned ? cudaHostAlloc((void **)&p, want, cudaHostAllocDefault)
-                               : cudaMalloc((void **)&p, want);
-        if (e != cudaSuccess) {
-            fprintf(stderr, "libb200rans: %s of %zu bytes failed: %s\n",
-                    pinned ? "cudaHostAlloc" : "cudaMalloc", want, cudaGetErrorString(e));
-            p = nullptr;
-            return B200RANS_ENOMEM;
-        }
-        cap = want;
-        return 0;
-    }
-    void release() { if (p) { if (pinned) cudaFreeHost(p); else cudaFree(p); } p = nullptr; cap = 0; }
-};
-
-// bump sub-allocator over an arena laid out before allocation (two passes: size, place)
-struct Layout {
-    size_t off = 0;
-    size_t take(size_t bytes, size_t a = 256) { off = al(off, a); size_t o = off; off += bytes; return o; }
-};
-
-constexpr int NSTAGE = 4;
-constexpr int NPIPE = 6;                  // lanes: chunks in flight in the host-buffer API
-// a pipeline chunk is ~chunk_bytes() of uncompressed data but at least chunk_min_streams() streams
-// (a chunk of few streams is latency bound); see the knobs below
-constexpr int CHUNK_MIN_STREAMS_SLOW = 1536;  // PACK / RLE streams take several ms each whatever their number: a
-                                              // chunk should fill most of the GPU's stream slots
-constexpr int CHUNK_MAX_STREAMS = 16384;
-struct Stage { Arena h; cudaEvent_t ev = nullptr; bool busy = false; };
-
-// Tuning knobs of the host-buffer pipeline (environment overrides are for measurement only).
-inline int env_int(const char *name, int dflt, int lo, int hi) {
-    const char *e = getenv(name);
-    if (!e) return dflt;
-    int v = atoi(e);
-    return v < lo ? lo : v > hi ? hi : v;
-}
-// chunks submitted (copy in + kernels queued) ahead of the chunk whose results are being read back:
-// the host blocks on that chunk's kernels, and without work queued behind it the copy engines idle
-inline int pipe_depth() { static int v = env_int("B200RANS_PIPE_DEPTH", 2, 1, NPIPE - 1); return v; }
-// plain streams of at least this many bytes get their counts from hist_kernel (one CTA per stream)
-// instead of counting inside the coder warp
-inline uint32_t hist_min_bytes(bool o1) {
-    static uint32_t v0 = (uint32_t)env_int("B200RANS_HIST_MIN_O0", 4096, 0, 0x7fffffff);
-    static uint32_t v1 = (uint32_t)env_int("B200RANS_HIST_MIN_O1", 4096, 0, 0x7fffffff);
-    return o1 ? v1 : v0;
-}
-inline size_t chunk_bytes() { static size_t v = (size_t)env_int("B200RANS_CHUNK_MB", 48, 1, 1024) << 20; return v; }
-inline int chunk_min_streams() { static int v = env_int("B200RANS_CHUNK_STREAMS", 256, 1, 16384); return v; }
-
-// One pipeline lane: a stream plus the arenas a chunk of work needs.  Chunks of a
-// large host-buffer batch rotate over NPIPE lanes so that the H2D copy of one
-// chunk, the kernels of the previous and the D2H copy of the one before overlap.
-struct Lane {
-    cudaStream_t st = nullptr;
-    cudaStream_t aux[2] = {nullptr, nullptr};   // side streams: coder launches of different routes run side by side
-    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
-    Arena work;                 // device: jobs, slots, scratch, pool
-    Arena io;                   // device: staged inputs / outputs of the host-buffer API
-    Arena crc;                  // device: CRC-32 tables and tile values (kept apart from `work`, which an
-                                // encode still in flight on another stream may be using)
-    Arena hio;                  // pinned: results read back
-    Stage stage[NSTAGE];        // pinned: job descriptors in flight
-    int next_stage = 0;
-
-    int init() {
-        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        for (auto &a : aux) CK(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-        for (auto &j : join) CK(cudaEventCreateWithFlags(&j, cudaEventDisableTiming));
-        hio.pinned = true;
-        for (auto &s : stage) { s.h.pinned = true; CK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming)); }
-        return 0;
-    }
-    // pinned staging block for descriptors; waits until its previous use has been consumed
-    int get_stage(size_t bytes, Stage **out) {
-        Stage &s = stage[next_stage];
-        next_stage = (next_stage + 1) % NSTAGE;
-        if (s.busy) { CK(cudaEventSynchronize(s.ev)); s.busy = false; }
-        int r = s.h.ensure(bytes);
-        if (r) return r;
-        *out = &s;
-        return 0;
-    }
-    void destroy() {
-        if (st) cudaStreamSynchronize(st);
-        work.release(); io.release(); crc.release(); hio.release();
-        for (auto &s : stage) { s.h.release(); if (s.ev) cudaEventDestroy(s.ev); }
-        for (auto &a : aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); a = nullptr; }
-        if (fork) cudaEventDestroy(fork);
-        for (auto &j : join) if (j) cudaEventDestroy(j);
-        if (st) cudaStreamDestroy(st);
-        st = nullptr;
-    }
-};
-
-struct Ctx {
-    int dev = 0;
-    bool ok = false;
-    Lane lane[NPIPE];
-    uint64_t launches = 0;
-    bool prof = false;          // bracket the coder kernels with timing events (bench.py roofline)
-    cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};   // enc start/stop, dec start/stop
-    bool pe_valid[2] = {false, false};
-
-    int init(int device) {
-        int n = 0;
-        cudaError_t e = cudaGetDeviceCount(&n);
-        if (e != cudaSuccess || n == 0) {
-            fprintf(stderr, "libb200rans: no usable CUDA device (%s); this library has no CPU path\n",
-                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
-            return B200RANS_ENODEV;
-        }
-        if (device < 0 || device >= n) return B200RANS_EINVAL;
-        dev = device;
-        CK(cudaSetDevice(dev));
-        for (auto &l : lane) { int r = l.init(); if (r) return r; }
-        for (auto &e2 : pe) CK(cudaEventCreate(&e2));
-        ok = true;
-        return 0;
-    }
-    ~Ctx() {
-        if (!ok) return;
-        cudaSetDevice(dev);
-        for (auto &l : lane) l.destroy();
-        for (auto &e : pe) if (e) cudaEventDestroy(e);
-    }
-};
+namespace b200rt {
 
 thread_local Ctx *tls_ctx = nullptr;
 thread_local int tls_device = -1;
 struct CtxOwner { ~CtxOwner() { delete tls_ctx; tls_ctx = nullptr; } };
 thread_local CtxOwner tls_owner;
+
+void set_thread_device(int device) { tls_device = device; }
+std::atomic<uint64_t> g_worker_launches{0};
 
 Ctx *get_ctx(int *err) {
     (void)&tls_owner;
@@ -203,31 +60,36 @@ inline int effective_order(uint32_t in_size, int order) {
     return order;
 }
 
-// Method trial (compress_with_methods, fqzcomp5.c:1979-2119; tok3's compress(),
-// tokenise_name3.c:1268-1417): the n calls of an enc_core batch are groups of candidate
-// encodings of the same input, calls d_first[k] .. d_first[k+1]-1 belonging to input k.
-// Every candidate's size goes to d_csize, the first smallest of each group is kept and
-// d_out_off / d_out_size / d_best are per input.
-struct Trial {
-    uint32_t inputs;
-    const uint32_t *d_first;    // [inputs + 1]
-    uint32_t *d_csize;          // [n]
-    uint32_t *d_jobidx;         // [n] scratch
-    int32_t *d_best;            // [inputs]
-};
-
 // Build and run the encode of a batch whose inputs are already on the device.
-// On return (asynchronously on st): d_out holds the packed streams, d_out_off /
-// d_out_size / d_total describe them.
+// On return (asynchronously on st): d_out holds the streams, d_out_off / d_out_size (and d_total,
+// packed mode only) describe them.
+//   packed mode (inslot == false): streams are copied back to back into d_out, each starting on a
+//       multiple of pack_align; slots live in the lane's work arena.
+//   in-slot mode: every caller item's slot is carved out of d_out (rans_compress_bound_4x16 bytes,
+//       256-byte aligned -- the reference's "one bound-sized buffer per call") and the stream stays
+//       where the encoder built it; no scan, no gather.  out_cap >= enc_slots_bound().
+size_t enc_slots_bound(int n, const uint32_t *in_size, const int *order) {
+    size_t t = 0;
+    for (int k = 0; k < n; k++) {
+        size_t b = al(compress_bound(in_size[k], order[k]) + 16, 16);
+        if (effective_order(in_size[k], order[k]) & X_STRIPE) b += STRIPE_LIST_BYTES + 16;
+        t = al(t, 256) + b;
+    }
+    return al(t, 256) + 256;
+}
+
 int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, const uint64_t *in_off,
              const uint32_t *in_size, const int *order, const uint32_t *caps,
              uint8_t *d_out, size_t out_cap, uint64_t *d_out_off, uint32_t *d_out_size,
-             uint64_t *d_total, const Trial *trial = nullptr) {
+             uint64_t *d_total, const Trial *trial, uint32_t pack_align, bool inslot) {
     if (n <= 0) return 0;
+    if (pack_align == 0 || (pack_align & (pack_align - 1))) return B200RANS_EINVAL;
     // ---- pass 1: count jobs and size scratch
     std::vector<StripePlan> stripes;
     size_t njobs = 0;
-    Layout L;
+    Layout L;                   // the lane's work arena
+    Layout LO;                  // in-slot mode: the caller's d_out, from its first 256-byte aligned address
+    const size_t out_adj = (size_t)((256 - ((uintptr_t)d_out & 255)) & 255);
     std::vector<uint32_t> first(n);
     for (int k = 0; k < n; k++) {
         int eo = effective_order(in_size[k], order[k]);
@@ -241,17 +103,23 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
         } else njobs++;
     }
     std::vector<EncJob> jobs(njobs);
+    std::vector<uint8_t> in_out(njobs, 0);    // slot offset is relative to d_out (in-slot mode, caller items)
     size_t o_jobs = L.take(njobs * sizeof(EncJob));
     size_t o_ctr = L.take(256);
+    size_t o_par = L.take(stripes.size() * 4 + 4);
     uint32_t n_o0 = 0, n_o1 = 0, n_o1w = 0, n_model = 0;
     size_t pool_bytes = 0;
     // ---- pass 2: place slots / work buffers
-    auto place = [&](EncJob &J, const uint8_t *in, uint32_t isz, int ord, uint32_t cap, uint32_t item) {
+    auto place = [&](size_t j, const uint8_t *in, uint32_t isz, int ord, uint32_t cap, uint32_t item, bool parent) {
+        EncJob &J = jobs[j];
         memset(&J, 0, sizeof(J));
         J.in = in; J.in_size = isz; J.order = ord; J.cap = cap; J.item = item;
         uint32_t slot_cap = (uint32_t)al(compress_bound(isz, ord) + 16, 16);
         J.slot_cap = slot_cap;
-        J.slot = (uint8_t *)L.take(slot_cap, 256);
+        const size_t slot_bytes = (size_t)slot_cap + (parent ? STRIPE_LIST_BYTES + 16 : 0);
+        if (inslot && item != 0xffffffffu) { J.slot = (uint8_t *)LO.take(slot_bytes, 256); in_out[j] = 1; }
+        else J.slot = (uint8_t *)L.take(slot_bytes, 256);
+        if (parent) return;
         if (ord & (X_PACK | X_RLE)) J.work = (uint8_t *)L.take((size_t)isz * 4 + isz / 4 + 8192, 256);
         else if (isz >= hist_min_bytes((ord & 1) != 0)) {
             // big plain streams: counts come from hist_kernel (order-1: up to (isz+1)^2 or 256^2 pairs)
@@ -271,62 +139,67 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
         } else n_o0++;
     };
     size_t si = 0;
+    uint32_t max_stripe_in = 0;
     for (int k = 0; k < n; k++) {
         uint32_t j = first[k];
         uint32_t cap = caps ? caps[k] : compress_bound(in_size[k], order[k]);
         if (si < stripes.size() && stripes[si].item == k) {
             StripePlan &sp = stripes[si++];
             sp.o_transposed = L.take(in_size[k], 256);
-            place(jobs[j], d_in + in_off[k], in_size[k], order[k], cap, (uint32_t)k);
-            if (jobs[j].route == ROUTE_O1_WIDE) n_o1w--;
-            if (jobs[j].route) { n_o1--; pool_bytes -= 256 * 256 * 12 + 300 * 1024 + (jobs[j].model ? 0 : 2 * (size_t)in_size[k] + 2048); } else n_o0--;
-            if (jobs[j].model) { jobs[j].model = nullptr; n_model--; }
+            place(j, d_in + in_off[k], in_size[k], order[k], cap, (uint32_t)k, true);
             jobs[j].route = ROUTE_NONE;      // assembled by stripe_select, not coded
             jobs[j].stripe_n = sp.N;
-            for (uint32_t s = 0; s < sp.nsub; s++) {
-                const StripeSub &ss = sp.sub[s];
+            jobs[j].stripe_nmeth = sp.nmeth;
+            max_stripe_in = std::max(max_stripe_in, in_size[k]);
+            for (uint32_t s2 = 0; s2 < sp.nsub; s2++) {
+                const StripeSub &ss = sp.sub[s2];
                 // sub-streams get generous private slots; the capacity rule of the
                 // reference is re-applied at selection time (need_cap)
-                place(jobs[j + 1 + s], (const uint8_t *)(sp.o_transposed + ss.off), ss.len, ss.order,
-                      0x7ffffff0u, 0xffffffffu);
+                place(j + 1 + s2, (const uint8_t *)(sp.o_transposed + ss.off), ss.len, ss.order,
+                      0x7ffffff0u, 0xffffffffu, false);
             }
         } else {
-            place(jobs[j], d_in + in_off[k], in_size[k], order[k], cap, (uint32_t)k);
+            place(j, d_in + in_off[k], in_size[k], order[k], cap, (uint32_t)k, false);
         }
     }
+    if (inslot && out_adj + LO.off > out_cap) return B200RANS_ESPACE;
     // the reference's worst case is one table per stream; real tables are tiny.
     pool_bytes = std::min<size_t>(pool_bytes, (size_t)16 << 30);
     pool_bytes = std::max<size_t>(pool_bytes, (size_t)8 << 20);
     size_t o_pool = L.take(pool_bytes, 256);
-    size_t o_soff = L.take(njobs * 8), o_ssz = L.take(njobs * 4);
+    size_t o_soff = L.take(njobs * 8), o_ssz = L.take(njobs * 4), o_tot = L.take(8);
     int r = Ln.work.ensure(L.off + 256);
     if (r) return r;
     uint8_t *W = Ln.work.p;
     // relocate offsets into pointers
-    for (auto &J : jobs) {
-        J.slot = W + (size_t)J.slot;
+    for (size_t j = 0; j < njobs; j++) {
+        EncJob &J = jobs[j];
+        J.slot = (in_out[j] ? d_out + out_adj : W) + (size_t)J.slot;
         if (J.work) J.work = W + (size_t)J.work;
         if (J.model) J.model = (uint32_t *)(W + ((size_t)J.model - 1));
     }
     for (auto &sp : stripes)
-        for (uint32_t s = 0; s < sp.nsub; s++) {
-            EncJob &J = jobs[sp.first_job + 1 + s];
+        for (uint32_t s2 = 0; s2 < sp.nsub; s2++) {
+            EncJob &J = jobs[sp.first_job + 1 + s2];
             J.in = W + (size_t)J.in;
         }
     Stage *S;
-    size_t stage_bytes = njobs * sizeof(EncJob) + 256;
+    const size_t par_bytes = stripes.size() * 4;
+    size_t stage_bytes = njobs * sizeof(EncJob) + par_bytes + 256;
     if ((r = Ln.get_stage(stage_bytes, &S))) return r;
     memcpy(S->h.p, jobs.data(), njobs * sizeof(EncJob));
+    uint32_t *h_par = (uint32_t *)(S->h.p + njobs * sizeof(EncJob));
+    for (size_t i = 0; i < stripes.size(); i++) h_par[i] = stripes[i].first_job;
     EncJob *d_jobs = (EncJob *)(W + o_jobs);
+    uint32_t *d_par = (uint32_t *)(W + o_par);
     CK(cudaMemcpyAsync(d_jobs, S->h.p, njobs * sizeof(EncJob), cudaMemcpyHostToDevice, st));
+    if (par_bytes) CK(cudaMemcpyAsync(d_par, h_par, par_bytes, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(W + o_ctr, 0, 256, st));
     Pool pool{W + o_pool, pool_bytes, (unsigned long long *)(W + o_ctr)};
+    const uint32_t npar = (uint32_t)stripes.size();
 
-    // ---- STRIPE: transpose parents into their sub-stream inputs
-    for (auto &sp : stripes) {
-        CK(launch_stripe_split(d_in + in_off[sp.item], W + sp.o_transposed, sp.in_size, sp.N, st));
-        C.launches++;
-    }
+    // ---- STRIPE: transpose parents into their sub-stream inputs (one launch for all of them)
+    if (npar) { CK(launch_stripe_split_batch(d_jobs, d_par, npar, max_stripe_in, st)); C.launches++; }
     // ---- histograms of the plain streams at full occupancy
     if (n_model) { CK(launch_hist(d_jobs, (uint32_t)njobs, st)); C.launches++; }
     // ---- encode: order-0 streams on the lean kernel, the rest on the order-1 kernel
@@ -343,7 +216,7 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
             if (!have[i]) continue;
             cudaStream_t s2 = used == 0 ? st : Ln.aux[used - 1];
             if (used) CK(cudaStreamWaitEvent(s2, Ln.fork, 0));
-            CK(launch_enc(d_jobs, (uint32_t)njobs, routes[i], pool, s2));
+            CK(launch_enc(d_jobs, (uint32_t)njobs, routes[i], pool, s2, inslot));
             C.launches++;
             if (used) { CK(cudaEventRecord(Ln.join[used - 1], s2)); CK(cudaStreamWaitEvent(st, Ln.join[used - 1], 0)); }
             used++;
@@ -351,21 +224,25 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
     }
     if (C.prof) { CK(cudaEventRecord(C.pe[1], st)); C.pe_valid[0] = true; }
     CK(cudaEventRecord(S->ev, st)); S->busy = true;
-    // ---- STRIPE: choose the smallest method per sub-stream and assemble the parent
-    for (auto &sp : stripes) {
-        CK(launch_stripe_select(d_jobs, sp.first_job, sp.N, sp.nmeth, st));
-        C.launches++;
-    }
+    // ---- STRIPE: choose the smallest method per sub-stream and write the parents' headers
+    if (npar) { CK(launch_stripe_select(d_jobs, d_par, npar, st)); C.launches++; }
     // ---- method trial: keep the first smallest candidate of each input
     if (trial) {
         CK(launch_trial_select(d_jobs, (uint32_t)njobs, trial->inputs, trial->d_first, trial->d_csize,
                                trial->d_jobidx, trial->d_best, st));
         C.launches += 2;
     }
-    // ---- pack the finished streams of the caller's items (sub-streams carry no item)
     uint64_t *d_off = d_out_off ? d_out_off : (uint64_t *)(W + o_soff);
     uint32_t *d_sz = d_out_size ? d_out_size : (uint32_t *)(W + o_ssz);
-    CK(launch_pack(d_jobs, (uint32_t)njobs, d_off, d_sz, d_total, d_out, out_cap, st));
+    if (inslot) {
+        // ---- streams stay in their slots; STRIPE parents collect their sub-streams into theirs
+        CK(launch_inslot_results(d_jobs, (uint32_t)njobs, d_par, npar, d_out, d_off, d_sz, st));
+        C.launches += npar ? 2 : 1;
+        return 0;
+    }
+    // ---- pack the finished streams of the caller's items (sub-streams carry no item)
+    CK(launch_pack(d_jobs, (uint32_t)njobs, d_off, d_sz, d_total ? d_total : (uint64_t *)(W + o_tot), d_out, out_cap,
+                   pack_align, st));
     C.launches += 2;
     return 0;
 }
@@ -387,9 +264,12 @@ int dec_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
         memset(&J, 0, sizeof(J));
         J.in = d_in + in_off[k]; J.in_size = in_size[k];
         J.out = d_out + out_off[k]; J.out_cap = out_cap[k];
-        int f = flags ? flags[k] : 0xff;                 // unknown: assume everything
+        // flag byte unknown: transform scratch is provided and the stream goes to the general
+        // (order-1) kernel, which also decodes order-0 and raw streams
+        const bool known = flags != nullptr;
+        const int f = known ? flags[k] : (X_PACK | X_RLE | 1);
         if (f & (X_PACK | X_RLE)) J.tmp = (uint8_t *)L.take((size_t)out_cap[k] * 2 + 4096, 256);
-        if ((f & 1) && !(f & X_CAT)) {
+        if (!known || ((f & 1) && !(f & X_CAT))) {
             J.route = 1; n_o1++;
             pool_bytes += 257 * 257 * 3 + 257 * 256 * 4 + 256 * 2048 + 16 * 1024;   // table text + DecO1Big
         } else n_o0++;
@@ -484,8 +364,8 @@ struct EncChunk {
 // call failed).
 int compress_batch_impl(int n, const unsigned char *const *in, const unsigned int *in_size, const int *order,
                         const uint32_t *caps, unsigned char *out, size_t out_cap, size_t *out_off,
-                        unsigned int *out_size, const uint32_t *mfirst = nullptr, const int *methods = nullptr,
-                        int *best = nullptr, unsigned int *csize = nullptr) {
+                        unsigned int *out_size, const uint32_t *mfirst, const int *methods,
+                        int *best, unsigned int *csize) {
     const bool M = mfirst != nullptr;
     int err = 0;
     Ctx *C = get_ctx(&err);
@@ -788,7 +668,7 @@ int uncompress_batch_impl(int n, const unsigned char *const *in, const unsigned 
     return rc;
 }
 
-}  // namespace
+}  // namespace b200rt
 
 // ============================================================ C ABI: part 1
 API unsigned int rans_compress_bound_4x16(unsigned int size, int order) {
@@ -810,15 +690,17 @@ API unsigned char *rans_compress_to_4x16(unsigned char *in, unsigned int in_size
     unsigned int isz[1] = {in_size}, osz[1] = {0};
     int ord[1] = {order};
     size_t ooff[1] = {0};
-    // stage through a bound-sized arena, then hand back exactly the stream
-    std::vector<unsigned char> arena;
-    size_t acap = (size_t)std::max(cap, compress_bound(in_size, order)) + 64;
-    unsigned char *tmp = out;
-    bool direct = acap <= cap;
-    if (!direct) { arena.resize(acap); tmp = arena.data(); }
-    int r = compress_batch_impl(1, ins, isz, ord, &cap, tmp, direct ? cap : acap, ooff, osz);
+    // the stream leaves the device into a reusable pinned arena of bound size; exactly its bytes
+    // are then handed to the caller (whose buffer may be smaller than the bound)
+    int err = 0;
+    Ctx *C = get_ctx(&err);
+    if (!C) { free(out_free); *out_size = 0; return NULL; }
+    const size_t acap = (size_t)std::max(cap, compress_bound(in_size, order)) + 64;
+    if (C->single.ensure(acap)) { free(out_free); *out_size = 0; return NULL; }
+    unsigned char *tmp = C->single.p;
+    int r = compress_batch_impl(1, ins, isz, ord, &cap, tmp, acap, ooff, osz);
     if (r || osz[0] == 0 || osz[0] > cap) { free(out_free); *out_size = 0; return NULL; }
-    if (tmp != out || ooff[0]) memmove(out, tmp + ooff[0], osz[0]);
+    memcpy(out, tmp + ooff[0], osz[0]);
     *out_size = osz[0];
     return out;
 }
@@ -956,13 +838,10 @@ API int b200rans_compress_batch_dev(void *stream, int n, const unsigned char *d_
     Ctx *C = get_ctx(&err);
     if (!C) return err;
     if (n < 0 || (n && (!d_in || !in_off || !in_size || !order || !d_out))) return B200RANS_EINVAL;
-    Lane &Ln = C->lane[0];
+    Lane &Ln = C->dlane;
     cudaStream_t st = stream ? (cudaStream_t)stream : Ln.st;
-    // the grand total lives at the head of the lane's io arena for this call
-    int r = Ln.io.ensure(256);
-    if (r) return r;
     return enc_core(*C, Ln, st, n, d_in, in_off, in_size, order, nullptr, d_out, out_cap, d_out_off, d_out_size,
-                    (uint64_t *)Ln.io.p);
+                    nullptr);
 }
 
 API int b200rans_uncompress_batch_dev(void *stream, int n, const unsigned char *d_in, const uint64_t *in_off,
@@ -975,7 +854,7 @@ API int b200rans_uncompress_batch_dev(void *stream, int n, const unsigned char *
     if (!C) return err;
     if (n < 0 || (n && (!d_in || !in_off || !in_size || !d_out || !out_off || !out_size || !d_out_size || !d_status)))
         return B200RANS_EINVAL;
-    Lane &Ln = C->lane[0];
+    Lane &Ln = C->dlane;
     cudaStream_t st = stream ? (cudaStream_t)stream : Ln.st;
     return dec_core(*C, Ln, st, n, d_in, in_off, in_size, flags, d_out, out_off, out_size, d_out_size, d_status);
 }
@@ -1004,7 +883,7 @@ API int b200fq_split_dev(void *stream, const unsigned char *d_text, uint32_t n, 
     int l = 0;
     CK(fq_split_launch(d_text, n, d_name, d_seq, d_qual, name_cap, seq_cap, d_len, d_flag, d_name_off, d_seq_off,
                        max_records, (uint8_t *)d_scratch, (FqInfo *)d_info,
-                       stream ? (cudaStream_t)stream : C->lane[0].st, &l));
+                       stream ? (cudaStream_t)stream : C->dlane.st, &l));
     C->launches += l;
     return 0;
 }
@@ -1021,7 +900,7 @@ API int b200fq_join_dev(void *stream, const unsigned char *d_name, uint32_t name
         return B200RANS_EINVAL;
     int l = 0;
     CK(fq_join_launch(d_name, name_len, d_seq, d_qual, d_len, num_records, plus_name, d_text, text_cap,
-                      (uint8_t *)d_scratch, (FqInfo *)d_info, stream ? (cudaStream_t)stream : C->lane[0].st, &l));
+                      (uint8_t *)d_scratch, (FqInfo *)d_info, stream ? (cudaStream_t)stream : C->dlane.st, &l));
     C->launches += l;
     return 0;
 }
@@ -1114,7 +993,7 @@ API int b200fqz_crc32_dev(void *stream, const unsigned char *d_buf, uint64_t n, 
     Ctx *C = get_ctx(&err);
     if (!C) return err;
     if ((n && !d_buf) || !d_crc) return B200RANS_EINVAL;
-    Lane &Ln = C->lane[0];
+    Lane &Ln = C->dlane;
     cudaStream_t st = stream ? (cudaStream_t)stream : Ln.st;
     int r = Ln.crc.ensure(crc32_scratch_bytes(n) + 256);
     if (r) return r;
@@ -1153,7 +1032,7 @@ API int b200fqz_assemble_block_dev(void *stream, uint32_t num_records, int n_pie
         total += pieces[i].len;
     }
     if (total > block_cap || total > 0xffffffffull) return B200RANS_ESPACE;
-    Lane &Ln = C->lane[0];
+    Lane &Ln = C->dlane;
     cudaStream_t st = stream ? (cudaStream_t)stream : Ln.st;
     int r = Ln.crc.ensure(crc32_scratch_bytes(total) + 256);
     if (r) return r;
@@ -1178,7 +1057,9 @@ API int b200fqz_assemble_block_dev(void *stream, uint32_t num_records, int n_pie
     return 0;
 }
 
-API uint64_t b200rans_launch_count(void) { return tls_ctx ? tls_ctx->launches : 0; }
+API uint64_t b200rans_launch_count(void) {
+    return (tls_ctx ? tls_ctx->launches : 0) + g_worker_launches.load(std::memory_order_relaxed);
+}
 
 API int b200rans_set_profiling(int on) {
     int e = 0;
@@ -1196,77 +1077,3 @@ API float b200rans_last_kernel_ms(int which) {
     return ms;
 }
 API const char *b200rans_version(void) { return "b200rans 0.1 (sm_100a)"; }
-
-// ------------------------------------------------------------- multi-GPU
-// Independent blocks, dealt round-robin over devices; one worker thread (and
-// therefore one context and stream) per device; results gathered in call order.
-namespace {
-template <typename F> int run_on_devices(int ngpu, F &&fn) {
-    int have = b200rans_device_count();
-    if (have <= 0) { fprintf(stderr, "libb200rans: no CUDA device; there is no CPU path\n"); return B200RANS_ENODEV; }
-    if (ngpu <= 0 || ngpu > have) return B200RANS_EINVAL;
-    std::vector<int> rc(ngpu, 0);
-    std::vector<std::thread> th;
-    for (int g = 0; g < ngpu; g++)
-        th.emplace_back([&, g] { tls_device = g; rc[g] = fn(g); });
-    for (auto &t : th) t.join();
-    for (int g = 0; g < ngpu; g++) if (rc[g]) return rc[g];
-    return 0;
-}
-}  // namespace
-
-API int b200rans_compress_batch_multi(int ngpu, int n, const unsigned char *const *in,
-                                      const unsigned int *in_size, const int *order, const int *block_of,
-                                      unsigned char *out, size_t out_cap, size_t *out_off,
-                                      unsigned int *out_size) {
-    if (n < 0 || (n && (!in || !in_size || !order || !out || !out_off || !out_size))) return B200RANS_EINVAL;
-    if (ngpu == 1) return b200rans_compress_batch(n, in, in_size, order, out, out_cap, out_off, out_size);
-    // every device gets a private slice of the arena sized by its streams' bounds
-    std::vector<std::vector<int>> idx(ngpu > 0 ? ngpu : 1);
-    if (ngpu <= 0) return B200RANS_EINVAL;
-    for (int k = 0; k < n; k++) idx[(block_of ? block_of[k] : k) % ngpu].push_back(k);
-    std::vector<size_t> base(ngpu + 1, 0);
-    for (int g = 0; g < ngpu; g++) {
-        size_t t = 0;
-        for (int k : idx[g]) t += al(compress_bound(in_size[k], order[k]), 16) + 16;
-        base[g + 1] = base[g] + al(t + 256, 256);
-    }
-    if (base[ngpu] > out_cap) return B200RANS_ESPACE;
-    return run_on_devices(ngpu, [&](int g) {
-        int m = (int)idx[g].size();
-        if (!m) return 0;
-        std::vector<const unsigned char *> i2(m);
-        std::vector<unsigned int> s2(m), z2(m);
-        std::vector<int> o2(m);
-        std::vector<size_t> f2(m);
-        for (int j = 0; j < m; j++) { int k = idx[g][j]; i2[j] = in[k]; s2[j] = in_size[k]; o2[j] = order[k]; }
-        int r = compress_batch_impl(m, i2.data(), s2.data(), o2.data(), nullptr, out + base[g],
-                                    base[g + 1] - base[g], f2.data(), z2.data());
-        if (r) return r;
-        for (int j = 0; j < m; j++) { int k = idx[g][j]; out_off[k] = base[g] + f2[j]; out_size[k] = z2[j]; }
-        return 0;
-    });
-}
-
-API int b200rans_uncompress_batch_multi(int ngpu, int n, const unsigned char *const *in,
-                                        const unsigned int *in_size, const int *block_of,
-                                        unsigned char *const *out, unsigned int *out_size, int *status) {
-    if (n < 0 || (n && (!in || !in_size || !out || !out_size))) return B200RANS_EINVAL;
-    if (ngpu == 1) return b200rans_uncompress_batch(n, in, in_size, out, out_size, status);
-    if (ngpu <= 0) return B200RANS_EINVAL;
-    std::vector<std::vector<int>> idx(ngpu);
-    for (int k = 0; k < n; k++) idx[(block_of ? block_of[k] : k) % ngpu].push_back(k);
-    return run_on_devices(ngpu, [&](int g) {
-        int m = (int)idx[g].size();
-        if (!m) return 0;
-        std::vector<const unsigned char *> i2(m);
-        std::vector<unsigned char *> o2(m);
-        std::vector<unsigned int> s2(m), z2(m);
-        std::vector<int> st2(m);
-        for (int j = 0; j < m; j++) { int k = idx[g][j]; i2[j] = in[k]; s2[j] = in_size[k]; o2[j] = out[k]; z2[j] = out_size[k]; }
-        int r = uncompress_batch_impl(m, i2.data(), s2.data(), o2.data(), z2.data(), st2.data());
-        if (r) return r;
-        for (int j = 0; j < m; j++) { int k = idx[g][j]; out_size[k] = z2[j]; if (status) status[k] = st2[j]; }
-        return 0;
-    });
-}

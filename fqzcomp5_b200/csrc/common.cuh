@@ -34,9 +34,11 @@ struct EncJob {
     uint8_t *work;          // scratch for transforms: 4.25 * in_size + 8192 bytes
     uint32_t item;          // index into the caller's arrays; 0xffffffff for STRIPE sub-streams
     uint32_t stripe_n;      // >0: STRIPE parent record; its tail is the chosen sub-streams,
-                            //     whose job indices sit at (uint32_t*)(slot + STRIPE_LIST_OFF)
+                            //     whose job indices sit at (uint32_t*)(slot + slot_cap) (the host
+                            //     allocates STRIPE_LIST_BYTES behind the slot of a parent)
     uint32_t route;         // ROUTE_*: which launch codes this stream
-    uint32_t pad_;
+    uint32_t stripe_nmeth;  // STRIPE parent: candidate methods per stripe; sub-stream (i, j) is the
+                            //     job at parent + 1 + i * stripe_nmeth + j
     uint32_t *model;        // counts precomputed by hist_kernel, or null (the coder counts itself):
                             //   [256] order-0 counts, [MODEL_HDR_WORDS..] order-1 pair counts in rank space
     uint64_t pad2_;
@@ -48,7 +50,7 @@ enum : uint32_t {
     ROUTE_O1_WIDE = 3,      // order-1 kernel with more shared memory per stream (PACK / RLE in front)
 };
 constexpr uint32_t MODEL_HDR_WORDS = 260;   // 256 counts, nsym, 3 pad
-constexpr uint32_t STRIPE_LIST_OFF = 2048;   // header is < 7 + 5*255 bytes
+constexpr uint32_t STRIPE_LIST_BYTES = 1024;  // 255 job indices behind a STRIPE parent's slot
 
 struct DecJob {
     const uint8_t *in;      // compressed stream (device)
@@ -170,6 +172,27 @@ __device__ inline void warp_copy(uint8_t *dst, const uint8_t *src, uint32_t n, i
     }
     uint32_t done = nv << 4;
     for (uint32_t i = done + lane; i < n; i += 32) dst[i] = src[i];
+}
+
+// Move n bytes UP to dst > src where the two ranges may overlap (memmove semantics): blocks of
+// 128 bytes from the highest down; a block is read completely before it is written, and writing
+// it can only touch source bytes of blocks already moved.
+__device__ inline void warp_move_up(uint8_t *dst, const uint8_t *src, uint32_t n, int lane) {
+    if (n == 0 || dst == src) return;
+    if (dst + 0 >= src + n) { warp_copy(dst, src, n, lane); return; }      // disjoint
+    uint32_t done = 0;
+    while (done < n) {
+        const uint32_t blk = n - done < 128 ? n - done : 128;
+        const uint32_t base = n - done - blk;
+        uint32_t v[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const uint32_t i = lane + 32 * q; v[q] = i < blk ? src[base + i] : 0; }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const uint32_t i = lane + 32 * q; if (i < blk) dst[base + i] = (uint8_t)v[q]; }
+        __syncwarp();
+        done += blk;
+    }
 }
 
 // cp.async 16 bytes, bytes beyond src_bytes are zero-filled and not read

@@ -27,8 +27,11 @@ struct CapCheck {
     }
 };
 
+// inslot: leave the finished stream contiguous inside its slot (head moved up against the payload,
+// as the reference's memmove at rANS_static32x16pr.c:249-251 does the other way round) and report it
+// as tail / tail_len with head_len 0, so that no packing pass is needed.
 template <bool O1>
-__device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const Pool &pool, int lane) {
+__device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const Pool &pool, int lane, bool inslot) {
     int order = J.order;
     const uint8_t *in = J.in;
     uint32_t in_size = J.in_size;
@@ -169,6 +172,18 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
         }
     }
     if (!cc.ok && status == ST_OK) status = ST_FAIL;
+    if (inslot && status == ST_OK) {
+        __syncwarp();
+        if (tail >= out && tail <= out + J.slot_cap) {          // coded payload at the slot's end
+            uint8_t *start = const_cast<uint8_t *>(tail) - head_len;
+            warp_move_up(start, out, head_len, lane);
+            tail = start;
+        } else {                                                // stored raw: the bytes are still the input's
+            warp_copy(out + head_len, tail, tail_len, lane);
+            tail = out;
+        }
+        tail_len += head_len; head_len = 0;
+    }
     if (lane == 0) {
         J.tail = tail; J.head_len = head_len; J.tail_len = tail_len;
         J.status = status; J.need_cap = cc.need;
@@ -178,12 +193,12 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
 
 template <bool O1>
 __global__ void __launch_bounds__((O1 ? ENC_WARPS_O1 : ENC_WARPS) * 32, O1 ? 11 : 7)   // O1: 22 warps per SM (<= 92 registers); O0: 28 warps (<= 72) so that the 3815 streams of a 1 GB block are one wave (unbounded the compiler takes 179 registers and residency collapses)
-enc_kernel(EncJob *jobs, uint32_t njobs, uint32_t warp_smem, Pool pool, uint32_t route) {
+enc_kernel(EncJob *jobs, uint32_t njobs, uint32_t warp_smem, Pool pool, uint32_t route, uint32_t inslot) {
     extern __shared__ __align__(16) uint8_t smem_all[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t j = blockIdx.x * (O1 ? ENC_WARPS_O1 : ENC_WARPS) + wid;
     if (j >= njobs || jobs[j].route != route) return;   // another launch's stream, or a STRIPE parent
-    enc_stream<O1>(jobs[j], smem_all + (size_t)wid * warp_smem, warp_smem, pool, lane);
+    enc_stream<O1>(jobs[j], smem_all + (size_t)wid * warp_smem, warp_smem, pool, lane, inslot != 0);
 }
 
 // ------------------------------------------------------------------------
@@ -318,7 +333,8 @@ dec_kernel(DecJob *jobs, uint32_t njobs, uint32_t warp_smem, Pool pool) {
 // per stream copies head and tail to their final place.
 // ------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
-scan_kernel(const EncJob *jobs, uint32_t njobs, uint64_t *out_off, uint32_t *out_size, uint64_t *total) {
+scan_kernel(const EncJob *jobs, uint32_t njobs, uint64_t *out_off, uint32_t *out_size, uint64_t *total,
+            uint32_t align) {
     __shared__ uint64_t wsum[32];
     __shared__ uint64_t carry;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -329,7 +345,7 @@ scan_kernel(const EncJob *jobs, uint32_t njobs, uint64_t *out_off, uint32_t *out
         uint32_t sz = 0;
         const bool item = k < njobs && jobs[k].item != 0xffffffffu;
         if (item && jobs[k].status == ST_OK) sz = jobs[k].head_len + jobs[k].tail_len;
-        uint64_t v = (sz + 15u) & ~15ull;                  // streams start 16-byte aligned
+        uint64_t v = ((uint64_t)sz + align - 1) & ~(uint64_t)(align - 1);   // streams start `align`-byte aligned (a power of two)
         uint64_t x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -372,7 +388,7 @@ gather_kernel(const EncJob *jobs, uint32_t njobs, const uint64_t *out_off, uint3
     if (wid == 0) warp_copy(dst, J.slot, hl, lane);
     if (J.stripe_n) {
         // STRIPE parent: the tail is the chosen sub-streams, back to back
-        const uint32_t *list = (const uint32_t *)(J.slot + STRIPE_LIST_OFF);
+        const uint32_t *list = (const uint32_t *)(J.slot + J.slot_cap);
         uint64_t o = hl;
         for (uint32_t i = 0; i < J.stripe_n; i++) {
             const EncJob &S = jobs[list[i]];
@@ -392,6 +408,51 @@ gather_kernel(const EncJob *jobs, uint32_t njobs, const uint64_t *out_off, uint3
     }
 }
 
+
+// In-slot output: a STRIPE parent's chosen sub-streams are appended to its header inside its own
+// slot (one CTA per parent), every other stream already sits contiguously in its slot.
+__global__ void __launch_bounds__(256)
+assemble_parents_kernel(EncJob *jobs, const uint32_t *parents, uint32_t nparents) {
+    if (blockIdx.x >= nparents) return;
+    EncJob &J = jobs[parents[blockIdx.x]];
+    if (J.status != ST_OK || !J.stripe_n) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint32_t hl = J.head_len, tl = J.tail_len, N = J.stripe_n;
+    const uint32_t *list = (const uint32_t *)(J.slot + J.slot_cap);
+    __syncthreads();
+    if ((uint64_t)hl + tl > J.slot_cap) { if (threadIdx.x == 0) J.status = ST_FAIL; return; }
+    uint64_t o = hl;
+    for (uint32_t i = 0; i < N; i++) {
+        const EncJob &S = jobs[list[i]];
+        if (wid == (int)(i % nw)) {
+            warp_copy(J.slot + o, S.slot, S.head_len, lane);
+            warp_copy(J.slot + o + S.head_len, S.tail, S.tail_len, lane);
+        }
+        o += S.head_len + S.tail_len;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { J.tail = J.slot; J.tail_len = hl + tl; J.head_len = 0; }
+}
+
+// where each caller item's stream was left (in-slot output): offset from `base`, size (0 = failed)
+__global__ void inslot_results_kernel(const EncJob *jobs, uint32_t njobs, const uint8_t *base, uint64_t *out_off,
+                                      uint32_t *out_size) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= njobs) return;
+    const EncJob &J = jobs[j];
+    if (J.item == 0xffffffffu) return;
+    const bool ok = J.status == ST_OK;
+    out_off[J.item] = ok ? (uint64_t)(J.tail - base) : 0;
+    out_size[J.item] = ok ? J.head_len + J.tail_len : 0;
+}
+
+cudaError_t launch_inslot_results(EncJob *d_jobs, uint32_t njobs, const uint32_t *d_parents, uint32_t nparents,
+                                  const uint8_t *base, uint64_t *d_off, uint32_t *d_size, cudaStream_t st) {
+    if (!njobs) return cudaSuccess;
+    if (nparents) assemble_parents_kernel<<<nparents, 256, 0, st>>>(d_jobs, d_parents, nparents);
+    inslot_results_kernel<<<(njobs + 255) / 256, 256, 0, st>>>(d_jobs, njobs, base, d_off, d_size);
+    return cudaGetLastError();
+}
 
 // ------------------------------------------------------------------------
 // Histograms at full occupancy: one CTA of 8 warps per stream counts its bytes
@@ -524,7 +585,7 @@ static cudaError_t ensure_rcp_table(cudaStream_t st) {
     return cudaSuccess;
 }
 
-cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, uint32_t route, Pool pool, cudaStream_t st) {
+cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, uint32_t route, Pool pool, cudaStream_t st, bool inslot) {
     if (!n) return cudaSuccess;
     const bool o1 = route != ROUTE_O0;
     if (o1) { cudaError_t e = ensure_rcp_table(st); if (e != cudaSuccess) return e; }
@@ -538,10 +599,10 @@ cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, uint32_t route, Pool pool, cu
     size_t sm = (size_t)ws * (o1 ? ENC_WARPS_O1 : ENC_WARPS);
     if (o1) {
         cudaFuncSetAttribute(enc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        enc_kernel<true><<<cdiv(n, ENC_WARPS_O1), ENC_WARPS_O1 * 32, sm, st>>>(d_jobs, n, ws, pool, route);
+        enc_kernel<true><<<cdiv(n, ENC_WARPS_O1), ENC_WARPS_O1 * 32, sm, st>>>(d_jobs, n, ws, pool, route, inslot ? 1u : 0u);
     } else {
         cudaFuncSetAttribute(enc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        enc_kernel<false><<<cdiv(n, ENC_WARPS), ENC_WARPS * 32, sm, st>>>(d_jobs, n, ws, pool, route);
+        enc_kernel<false><<<cdiv(n, ENC_WARPS), ENC_WARPS * 32, sm, st>>>(d_jobs, n, ws, pool, route, inslot ? 1u : 0u);
     }
     return cudaGetLastError();
 }
@@ -613,9 +674,9 @@ cudaError_t launch_trial_select(EncJob *d_jobs, uint32_t njobs, uint32_t ninputs
 }
 
 cudaError_t launch_pack(const EncJob *d_jobs, uint32_t n, uint64_t *d_off, uint32_t *d_size,
-                        uint64_t *d_total, uint8_t *d_out, uint64_t out_cap, cudaStream_t st) {
+                        uint64_t *d_total, uint8_t *d_out, uint64_t out_cap, uint32_t align, cudaStream_t st) {
     if (!n) return cudaSuccess;
-    scan_kernel<<<1, 1024, 0, st>>>(d_jobs, n, d_off, d_size, d_total);
+    scan_kernel<<<1, 1024, 0, st>>>(d_jobs, n, d_off, d_size, d_total, align);
     gather_kernel<<<n, 256, 0, st>>>(d_jobs, n, d_off, d_size, d_out, out_cap);
     return cudaGetLastError();
 }

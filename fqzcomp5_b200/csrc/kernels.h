@@ -20,12 +20,15 @@ constexpr uint32_t DEC_SMEM_O0 = 8192;     // DecO0Smem, 8 KiB aligned
 constexpr uint32_t DEC_SMEM_O1 = 8192;     // DecO1Smem header + 16-bit cumulative rows + 64-bucket index for <= 41 symbols (26 warps per SM: measured 1.35x over 15 KiB / 256 buckets)
 
 cudaError_t launch_hist(EncJob *d_jobs, uint32_t n, cudaStream_t st);
-cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, uint32_t route, Pool pool, cudaStream_t st);
+cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, uint32_t route, Pool pool, cudaStream_t st, bool inslot = false);
 cudaError_t launch_dec(DecJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStream_t st);
 // method trial: items first[k]..first[k+1]-1 are the candidates of input k -> sizes of all, first smallest kept
 cudaError_t launch_trial_select(EncJob *d_jobs, uint32_t njobs, uint32_t ninputs, const uint32_t *d_first,
                                 uint32_t *d_csize, uint32_t *d_jobidx, int32_t *d_best, cudaStream_t st);
 cudaError_t launch_pack(const EncJob *d_jobs, uint32_t n, uint64_t *d_off, uint32_t *d_size,
-                        uint64_t *d_total, uint8_t *d_out, uint64_t out_cap, cudaStream_t st);
+                        uint64_t *d_total, uint8_t *d_out, uint64_t out_cap, uint32_t align, cudaStream_t st);
+// in-slot output: STRIPE parents are assembled inside their own slots, then every item's place is reported
+cudaError_t launch_inslot_results(EncJob *d_jobs, uint32_t njobs, const uint32_t *d_parents, uint32_t nparents,
+                                  const uint8_t *base, uint64_t *d_off, uint32_t *d_size, cudaStream_t st);
 
 }  // namespace b200

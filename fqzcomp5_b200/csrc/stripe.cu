@@ -17,6 +17,19 @@ __global__ void stripe_split_kernel(const uint8_t *in, uint8_t *tr, uint32_t n, 
         tr[part_start(i % N, n, N) + i / N] = in[i];
 }
 
+// All STRIPE parents of a batch in one launch: blockIdx.y walks the parents, the transposed copy of
+// parent p is the input of its first sub-stream (the parts are stored back to back from there).
+__global__ void stripe_split_batch_kernel(const EncJob *jobs, const uint32_t *parents, uint32_t nparents) {
+    for (uint32_t p = blockIdx.y; p < nparents; p += gridDim.y) {
+        const EncJob &P = jobs[parents[p]];
+        const uint32_t n = P.in_size, N = P.stripe_n;
+        const uint8_t *in = P.in;
+        uint8_t *tr = const_cast<uint8_t *>(jobs[parents[p] + 1].in);
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+            tr[part_start(i % N, n, N) + i / N] = in[i];
+    }
+}
+
 __global__ void stripe_join_kernel(const uint8_t *parts, uint8_t *out, uint32_t n, uint32_t N) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         out[i] = parts[part_start(i % N, n, N) + i / N];
@@ -25,11 +38,14 @@ __global__ void stripe_join_kernel(const uint8_t *parts, uint8_t *out, uint32_t 
 // One thread walks the stripes in order, exactly as the reference's loop does:
 // a candidate counts only if the space left in the caller's buffer would have
 // let it succeed (need_cap), and the first smallest one wins.
-__global__ void stripe_select_kernel(EncJob *jobs, uint32_t parent, uint32_t N, uint32_t nmeth) {
-    if (threadIdx.x || blockIdx.x) return;
+__global__ void stripe_select_kernel(EncJob *jobs, const uint32_t *parents, uint32_t nparents) {
+    const uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi >= nparents) return;
+    const uint32_t parent = parents[pi];
     EncJob &P = jobs[parent];
+    const uint32_t N = P.stripe_n, nmeth = P.stripe_nmeth;
     uint8_t *out = P.slot;
-    uint32_t *list = (uint32_t *)(P.slot + STRIPE_LIST_OFF);
+    uint32_t *list = (uint32_t *)(P.slot + P.slot_cap);
     const uint32_t cap = P.cap;
     int order = P.order;
     // the caller's order after the size fix-ups; the flag byte drops NOSZ (:1314)
@@ -84,8 +100,19 @@ cudaError_t launch_stripe_join(const uint8_t *d_parts, uint8_t *d_out, uint32_t 
     stripe_join_kernel<<<blocks, 256, 0, st>>>(d_parts, d_out, n, N);
     return cudaGetLastError();
 }
-cudaError_t launch_stripe_select(EncJob *d_jobs, uint32_t parent, uint32_t N, uint32_t nmeth, cudaStream_t st) {
-    stripe_select_kernel<<<1, 32, 0, st>>>(d_jobs, parent, N, nmeth);
+cudaError_t launch_stripe_split_batch(const EncJob *d_jobs, const uint32_t *d_parents, uint32_t nparents,
+                                      uint32_t max_in_size, cudaStream_t st) {
+    if (!nparents) return cudaSuccess;
+    uint32_t bx = (max_in_size + 4095) / 4096;         // 16 bytes per thread and trip at most
+    if (bx < 1) bx = 1;
+    if (bx > 64) bx = 64;
+    uint32_t by = nparents < 32768 ? nparents : 32768;
+    stripe_split_batch_kernel<<<dim3(bx, by), 256, 0, st>>>(d_jobs, d_parents, nparents);
+    return cudaGetLastError();
+}
+cudaError_t launch_stripe_select(EncJob *d_jobs, const uint32_t *d_parents, uint32_t nparents, cudaStream_t st) {
+    if (!nparents) return cudaSuccess;
+    stripe_select_kernel<<<(nparents + 31) / 32, 32, 0, st>>>(d_jobs, d_parents, nparents);
     return cudaGetLastError();
 }
 cudaError_t launch_dec_results(const DecJob *d_jobs, uint32_t n, uint32_t *d_osz, int *d_status, cudaStream_t st) {

@@ -33,7 +33,10 @@ bool stripe_plan_decode(DecItem &it, const unsigned char *in, uint32_t in_size, 
 
 cudaError_t launch_stripe_split(const uint8_t *d_in, uint8_t *d_tr, uint32_t n, uint32_t N, cudaStream_t st);
 cudaError_t launch_stripe_join(const uint8_t *d_parts, uint8_t *d_out, uint32_t n, uint32_t N, cudaStream_t st);
-cudaError_t launch_stripe_select(EncJob *d_jobs, uint32_t parent, uint32_t N, uint32_t nmeth, cudaStream_t st);
+// every STRIPE parent of a batch at once: d_parents lists their job indices
+cudaError_t launch_stripe_split_batch(const EncJob *d_jobs, const uint32_t *d_parents, uint32_t nparents,
+                                      uint32_t max_in_size, cudaStream_t st);
+cudaError_t launch_stripe_select(EncJob *d_jobs, const uint32_t *d_parents, uint32_t nparents, cudaStream_t st);
 cudaError_t launch_dec_results(const DecJob *d_jobs, uint32_t n, uint32_t *d_osz, int *d_status, cudaStream_t st);
 
 }  // namespace b200

@@ -186,10 +186,46 @@ int b200rans_uncompress_batch_dev(void *stream, int n,
                                   const uint64_t *out_off, const unsigned int *out_size,
                                   unsigned int *d_out_size, int *d_status);
 
+/* ---- device-resident variants, second form -------------------------------
+ * b200rans_compress_batch_dev2 adds `flags`:
+ *   B200RANS_OUT_IN_SLOT   every call gets its own rans_compress_bound_4x16-sized,
+ *                          256-byte aligned slot inside d_out -- the reference's
+ *                          "one bound-sized buffer per call" (fqzcomp5.c:1996) -- and the
+ *                          finished stream stays where the encoder built it
+ *                          (d_out_off[k] = its first byte); no packing pass runs.
+ *                          out_cap >= b200rans_compress_slots_bound(n, in_size, order).
+ *   0                      as b200rans_compress_batch_dev (streams packed back to back).
+ * b200rans_compress_trials_dev is b200rans_compress_trials with inputs and outputs in
+ * HBM: d_best [n], d_csize [method_first[n]] (either may be NULL) are DEVICE arrays;
+ * pack_align (a power of two, 1 = no gaps) places the winners in d_out.
+ * b200rans_tok3_methods fills out[] (<= 8 entries) with the candidate `order` values
+ * tok3's compress() walks for one token stream (tokenise_name3.c:1283-1357 tables with
+ * the filters of :1374-1378: X32 cleared, STRIPE dropped when in_len % 4), returning
+ * their number: what a C caller passes to b200rans_compress_trials per stream. */
+#define B200RANS_OUT_IN_SLOT 1u
+size_t b200rans_compress_slots_bound(int n, const unsigned int *in_size, const int *order);
+int b200rans_compress_batch_dev2(void *stream, int n,
+                                 const unsigned char *d_in,
+                                 const uint64_t *in_off, const unsigned int *in_size,
+                                 const int *order,
+                                 unsigned char *d_out, size_t out_cap,
+                                 uint64_t *d_out_off, unsigned int *d_out_size, unsigned int flags);
+int b200rans_compress_trials_dev(void *stream, int n,
+                                 const unsigned char *d_in,
+                                 const uint64_t *in_off, const unsigned int *in_size,
+                                 const unsigned int *method_first, const int *methods,
+                                 unsigned char *d_out, size_t out_cap, unsigned int pack_align,
+                                 uint64_t *d_out_off, unsigned int *d_out_size,
+                                 int *d_best, unsigned int *d_csize);
+int b200rans_tok3_methods(int level, int token_type, unsigned int in_len, int *out);
+
 /* Multi-GPU block partitioning: streams are dealt round-robin by
- * `block_of[k]` (or by k when NULL) over the first `ngpu` devices, one worker
- * thread and stream per device, results gathered in call order.  No
- * collective is involved. */
+ * `block_of[k]` >= 0 (or by k when NULL) over the first `ngpu` devices, results
+ * gathered in call order (the hts_tpool contract, thread_pool.c:113-164).  The
+ * worker threads -- B200RANS_WORKERS_PER_DEVICE per device, each with its own
+ * context, streams and arenas -- are created on first use and kept for the life
+ * of the process.  No collective is involved. */
+#define B200RANS_WORKERS_PER_DEVICE 2
 int b200rans_compress_batch_multi(int ngpu, int n,
                                   const unsigned char *const *in, const unsigned int *in_size,
                                   const int *order, const int *block_of,
@@ -287,7 +323,79 @@ int b200fqz_crc32_dev(void *stream, const unsigned char *d_buf, uint64_t n, uint
 int b200fqz_assemble_block_dev(void *stream, uint32_t num_records, int n_pieces, const b200fqz_piece *pieces,
                                unsigned char *d_block, uint64_t block_cap, uint32_t *block_len);
 
-/* Number of kernel launches issued by this thread's context so far. */
+/* ------------------------------------------------------------------------
+ * Part 5: one call per fqzcomp5 block (encode_block / decode_block,
+ * fqzcomp5.c:2147-2280, :2290-2547) -- FASTQ text in, framed block out, and
+ * back, everything between on the device: split (part 3), method trial over
+ * the section slices (part 2), framing + CRC-32 (part 4); decode: CRC check,
+ * batched decode, join.
+ *
+ * Sections are cut into `slice_bytes` pieces (rounded down to whole reads when
+ * the read length is fixed), each an independent rans_compress_to_4x16 stream
+ * tried under the section's method list, first smallest kept (one
+ * call has 4 or 32 serial lanes, a GPU needs thousands).  slice_bytes == 0
+ * codes every section as ONE stream: the layout of a section is then exactly
+ * the reference's ([u8 strat = 0][u32 ulen][u32 clen][stream], :2218-2232) and
+ * a block whose name stream the caller supplies is a stock FQZ5 block.
+ * With slices the section is
+ *   [u8 strat = B200FQZ_STRAT_SLICED][u32 ulen][u32 clen]
+ *   [u32 nslices][u32 slice_bytes][u32 csize[nslices]][streams back to back]
+ * which stock fqzcomp5 does not read (its format has one stream per section).
+ *
+ * Methods are `order` values as rans_compress_to_4x16 takes them;
+ * B200FQZ_RANSXN1 in a list stands for RANSXN1 = (fixed_len << 8) + 9 and is
+ * skipped when the block's reads differ in length (fqzcomp5.c:2013-2022).
+ * Names: with n_name_methods > 0 the name buffer is a third section coded like
+ * the others (the codec half of TLZP3 = LZP + order 5, fqzcomp5.c:2024-2028);
+ * with 0 the caller's `name_coder` turns the name buffer into the name section
+ * (the tokeniser is host code) while the device runs the trials.
+ * ---------------------------------------------------------------------- */
+#define B200FQZ_RANSXN1      (-1)
+#define B200FQZ_STRAT_SLICED 0xB2
+#define B200FQZ_MAX_METHODS  16
+
+typedef int (*b200fqz_name_coder)(void *user, const unsigned char *names, uint32_t name_len,
+                                  const uint32_t *flags, uint32_t num_records,
+                                  unsigned char **out, uint32_t *out_len);   /* *out: malloc()ed, freed by the library */
+typedef struct {
+    uint32_t slice_bytes;
+    int n_name_methods, n_seq_methods, n_qual_methods;
+    int name_methods[B200FQZ_MAX_METHODS], seq_methods[B200FQZ_MAX_METHODS], qual_methods[B200FQZ_MAX_METHODS];
+    b200fqz_name_coder name_coder;
+    void *name_user;
+} b200fqz_block_opts;
+
+typedef struct {
+    int32_t  status;                /* 0 ok; 1 malformed input (the reference returns NULL); 3 CRC mismatch */
+    uint32_t num_records, consumed; /* encode: bytes of text taken (load_seqs' *last_offset) */
+    int32_t  fixed_len;
+    uint32_t ulen[3], clen[3];      /* name, seq, qual: section bytes in and coded */
+    uint32_t nslices[3];
+    uint64_t csize[3][B200FQZ_MAX_METHODS];   /* per method: summed size over the slices (metrics_update's input) */
+    uint32_t wins[3][B200FQZ_MAX_METHODS];    /* per method: slices it won */
+    uint32_t block_len;             /* encode: bytes of block produced; decode: bytes of text produced */
+    uint32_t crc;
+} b200fqz_block_report;
+
+/* Host buffers (pinned for full PCIe rate).  text[0, n) holds FASTQ text; the block is written to
+ * block[0, block_cap); b200fqz_block_bound(n) bytes always suffice. */
+size_t b200fqz_block_bound(uint32_t n);
+int b200fqz_encode_block(const unsigned char *text, uint32_t n, const b200fqz_block_opts *opts,
+                         unsigned char *block, size_t block_cap, b200fqz_block_report *rep);
+/* block[0, block_len) as written by b200fqz_encode_block with n_name_methods > 0; text_cap bytes at text. */
+int b200fqz_decode_block(const unsigned char *block, uint32_t block_len, int plus_name,
+                         unsigned char *text, size_t text_cap, b200fqz_block_report *rep);
+/* nblocks independent blocks dealt round-robin over the first ngpu devices (block b on device
+ * b % ngpu) by the persistent workers; results in call order. rep[b].status is per block. */
+int b200fqz_encode_blocks_multi(int ngpu, int nblocks, const unsigned char *const *text, const uint32_t *n,
+                                const b200fqz_block_opts *opts, unsigned char *const *block,
+                                const size_t *block_cap, b200fqz_block_report *rep);
+int b200fqz_decode_blocks_multi(int ngpu, int nblocks, const unsigned char *const *block,
+                                const uint32_t *block_len, int plus_name, unsigned char *const *text,
+                                const size_t *text_cap, b200fqz_block_report *rep);
+
+/* Number of kernel launches issued by this thread's context so far (workers of the
+ * multi-GPU calls add theirs when a call returns). */
 uint64_t b200rans_launch_count(void);
 
 /* Measurement hooks: with profiling on, the encode / decode coder kernel of each

@@ -235,24 +235,147 @@ def test_one_large_stream_per_call(gpu_codec, checker):
         assert gpu_codec.rans_uncompress_4x16(want) == data, hex(order)
 
 
-def test_multi_gpu_batch_api(gpu_codec, checker):
-    """b200rans_*_batch_multi: blocks dealt round-robin to the GPUs of the box, results in call
-    order (runs with however many GPUs are visible, 1 included)."""
-    import torch
-    ngpu = min(torch.cuda.device_count(), 2)
+def _multi_roundtrip(gpu_codec, checker, ngpu):
     parts = [np.frombuffer(corpus.make("illumina_qual", 262144, s), np.uint8) for s in range(12)]
     buf = np.concatenate(parts)
     offs = [262144 * i for i in range(12)]
     sizes = [262144] * 12
     orders = [4, 5] * 6
-    out, ooff, osz = gpu_codec.compress_batch(buf, offs, sizes, orders, ngpu=ngpu,
-                                              block_of=[i // 3 for i in range(12)])
-    for k in range(12):
-        assert out[int(ooff[k]):int(ooff[k]) + int(osz[k])].tobytes() == checker.compress(parts[k].tobytes(), orders[k])
-    back = np.empty(buf.size, np.uint8)
-    rsz, st = gpu_codec.uncompress_batch(out, ooff, osz, back, offs, sizes, ngpu=ngpu,
-                                         block_of=[i // 3 for i in range(12)])
-    assert (st == 0).all() and np.array_equal(back, buf)
+    block_of = [i // 3 for i in range(12)]
+    for _ in range(2):          # the second call runs on the workers and contexts the first one created
+        out, ooff, osz = gpu_codec.compress_batch(buf, offs, sizes, orders, ngpu=ngpu, block_of=block_of, multi=True)
+        for k in range(12):
+            assert out[int(ooff[k]):int(ooff[k]) + int(osz[k])].tobytes() == checker.compress(parts[k].tobytes(), orders[k])
+        back = np.empty(buf.size, np.uint8)
+        rsz, st = gpu_codec.uncompress_batch(out, ooff, osz, back, offs, sizes, ngpu=ngpu, block_of=block_of, multi=True)
+        assert (st == 0).all() and np.array_equal(back, buf)
+
+
+def test_multi_batch_api_on_persistent_worker(gpu_codec, checker):
+    """b200rans_*_batch_multi with ngpu = 1: the call still runs on the library's persistent worker
+    thread (its own context and arenas), results in call order."""
+    _multi_roundtrip(gpu_codec, checker, 1)
+    with pytest.raises(gpu_codec.B200RansError):
+        gpu_codec.compress_batch(np.zeros(8, np.uint8), [0], [8], [0], ngpu=1, block_of=[-1], multi=True)
+
+
+def test_multi_gpu_batch_api(gpu_codec, checker):
+    """b200rans_*_batch_multi on TWO devices: blocks dealt round-robin, one persistent worker and
+    context per device, results gathered in call order.  Skipped (not downgraded) on a one-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    _multi_roundtrip(gpu_codec, checker, 2)
+
+
+def test_decode_without_flags(gpu_codec, checker):
+    """b200rans_uncompress_batch_dev with flags == NULL ("unknown"): order-0, order-1, raw and
+    PACK / RLE streams all decode through the general kernel."""
+    import torch
+    items = [("illumina_qual", 100000, 4), ("illumina_qual", 100000, 5), ("illumina_qual", 70000, 0),
+             ("ont_qual", 90000, 1), ("illumina_seq", 120000, 0xc5), ("runs", 50000, 0x44), ("random", 3000, 4),
+             ("binned_qual", 80000, 0x84), ("text", 60000, 5), ("illumina_qual", 0, 5)]
+    raw = [corpus.make(g, n, 3) for g, n, _ in items]
+    comp = [checker.compress(d, o) for d, (_, _, o) in zip(raw, items)]
+    coff = np.concatenate([[0], np.cumsum([(len(c) + 15) & ~15 for c in comp])[:-1]]).astype(np.uint64)
+    arena = np.zeros(int(coff[-1]) + len(comp[-1]) + 64, np.uint8)
+    for c, o in zip(comp, coff):
+        arena[int(o):int(o) + len(c)] = np.frombuffer(c, np.uint8)
+    sizes = np.array([len(d) for d in raw], np.uint32)
+    ooff = np.concatenate([[0], np.cumsum((sizes + 15) & ~15)[:-1]]).astype(np.uint64)
+    d_in = torch.from_numpy(arena).cuda()
+    d_out = torch.zeros(int(ooff[-1]) + int(sizes[-1]) + 64, dtype=torch.uint8, device="cuda")
+    d_osz = torch.zeros(len(items), dtype=torch.int32, device="cuda")
+    d_st = torch.ones(len(items), dtype=torch.int32, device="cuda")
+    st = torch.cuda.Stream()
+    gpu_codec.uncompress_batch_dev(st.cuda_stream, d_in.data_ptr(), coff, np.array([len(c) for c in comp], np.uint32),
+                                   d_out.data_ptr(), ooff, sizes, d_osz.data_ptr(), d_st.data_ptr(), flags=None)
+    st.synchronize()
+    assert d_st.cpu().tolist() == [0] * len(items)
+    back = d_out.cpu().numpy()
+    for d, o in zip(raw, ooff):
+        assert back[int(o):int(o) + len(d)].tobytes() == d
+
+
+def test_in_slot_output(gpu_codec, checker):
+    """b200rans_compress_batch_dev2 with OUT_IN_SLOT: every stream stays in its own bound-sized slot
+    (no packing pass) and is still the reference's bytes -- coded, raw (CAT), STRIPE, tiny, empty,
+    self-compressed order-1 tables, PACK / RLE."""
+    import torch
+    items = [("illumina_qual", 262144, 4), ("illumina_qual", 262144, 5), ("ont_qual", 100001, 5),
+             ("illumina_seq", 200000, 0xc5), ("random", 5000, 4), ("const", 70000, 0x84), ("text", 30000, 1),
+             ("illumina_qual", 0, 0), ("runs", 90000, 0x44), ("illumina_qual", 60000, (150 << 8) | 9),
+             ("nsym4", 777, 0xc1), ("wide", 300000, 5), ("illumina_qual", 19, 5), ("stripe32", 40000, (4 << 8) | 9),
+             ("illumina_qual", 33, 4), ("text", 300000, 5)] * 2
+    parts = [np.frombuffer(corpus.make(g, n, 3), np.uint8) for g, n, _ in items]
+    orders = np.array([o for _, _, o in items], np.int32)
+    sizes = np.array([p.size for p in parts], np.uint32)
+    offs = np.concatenate([[0], np.cumsum((sizes + 15) & ~15)[:-1]]).astype(np.uint64)
+    buf = np.zeros(int(offs[-1]) + int(sizes[-1]) + 64, np.uint8)
+    for p_, o in zip(parts, offs):
+        buf[int(o):int(o) + p_.size] = p_
+    d_in = torch.from_numpy(buf).cuda()
+    cap = gpu_codec.compress_slots_bound(sizes, orders)
+    d_out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    d_off = torch.zeros(len(items), dtype=torch.int64, device="cuda")
+    d_sz = torch.zeros(len(items), dtype=torch.int32, device="cuda")
+    st = torch.cuda.Stream()
+    gpu_codec.compress_batch_dev2(st.cuda_stream, d_in.data_ptr(), offs, sizes, orders, d_out.data_ptr(), cap,
+                                  d_off.data_ptr(), d_sz.data_ptr(), flags=gpu_codec.OUT_IN_SLOT)
+    st.synchronize()
+    off, sz, comp = d_off.cpu().numpy(), d_sz.cpu().numpy(), d_out.cpu().numpy()
+    for k, (p_, o) in enumerate(zip(parts, orders)):
+        want = checker.compress(p_.tobytes(), int(o))
+        assert comp[off[k]:off[k] + sz[k]].tobytes() == want, (k, items[k], int(sz[k]), len(want))
+    # and the slots decode where they lie
+    d_back = torch.zeros(buf.size, dtype=torch.uint8, device="cuda")
+    d_osz = torch.zeros(len(items), dtype=torch.int32, device="cuda")
+    d_st = torch.ones(len(items), dtype=torch.int32, device="cuda")
+    plain = [k for k in range(len(items)) if not (comp[off[k]] & 8)]         # STRIPE goes through the host-buffer API
+    gpu_codec.uncompress_batch_dev(st.cuda_stream, d_out.data_ptr(), off[plain].astype(np.uint64),
+                                   sz[plain].astype(np.uint32), d_back.data_ptr(), offs[plain], sizes[plain],
+                                   d_osz.data_ptr(), d_st.data_ptr(), flags=comp[off[plain]])
+    st.synchronize()
+    assert int(d_st[:len(plain)].abs().sum()) == 0
+    back = d_back.cpu().numpy()
+    for k in plain:
+        assert np.array_equal(back[int(offs[k]):int(offs[k]) + int(sizes[k])], parts[k]), k
+
+
+def test_method_trial_device_resident(gpu_codec, checker):
+    """b200rans_compress_trials_dev: ragged trial with inputs and winners in HBM, winners packed without
+    gaps (pack_align 1) as the block pipeline uses it."""
+    import torch
+    lists = [[0, 1, 129, 193, gpu_codec.ransxn1_order(150)], [4, 5, 133, 197], [1], [193, 0]]
+    items = [("illumina_qual", 150 * 300, 1), ("illumina_seq", 150 * 900, 2), ("runs", 70000, 3), ("random", 9000, 4),
+             ("binned_qual", 150 * 500, 5), ("illumina_qual", 0, 6), ("text", 50000, 7), ("const", 20000, 8)]
+    parts = [np.frombuffer(corpus.make(g, n, s), np.uint8) for g, n, s in items]
+    ml = [lists[i % len(lists)] for i in range(len(items))]
+    sizes = np.array([p_.size for p_ in parts], np.uint32)
+    offs = np.concatenate([[0], np.cumsum((sizes + 15) & ~15)[:-1]]).astype(np.uint64)
+    buf = np.zeros(int(offs[-1]) + int(sizes[-1]) + 64, np.uint8)
+    for p_, o in zip(parts, offs):
+        buf[int(o):int(o) + p_.size] = p_
+    d_in = torch.from_numpy(buf).cuda()
+    cap = int(sum(max(gpu_codec.rans_compress_bound_4x16(int(s), m) for m in l) for s, l in zip(sizes, ml))) + 4096
+    d_out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    n, mm = len(items), sum(len(l) for l in ml)
+    d_off = torch.zeros(n, dtype=torch.int64, device="cuda")
+    d_sz = torch.zeros(n, dtype=torch.int32, device="cuda")
+    d_best = torch.full((n,), -7, dtype=torch.int32, device="cuda")
+    d_cs = torch.zeros(mm, dtype=torch.int32, device="cuda")
+    st = torch.cuda.Stream()
+    first = gpu_codec.compress_trials_dev(st.cuda_stream, d_in.data_ptr(), offs, sizes, ml, d_out.data_ptr(), cap, 1,
+                                          d_off.data_ptr(), d_sz.data_ptr(), d_best.data_ptr(), d_cs.data_ptr())
+    st.synchronize()
+    off, sz, best, cs, comp = (t.cpu().numpy() for t in (d_off, d_sz, d_best, d_cs, d_out))
+    at = 0
+    for k in range(n):
+        wb, wout, wsizes = _cpu_trial(checker, parts[k].tobytes(), ml[k])
+        assert cs[first[k]:first[k + 1]].tolist() == wsizes and best[k] == wb, (k, items[k])
+        assert off[k] == at, "winners are packed without gaps, in input order"
+        assert comp[off[k]:off[k] + sz[k]].tobytes() == wout
+        at += int(sz[k])
 
 
 def test_randomised_differential(gpu_codec, checker):

@@ -88,3 +88,17 @@ def test_bench_extra_workloads_are_registered():
     import bench
     assert set(bench.EXTRA) == {"fastq_split", "fastq_join", "crc32"}
     assert "illumina_qual_o0" in bench.WORKLOADS and bench.METRIC.startswith("rANS32x16")
+
+
+def test_tok3_tables_in_c():
+    """b200rans_tok3_methods (C, no device needed) against the Python transcription of
+    tokenise_name3.c:1283-1357 with the filters of :1374-1378."""
+    from fqzcomp5_b200 import codec
+    for level in range(1, 10):
+        row = codec.TOK3_METHODS[codec.tok3_level_row(level)]
+        for t in range(13):
+            for n in (0, 3, 4, 1001):
+                assert codec.tok3_methods(level, t, n) == codec.tok3_method_list(row[t], n)
+    import pytest
+    with pytest.raises(codec.B200RansError):
+        codec.tok3_methods(3, 13, 4)
