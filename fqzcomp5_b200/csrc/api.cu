@@ -68,6 +68,19 @@ inline int effective_order(uint32_t in_size, int order) {
 //   in-slot mode: every caller item's slot is carved out of d_out (rans_compress_bound_4x16 bytes,
 //       256-byte aligned -- the reference's "one bound-sized buffer per call") and the stream stays
 //       where the encoder built it; no scan, no gather.  out_cap >= enc_slots_bound().
+// Bytes a stream's private slot needs.  rans_compress_bound_4x16 reserves 257*257*3 bytes for an order-1
+// table whatever the input size; a table never exceeds the alphabet list (<= 513 bytes) plus two bytes
+// per distinct (context, symbol) pair and two per zero run (at most one more run than pairs per row),
+// i.e. 4 * (n + 32) + 2 * 256 + 513 bytes, so small streams (STRIPE sub-streams above all) get small slots.
+inline uint32_t slot_cap_for(uint32_t isz, int ord) {
+    uint32_t b = compress_bound(isz, ord);
+    if (ord & 1) {
+        const uint64_t table_worst = 257 * 257 * 3 + 4, table_real = 4ull * isz + 2048;
+        if (table_real < table_worst) b -= (uint32_t)(table_worst - table_real);
+    }
+    return (uint32_t)al(b + 16, 16);
+}
+
 size_t enc_slots_bound(int n, const uint32_t *in_size, const int *order) {
     size_t t = 0;
     for (int k = 0; k < n; k++) {
@@ -114,7 +127,9 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
         EncJob &J = jobs[j];
         memset(&J, 0, sizeof(J));
         J.in = in; J.in_size = isz; J.order = ord; J.cap = cap; J.item = item;
-        uint32_t slot_cap = (uint32_t)al(compress_bound(isz, ord) + 16, 16);
+        // caller items keep the reference's bound in in-slot mode (it is what the header promises)
+        uint32_t slot_cap = (inslot && item != 0xffffffffu) ? (uint32_t)al(compress_bound(isz, ord) + 16, 16)
+                                                            : slot_cap_for(isz, ord);
         J.slot_cap = slot_cap;
         const size_t slot_bytes = (size_t)slot_cap + (parent ? STRIPE_LIST_BYTES + 16 : 0);
         if (inslot && item != 0xffffffffu) { J.slot = (uint8_t *)LO.take(slot_bytes, 256); in_out[j] = 1; }
@@ -135,7 +150,9 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
             n_o1++;
             // symbol table (16 B/pair), pair counts (4 B/pair), coded table scratch
             // + 16-bit pair keys of the partitioned pair count (large alphabets without a model)
-            pool_bytes += 256 * 256 * 12 + 300 * 1024 + (J.model ? 0 : 2 * (size_t)isz + 2048);
+            const size_t m = std::min<size_t>(256, (size_t)isz + 1);       // alphabet of a short stream
+            pool_bytes += m * m * 12 + std::min<size_t>(300 * 1024, 5 * (size_t)isz + 8192) + 2048 +
+                          (J.model ? 0 : 2 * (size_t)isz + 2048);
         } else n_o0++;
     };
     size_t si = 0;

@@ -282,7 +282,7 @@ def test_decode_without_flags(gpu_codec, checker):
     for c, o in zip(comp, coff):
         arena[int(o):int(o) + len(c)] = np.frombuffer(c, np.uint8)
     sizes = np.array([len(d) for d in raw], np.uint32)
-    ooff = np.concatenate([[0], np.cumsum((sizes + 15) & ~15)[:-1]]).astype(np.uint64)
+    ooff = np.concatenate([[0], np.cumsum((sizes.astype(np.int64) + 15) // 16 * 16)[:-1]]).astype(np.uint64)
     d_in = torch.from_numpy(arena).cuda()
     d_out = torch.zeros(int(ooff[-1]) + int(sizes[-1]) + 64, dtype=torch.uint8, device="cuda")
     d_osz = torch.zeros(len(items), dtype=torch.int32, device="cuda")
@@ -310,7 +310,7 @@ def test_in_slot_output(gpu_codec, checker):
     parts = [np.frombuffer(corpus.make(g, n, 3), np.uint8) for g, n, _ in items]
     orders = np.array([o for _, _, o in items], np.int32)
     sizes = np.array([p.size for p in parts], np.uint32)
-    offs = np.concatenate([[0], np.cumsum((sizes + 15) & ~15)[:-1]]).astype(np.uint64)
+    offs = np.concatenate([[0], np.cumsum((sizes.astype(np.int64) + 15) // 16 * 16)[:-1]]).astype(np.uint64)
     buf = np.zeros(int(offs[-1]) + int(sizes[-1]) + 64, np.uint8)
     for p_, o in zip(parts, offs):
         buf[int(o):int(o) + p_.size] = p_
@@ -352,7 +352,7 @@ def test_method_trial_device_resident(gpu_codec, checker):
     parts = [np.frombuffer(corpus.make(g, n, s), np.uint8) for g, n, s in items]
     ml = [lists[i % len(lists)] for i in range(len(items))]
     sizes = np.array([p_.size for p_ in parts], np.uint32)
-    offs = np.concatenate([[0], np.cumsum((sizes + 15) & ~15)[:-1]]).astype(np.uint64)
+    offs = np.concatenate([[0], np.cumsum((sizes.astype(np.int64) + 15) // 16 * 16)[:-1]]).astype(np.uint64)
     buf = np.zeros(int(offs[-1]) + int(sizes[-1]) + 64, np.uint8)
     for p_, o in zip(parts, offs):
         buf[int(o):int(o) + p_.size] = p_
