@@ -312,9 +312,14 @@ def measure_codec(args, name, data, env, with_cpu):
     assert (csz > 0).all(), "a stream failed to compress"
     assert np.array_equal(csz, packed_csz), "in-slot and packed outputs differ in size"
     flags = d_comp[torch.from_numpy(coff.astype(np.int64)).to(dev)].cpu().numpy()
-    if (order & 0xC0) == 0xC0 and name == "illumina_seq_c5":
-        # the emitted flag byte keeps PACK (0x80) and RLE (0x40)
-        assert ((flags & 0xC0) == 0xC0).all(), "config 3: a stream dropped PACK or RLE"
+    flag_hist = {hex(int(f)): int(c) for f, c in zip(*np.unique(flags, return_counts=True))}
+    if name == "illumina_seq_c5":
+        # the emitted flag byte keeps PACK (0x80) -- every stream -- and RLE (0x40).  At 256 KiB
+        # per call the reference itself rejects RLE for about a third of the slices (its .99 test,
+        # rANS_static4x16pr.c:1485: too few poly-G tails in that slice); those streams are 0x85 on the CPU too
+        # (the byte comparison below covers both kinds).
+        assert ((flags & 0x85) == 0x85).all(), "config 3: a stream dropped PACK, X32 or order 1"
+        assert int(((flags & 0xC0) == 0xC0).sum()) * 2 > flags.size, "config 3: RLE kept by fewer than half the streams"
     dec(coff, csz, flags)
     torch.cuda.synchronize()
     assert int(d_st.abs().sum()) == 0, "a stream failed to decompress"
@@ -409,7 +414,7 @@ def measure_codec(args, name, data, env, with_cpu):
             "enc_step_traffic": traffic.get("enc_step"), "dec_step_traffic": traffic.get("dec_step")}
     res = {
         "ms_enc": ms_enc, "ms_dec": ms_dec, "e2e_enc_s": e2e_enc, "e2e_dec_s": e2e_dec,
-        "U": U, "C": Cc, "n": n, "order": order, "S": S,
+        "U": U, "C": Cc, "n": n, "order": order, "S": S, "flags": flag_hist,
         "packed_enc_ms": float(np.mean(tp)) if tp else None,
         "gpu_launches": int(launches), "roofline": r_enc if ke >= kd else r_dec,
         "roofline_enc": r_enc, "roofline_dec": r_dec, "roofline_step": step,
@@ -470,7 +475,7 @@ def codec_entry(name, r, world, ms_enc, ms_dec, e2e_ms):
         "e2e": {"value": world * U / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s",
                 "h2d_bytes_per_step": U + Cc, "d2h_bytes_per_step": U + Cc,
                 "enc_gbs": U / r["e2e_enc_s"] / 1e9, "dec_gbs": U / r["e2e_dec_s"] / 1e9},
-        "gpu_launches": r["gpu_launches"],
+        "gpu_launches": r["gpu_launches"], "stream_flags": r["flags"],
         "roofline": r["roofline"], "roofline_enc": r["roofline_enc"], "roofline_dec": r["roofline_dec"],
         "roofline_step": r["roofline_step"], "clocks": r["clocks"], "wall_s_timed_region": r["wall_s_timed_region"],
     }
