@@ -74,9 +74,10 @@ inline int effective_order(uint32_t in_size, int order) {
 // i.e. 4 * (n + 32) + 2 * 256 + 513 bytes, so small streams (STRIPE sub-streams above all) get small slots.
 inline uint32_t slot_cap_for(uint32_t isz, int ord) {
     uint32_t b = compress_bound(isz, ord);
-    if (ord & 1) {
-        const uint64_t table_worst = 257 * 257 * 3 + 4, table_real = 4ull * isz + 2048;
-        if (table_real < table_worst) b -= (uint32_t)(table_worst - table_real);
+    if (ord & 0xff) {       // the bound takes the order-1 branch for ANY non-zero flag byte (rANS_static4x16pr.c:97-100)
+        const uint64_t table_worst = 257 * 257 * 3 + 4;
+        const uint64_t table_real = (ord & 1) ? std::min<uint64_t>(table_worst, 4ull * isz + 2048) : 0;
+        b -= (uint32_t)(table_worst - table_real);
     }
     return (uint32_t)al(b + 16, 16);
 }
@@ -181,7 +182,7 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
     }
     if (inslot && out_adj + LO.off > out_cap) return B200RANS_ESPACE;
     // the reference's worst case is one table per stream; real tables are tiny.
-    pool_bytes = std::min<size_t>(pool_bytes, (size_t)16 << 30);
+    pool_bytes = std::min<size_t>(pool_bytes, (size_t)8 << 30);
     pool_bytes = std::max<size_t>(pool_bytes, (size_t)8 << 20);
     size_t o_pool = L.take(pool_bytes, 256);
     size_t o_soff = L.take(njobs * 8), o_ssz = L.take(njobs * 4), o_tot = L.take(8);

@@ -32,7 +32,7 @@ struct Arena {
     bool pinned = false;
     int ensure(size_t need) {
         if (need <= cap) return 0;
-        size_t want = need + need / 4 + (1 << 20);
+        size_t want = need + (need < ((size_t)2 << 30) ? need / 4 : need / 32) + (1 << 20);   // big arenas: little slack
         if (p) { if (pinned) cudaFreeHost(p); else cudaFree(p); p = nullptr; cap = 0; }
         cudaError_t e = pinned ? cudaHostAlloc((void **)&p, want, cudaHostAllocDefault)
                                : cudaMalloc((void **)&p, want);
