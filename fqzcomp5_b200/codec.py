@@ -37,6 +37,7 @@ EXPORTS = [
     "b200fqz_crc32", "b200fqz_crc32_dev", "b200fqz_assemble_block_dev",
     "b200rans_compress_slots_bound", "b200rans_compress_batch_dev2", "b200rans_compress_trials_dev",
     "b200rans_tok3_methods",
+    "b200fq_split_mode", "b200fq_split_dev_mode",
     "b200fqz_block_bound", "b200fqz_encode_block", "b200fqz_decode_block",
     "b200fqz_encode_blocks_multi", "b200fqz_decode_blocks_multi",
 ]
@@ -92,6 +93,8 @@ def lib():
         L.b200rans_compress_methods.argtypes = [vp, u32, i32, vp, pu32, pi32, vp]
         L.b200rans_compress_methods.restype = vp
         L.b200fq_split.argtypes = [vp, u32, vp, u32, vp, vp, u32, vp, vp, u32, vp]
+        L.b200fq_split_mode.argtypes = [i32, u32, vp, u32, vp, u32, vp, vp, u32, vp, vp, u32, vp]
+        L.b200fq_split_dev_mode.argtypes = [vp, i32, u32, vp, u32, vp, u32, vp, vp, u32, vp, vp, vp, vp, u32, vp, sz, vp]
         L.b200fq_join.argtypes = [vp, u32, vp, vp, u32, vp, u32, i32, vp, u32, vp]
         L.b200fq_split_scratch_bytes.argtypes = [u32, u32]
         L.b200fq_split_scratch_bytes.restype = sz
@@ -481,10 +484,17 @@ class FqInfo(C.Structure):
     """b200fq_info (include/b200rans.h)."""
     _fields_ = [("status", C.c_int32), ("num_records", C.c_uint32), ("name_len", C.c_uint32),
                 ("seq_len", C.c_uint32), ("qual_len", C.c_uint32), ("fixed_len", C.c_int32),
-                ("consumed", C.c_uint32), ("text_len", C.c_uint32)]
+                ("consumed", C.c_uint32), ("text_len", C.c_uint32), ("more", C.c_uint32)]
 
 
-def load_seqs(text, max_records=None):
+def load_seqs_kseq(text, blk_size, max_records=None):
+    """The live loader's rules (load_seqs_kseq, fqzcomp5.c:423-623) on the GPU for strict 4-line FASTQ: one
+    block of at most blk_size accounted bytes from the front of `text`.  Returns load_seqs' dict plus `more`
+    (1: the block-size rule ended the block; 0: the text ran out), or None where the reference fails."""
+    return load_seqs(text, max_records, mode=1, blk_size=blk_size)
+
+
+def load_seqs(text, max_records=None, mode=0, blk_size=0):
     """The reference's load_seqs (fqzcomp5.c:279-410) on the GPU: a block of FASTQ text ->
     dict(num_records, name, seq, qual, len, flag, fixed_len, consumed), or None where the
     reference returns NULL.  `text`: bytes or a uint8 numpy array (pinned for full PCIe rate)."""
@@ -496,8 +506,8 @@ def load_seqs(text, max_records=None):
         name = np.empty(n + 16, np.uint8); seq = np.empty(n + 16, np.uint8); qual = np.empty(n + 16, np.uint8)
         ln = np.empty(mr + 1, np.uint32); fl = np.empty(mr + 1, np.uint32)
         info = FqInfo()
-        rc = L.b200fq_split(_addr(t) if n else None, n, _addr(name), n + 16, _addr(seq), _addr(qual), n + 16,
-                            _addr(ln), _addr(fl), mr, C.addressof(info))
+        rc = L.b200fq_split_mode(mode, blk_size, _addr(t) if n else None, n, _addr(name), n + 16, _addr(seq),
+                                 _addr(qual), n + 16, _addr(ln), _addr(fl), mr, C.addressof(info))
         _check(rc, "b200fq_split")
         if info.status == 2 and max_records is None and mr < n // 4 + 64:
             mr = n // 4 + 64            # more records than guessed: the smallest record is 6 bytes... retry
@@ -510,7 +520,7 @@ def load_seqs(text, max_records=None):
     R = info.num_records
     return dict(num_records=R, name=name[:info.name_len].tobytes(), seq=seq[:info.seq_len].tobytes(),
                 qual=qual[:info.qual_len].tobytes(), len=ln[:R].tolist(), flag=fl[:R].tolist(),
-                fixed_len=info.fixed_len, consumed=info.consumed)
+                fixed_len=info.fixed_len, consumed=info.consumed, **({"more": info.more} if mode else {}))
 
 
 def output_fastq(name, seq, qual, lens, plus_name=0):
@@ -571,7 +581,7 @@ class BlockOpts(C.Structure):
     _fields_ = [("slice_bytes", C.c_uint32), ("n_name_methods", C.c_int), ("n_seq_methods", C.c_int),
                 ("n_qual_methods", C.c_int), ("name_methods", C.c_int * MAX_METHODS),
                 ("seq_methods", C.c_int * MAX_METHODS), ("qual_methods", C.c_int * MAX_METHODS),
-                ("name_coder", NAME_CODER), ("name_user", C.c_void_p)]
+                ("name_coder", NAME_CODER), ("name_user", C.c_void_p), ("kseq_blk_size", C.c_uint32)]
 
 
 class BlockReport(C.Structure):

@@ -891,9 +891,19 @@ API int b200fq_split_dev(void *stream, const unsigned char *d_text, uint32_t n, 
                          uint32_t name_cap, unsigned char *d_seq, unsigned char *d_qual, uint32_t seq_cap,
                          uint32_t *d_len, uint32_t *d_flag, uint32_t *d_name_off, uint32_t *d_seq_off,
                          uint32_t max_records, void *d_scratch, size_t scratch_bytes, b200fq_info *d_info) {
+    return b200fq_split_dev_mode(stream, B200FQ_MODE_LOAD_SEQS, 0, d_text, n, d_name, name_cap, d_seq, d_qual, seq_cap,
+                                 d_len, d_flag, d_name_off, d_seq_off, max_records, d_scratch, scratch_bytes, d_info);
+}
+
+API int b200fq_split_dev_mode(void *stream, int mode, uint32_t blk_size, const unsigned char *d_text, uint32_t n,
+                              unsigned char *d_name, uint32_t name_cap, unsigned char *d_seq, unsigned char *d_qual,
+                              uint32_t seq_cap, uint32_t *d_len, uint32_t *d_flag, uint32_t *d_name_off,
+                              uint32_t *d_seq_off, uint32_t max_records, void *d_scratch, size_t scratch_bytes,
+                              b200fq_info *d_info) {
     int err = 0;
     Ctx *C = get_ctx(&err);
     if (!C) return err;
+    if (mode != B200FQ_MODE_LOAD_SEQS && mode != B200FQ_MODE_KSEQ) return B200RANS_EINVAL;
     if (!d_text || !d_name || !d_seq || !d_qual || !d_len || !d_flag || !d_name_off || !d_seq_off || !d_scratch ||
         !d_info || n > 0x7fffffffu || ((uintptr_t)d_text & 15) || ((uintptr_t)d_scratch & 255) ||
         scratch_bytes < fq_split_scratch_bytes(n, max_records))
@@ -901,7 +911,7 @@ API int b200fq_split_dev(void *stream, const unsigned char *d_text, uint32_t n, 
     int l = 0;
     CK(fq_split_launch(d_text, n, d_name, d_seq, d_qual, name_cap, seq_cap, d_len, d_flag, d_name_off, d_seq_off,
                        max_records, (uint8_t *)d_scratch, (FqInfo *)d_info,
-                       stream ? (cudaStream_t)stream : C->dlane.st, &l));
+                       stream ? (cudaStream_t)stream : C->dlane.st, &l, mode == B200FQ_MODE_KSEQ, blk_size));
     C->launches += l;
     return 0;
 }
@@ -926,9 +936,17 @@ API int b200fq_join_dev(void *stream, const unsigned char *d_name, uint32_t name
 API int b200fq_split(const unsigned char *text, uint32_t n, unsigned char *name, uint32_t name_cap,
                      unsigned char *seq, unsigned char *qual, uint32_t seq_cap, uint32_t *len, uint32_t *flag,
                      uint32_t max_records, b200fq_info *info) {
+    return b200fq_split_mode(B200FQ_MODE_LOAD_SEQS, 0, text, n, name, name_cap, seq, qual, seq_cap, len, flag,
+                             max_records, info);
+}
+
+API int b200fq_split_mode(int mode, uint32_t blk_size, const unsigned char *text, uint32_t n, unsigned char *name,
+                          uint32_t name_cap, unsigned char *seq, unsigned char *qual, uint32_t seq_cap, uint32_t *len,
+                          uint32_t *flag, uint32_t max_records, b200fq_info *info) {
     int err = 0;
     Ctx *C = get_ctx(&err);
     if (!C) return err;
+    if (mode != B200FQ_MODE_LOAD_SEQS && mode != B200FQ_MODE_KSEQ) return B200RANS_EINVAL;
     if ((n && !text) || !name || !seq || !qual || !len || !flag || !info || n > 0x7fffffffu) return B200RANS_EINVAL;
     Lane &Ln = C->lane[0];
     cudaStream_t st = Ln.st;
@@ -948,7 +966,7 @@ API int b200fq_split(const unsigned char *text, uint32_t n, unsigned char *name,
     int l = 0;
     CK(fq_split_launch(D + o_text, n, D + o_name, D + o_seq, D + o_qual, name_cap, seq_cap, (uint32_t *)(D + o_len),
                        (uint32_t *)(D + o_flag), (uint32_t *)(D + o_no), (uint32_t *)(D + o_so), max_records,
-                       D + o_scr, (FqInfo *)(D + o_info), st, &l));
+                       D + o_scr, (FqInfo *)(D + o_info), st, &l, mode == B200FQ_MODE_KSEQ, blk_size));
     C->launches += l;
     CK(cudaMemcpyAsync(Ln.hio.p, D + o_info, sizeof(FqInfo), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

@@ -183,7 +183,8 @@ int encode_block_impl(const unsigned char *text, uint32_t n, const b200fqz_block
         int l = 0;
         CK(fq_split_launch(D0 + o_text, n, D0 + o_name, D0 + o_seq, D0 + o_qual, name_cap, seq_cap,
                            (uint32_t *)(D0 + o_len), (uint32_t *)(D0 + o_flag), (uint32_t *)(D0 + o_no),
-                           (uint32_t *)(D0 + o_so), mr, D0 + o_scr, (FqInfo *)(D0 + o_info), st, &l));
+                           (uint32_t *)(D0 + o_so), mr, D0 + o_scr, (FqInfo *)(D0 + o_info), st, &l,
+                           o->kseq_blk_size != 0, o->kseq_blk_size));
         C->launches += l;
         CK(cudaMemcpyAsync(C->hblk.p, D0 + o_info, sizeof(FqInfo), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));

@@ -39,7 +39,8 @@ struct FqWork {                          // zeroed before every call
     uint32_t maxlen;
     uint32_t have_len;
     uint32_t tot[2];                     // totals of the two scanned arrays
-    uint32_t pad[8];
+    uint32_t cut;                        // kseq mode: records taken by the block-size rule
+    uint32_t pad[7];
 };
 
 __device__ __forceinline__ uint32_t eq_mask4(uint32_t w, uint32_t pat) {    // 4 bits: byte j of w == pattern
@@ -212,6 +213,88 @@ records_kernel(const uint8_t *__restrict__ text, uint32_t n, const uint32_t *__r
     }
 }
 
+// ---------------------------------------------------------------- split, kseq mode (load_seqs_kseq, fqzcomp5.c:423-623)
+// The live loader reads kseq records (kseq.h:176-218).  For strict 4-line FASTQ a record is
+//   name    = header up to its first isspace() byte,   comment = the rest of the header line
+//   stored  = name [+ ' ' + comment when the comment is not empty] + NUL          (:485-510)
+//   size    = name.l + 1 + seq.l + qual.l, and a block takes records while the running total
+//             stays <= blk_size, one at least (:468-476)
+// hdr_info(): stored length and the position of the separator inside the header (0xffffffff: none).
+__device__ __forceinline__ bool is_space(uint32_t c) { return c == ' ' || (c >= 9 && c <= 13); }
+
+__global__ void __launch_bounds__(256)
+records_kseq_kernel(const uint8_t *__restrict__ text, uint32_t n, const uint32_t *__restrict__ nl, uint32_t cap_nl,
+                    uint32_t max_records, uint32_t *__restrict__ nlen1, uint32_t *__restrict__ len,
+                    uint32_t *__restrict__ rsize, uint32_t *__restrict__ wsp, uint8_t *__restrict__ rerr, FqWork *W) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t total = W->total;
+    bool capped = false;
+    if (total > cap_nl) { capped = true; total = cap_nl; }
+    uint32_t R = total >> 2;
+    if (R > max_records) { capped = true; R = max_records; }
+    if (capped && r == 0) atomicOr(&W->err, 2u);
+    if (r >= R) return;
+    const uint32_t a = r ? nl[4 * r - 1] + 1 : 0;
+    const uint32_t n0 = nl[4 * r], n1 = nl[4 * r + 1], n2 = nl[4 * r + 2], n3 = nl[4 * r + 3];
+    const uint32_t sl = n1 - n0 - 1, ql = n3 - n2 - 1;
+    const uint32_t L = n0 - a - 1;                   // header without '@'
+    uint32_t ws = 0xffffffffu;
+    for (uint32_t i = 0; i < L; i++) if (is_space(text[a + 1 + i])) { ws = i; break; }
+    const uint32_t name_l = ws == 0xffffffffu ? L : ws;
+    const uint32_t stored = (ws != 0xffffffffu && ws + 1 == L) ? L - 1 : L;      // an empty comment leaves no separator
+    nlen1[r] = stored + 1;
+    len[r] = sl;
+    rsize[r] = name_l + 1 + sl + ql;
+    wsp[r] = ws;
+    uint32_t e = 0;
+    if (text[a] != '@' || text[n1 + 1] != '+' || sl != ql) e = 1;                // kseq: FASTA / "-2 truncated quality"
+    if (sl) {
+        const uint32_t c0 = text[n0 + 1];
+        if (c0 == '@' || c0 == '+' || c0 == '>') e = 1;                          // would end kseq's sequence loop
+        if (text[n1 - 1] == '\r' || text[n3 - 1] == '\r') e = 1;                // CRLF text is not handled here
+    }
+    rerr[r] = (uint8_t)e;
+}
+
+// records taken: the longest prefix whose sizes sum to <= blk_size, one at least.  roff = exclusive
+// prefix of rsize.
+__global__ void __launch_bounds__(256)
+cut_kseq_kernel(const uint32_t *__restrict__ rsize, const uint32_t *__restrict__ roff, uint32_t cap_nl,
+                uint32_t max_records, uint32_t blk_size, FqWork *W) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t R = min(min(W->total, cap_nl) >> 2, max_records);
+    if (r >= R) return;
+    const uint64_t incl = (uint64_t)roff[r] + rsize[r];
+    const bool fits = r == 0 || incl <= blk_size;
+    const bool next_fits = r + 1 < R && (uint64_t)roff[r + 1] + rsize[r + 1] <= blk_size;
+    if (fits && !next_fits) W->cut = r + 1;          // the sums grow with r: exactly one thread
+}
+
+// statistics and checks over the records taken (and the one behind them, which the reference has
+// parsed before it decides to keep it for the next block)
+__global__ void __launch_bounds__(256)
+stats_kseq_kernel(const uint32_t *__restrict__ len, const uint8_t *__restrict__ rerr, uint32_t cap_nl,
+                  uint32_t max_records, FqWork *W) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t R = min(min(W->total, cap_nl) >> 2, max_records), cut = W->cut;
+    uint32_t not_mn = 0, mx = 0, have = 0, e = 0;
+    if (r < cut) { not_mn = ~len[r]; mx = len[r]; have = 1; }
+    if (r <= cut && r < R) e = rerr[r];
+    not_mn = __reduce_max_sync(FULL, not_mn);
+    mx = __reduce_max_sync(FULL, mx);
+    have = __reduce_max_sync(FULL, have);
+    e = __reduce_max_sync(FULL, e);
+    if ((threadIdx.x & 31) == 0) {
+        volatile FqWork *V = W;
+        if (have) {
+            if (not_mn > V->not_minlen) atomicMax(&W->not_minlen, not_mn);
+            if (mx > V->maxlen) atomicMax(&W->maxlen, mx);
+            if (!V->have_len) W->have_len = 1;
+        }
+        if (e) atomicOr(&W->err, 1u);
+    }
+}
+
 __global__ void set_count(FqWork *W, uint32_t cap_nl, uint32_t max_records) {
     uint32_t t = min(W->total, cap_nl) >> 2;
     W->tot[0] = min(t, max_records);
@@ -333,13 +416,15 @@ __global__ void __launch_bounds__(256)
 scatter_kernel(const uint8_t *__restrict__ text, uint32_t n, const uint32_t *__restrict__ nl, uint32_t cap_nl,
                uint32_t max_records, const uint32_t *__restrict__ name_off, const uint32_t *__restrict__ seq_off,
                uint8_t *__restrict__ name, uint8_t *__restrict__ seq, uint8_t *__restrict__ qual, uint32_t name_cap,
-               uint32_t seq_cap, uint32_t *__restrict__ flag, FqWork *W) {
+               uint32_t seq_cap, uint32_t *__restrict__ flag, FqWork *W, const uint32_t *__restrict__ wsp) {
+    // wsp != null: kseq mode -- the records taken are W->cut, names are stored in kseq's form (separator
+    // -> ' ', dropped before an empty comment) and READ2 follows fqzcomp5.c:512-520
     __shared__ uint32_t s_nl[4 * GREC + 1];      // newline in front of the group, then the group's own
     __shared__ uint32_t s_no[GREC], s_so[GREC];
     __shared__ __align__(16) uint8_t s_text[SPAN_CAP + 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t total = min(W->total, cap_nl);
-    const uint32_t R = min(total >> 2, max_records) - W->drop_last;
+    const uint32_t R = wsp ? W->cut : min(total >> 2, max_records) - W->drop_last;
     const uint32_t r0 = blockIdx.x * GREC;
     if (r0 >= R) return;
     const uint32_t g = min(GREC, R - r0);
@@ -366,6 +451,37 @@ scatter_kernel(const uint8_t *__restrict__ text, uint32_t n, const uint32_t *__r
         const uint32_t no = s_no[j], so = s_so[j];
         if (byte_at(a) != '@' || byte_at(n1 + 1) != '+') err |= 1u;           // fqzcomp5.c:302-304, :351-352
         if ((uint64_t)no + L + 1 > name_cap || (uint64_t)so + sl > seq_cap) { err |= 2u; continue; }
+        if (wsp) {
+            // kseq's stored name: header with its first isspace() byte turned into ' ', or cut there
+            // when nothing follows it (an empty comment, fqzcomp5.c:487-507)
+            const uint32_t ws = wsp[r];
+            const uint32_t Ls = (ws != 0xffffffffu && ws + 1 == L) ? L - 1 : L;
+            copy(name + no, a + 1, Ls, 0);
+            __syncwarp();
+            if (lane == 0) { if (ws < Ls) name[no + ws] = ' '; name[no + Ls] = 0; }
+            copy(seq + so, n0 + 1, sl, 0);
+            copy(qual + so, n2 + 1, sl, 0xdfdfdfdfu);                         // - 33 (fqzcomp5.c:563-564)
+            // READ2 (:512-520): the stored string ends in "/2" (name longer than one byte), or equals the
+            // previous record's stored string
+            const uint32_t name_l = ws == 0xffffffffu ? L : ws;
+            bool f = name_l > 1 && Ls >= 2 && byte_at(a + Ls) == '2' && byte_at(a + Ls - 1) == '/';
+            if (!f && r) {
+                uint32_t pa, pn0;
+                if (j) { pa = s_nl[4 * j - 4] + 1; pn0 = s_nl[4 * j - 3]; }
+                else { pa = r > 1 ? nl[4 * r - 5] + 1 : 0; pn0 = nl[4 * r - 4]; }
+                const uint32_t pL = pn0 - pa - 1, pws = wsp[r - 1];
+                const uint32_t pLs = (pws != 0xffffffffu && pws + 1 == pL) ? pL - 1 : pL;
+                bool same = pLs == Ls && (pws < pLs ? pws : 0xffffffffu) == (ws < Ls ? ws : 0xffffffffu);
+                if (same) {
+                    bool eq = true;     // separators sit at the same place: compare everything else
+                    for (uint32_t i = lane; i < Ls; i += 32) eq = eq && (i == ws || text[a + 1 + i] == text[pa + 1 + i]);
+                    same = __all_sync(FULL, eq);
+                }
+                f = same;
+            }
+            if (lane == 0) flag[r] = f ? FREAD2 : 0u;
+            continue;
+        }
         copy(name + no, a + 1, L, 0);
         if (lane == 0) name[no + L] = 0;
         copy(seq + so, n0 + 1, sl, 0);
@@ -393,9 +509,12 @@ scatter_kernel(const uint8_t *__restrict__ text, uint32_t n, const uint32_t *__r
 
 __global__ void split_finalize(const uint32_t *nl, uint32_t cap_nl, uint32_t max_records, const uint32_t *name_off,
                                const uint32_t *seq_off, const uint32_t *nlen1, const uint32_t *len, FqWork *W,
-                               FqInfo *info) {
+                               FqInfo *info, int kseq) {
     uint32_t total = min(W->total, cap_nl);
-    uint32_t R = min(total >> 2, max_records) - W->drop_last;
+    uint32_t R = kseq ? W->cut : min(total >> 2, max_records) - W->drop_last;
+    // kseq mode: 1 when the block-size rule ended the block (a complete record was left for the next one),
+    // 0 when the text ran out first (the caller appends more text and calls again, unless the file ended)
+    info->more = kseq ? (R < min(total >> 2, max_records) ? 1u : 0u) : 0u;
     info->status = (W->err & 1u) ? 1 : (W->err & 2u) ? 2 : 0;
     info->num_records = R;
     info->name_len = R ? name_off[R - 1] + nlen1[R - 1] : 0;
@@ -478,7 +597,7 @@ inline uint32_t cdivu(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct SplitLayout {
-    size_t work, tile_cnt, tile_off, masks, nl, nlen1, sums0, sums1, toff0, toff1, total;
+    size_t work, tile_cnt, tile_off, masks, nl, nlen1, sums0, sums1, toff0, toff1, rsize, roff, wsp, rerr, sums2, toff2, total;
     uint32_t ntiles, cap_nl, stiles;
     SplitLayout(uint32_t n, uint32_t max_records) {
         ntiles = cdivu(n ? n : 1, TILE);
@@ -495,6 +614,13 @@ struct SplitLayout {
         sums1 = o; o += al256((size_t)stiles * 4);
         toff0 = o; o += al256((size_t)stiles * 4);
         toff1 = o; o += al256((size_t)stiles * 4);
+        // kseq mode: record sizes, their prefix, separator positions, per-record verdicts
+        rsize = o; o += al256((size_t)max_records * 4 + 4);
+        roff = o; o += al256((size_t)max_records * 4 + 4);
+        wsp = o; o += al256((size_t)max_records * 4 + 4);
+        rerr = o; o += al256((size_t)max_records + 4);
+        sums2 = o; o += al256((size_t)stiles * 4);
+        toff2 = o; o += al256((size_t)stiles * 4);
         total = o;
     }
 };
@@ -506,7 +632,7 @@ size_t fq_split_scratch_bytes(uint32_t n, uint32_t max_records) { return SplitLa
 cudaError_t fq_split_launch(const uint8_t *d_text, uint32_t n, uint8_t *d_name, uint8_t *d_seq, uint8_t *d_qual,
                             uint32_t name_cap, uint32_t seq_cap, uint32_t *d_len, uint32_t *d_flag,
                             uint32_t *d_name_off, uint32_t *d_seq_off, uint32_t max_records, uint8_t *S,
-                            FqInfo *d_info, cudaStream_t st, int *launches) {
+                            FqInfo *d_info, cudaStream_t st, int *launches, int kseq, uint32_t blk_size) {
     SplitLayout L(n, max_records);
     FqWork *W = (FqWork *)(S + L.work);
     uint32_t *tile_cnt = (uint32_t *)(S + L.tile_cnt), *tile_off = (uint32_t *)(S + L.tile_off);
@@ -519,16 +645,32 @@ cudaError_t fq_split_launch(const uint8_t *d_text, uint32_t n, uint8_t *d_name, 
     count_kernel<true><<<L.ntiles, TPB, 0, st>>>(d_text, n, '\n', tile_cnt, masks, W);
     scan_small<<<1, 1024, 0, st>>>(tile_cnt, tile_off, &W->total, nullptr, nullptr, nullptr, L.ntiles, nullptr, 0, 1);
     mark_kernel<<<L.ntiles, TPB, 0, st>>>(masks, tile_off, nl, L.cap_nl);
-    records_kernel<<<cdivu(max_records + 1, 256), 256, 0, st>>>(d_text, n, nl, L.cap_nl, max_records, nlen1, d_len, W);
+    uint32_t *rsize = (uint32_t *)(S + L.rsize), *roff = (uint32_t *)(S + L.roff), *wsp = (uint32_t *)(S + L.wsp);
+    uint8_t *rerr = S + L.rerr;
+    if (kseq)
+        records_kseq_kernel<<<cdivu(max_records + 1, 256), 256, 0, st>>>(d_text, n, nl, L.cap_nl, max_records, nlen1,
+                                                                       d_len, rsize, wsp, rerr, W);
+    else
+        records_kernel<<<cdivu(max_records + 1, 256), 256, 0, st>>>(d_text, n, nl, L.cap_nl, max_records, nlen1, d_len, W);
     // element count of the offset scans (a held-back last record is scanned too, harmlessly)
     set_count<<<1, 1, 0, st>>>(W, L.cap_nl, max_records);
+    if (kseq) {
+        // the block-size rule: prefix of the record sizes, the cut, then statistics over the records taken
+        uint32_t *sums2 = (uint32_t *)(S + L.sums2), *toff2 = (uint32_t *)(S + L.toff2);
+        scan_reduce<<<L.stiles, 256, 0, st>>>(rsize, nullptr, &W->tot[0], max_records, sums2, nullptr);
+        scan_small<<<1, 1024, 0, st>>>(sums2, toff2, nullptr, nullptr, nullptr, nullptr, 0, &W->tot[0], max_records, STILE);
+        scan_apply<<<L.stiles, 256, 0, st>>>(rsize, nullptr, &W->tot[0], max_records, toff2, nullptr, roff, nullptr);
+        cut_kseq_kernel<<<cdivu(max_records + 1, 256), 256, 0, st>>>(rsize, roff, L.cap_nl, max_records, blk_size, W);
+        stats_kseq_kernel<<<cdivu(max_records + 1, 256), 256, 0, st>>>(d_len, rerr, L.cap_nl, max_records, W);
+        if (launches) *launches += 5;
+    }
     scan_reduce<<<L.stiles, 256, 0, st>>>(nlen1, d_len, &W->tot[0], max_records, sums0, sums1);
     scan_small<<<1, 1024, 0, st>>>(sums0, toff0, nullptr, sums1, toff1, nullptr, 0, &W->tot[0], max_records, STILE);
     scan_apply<<<L.stiles, 256, 0, st>>>(nlen1, d_len, &W->tot[0], max_records, toff0, toff1, d_name_off, d_seq_off);
     scatter_kernel<<<cdivu(max_records ? max_records : 1, GREC), 256, 0, st>>>(
         d_text, n, nl, L.cap_nl, max_records, d_name_off, d_seq_off, d_name, d_seq, d_qual, name_cap, seq_cap,
-        d_flag, W);
-    split_finalize<<<1, 1, 0, st>>>(nl, L.cap_nl, max_records, d_name_off, d_seq_off, nlen1, d_len, W, d_info);
+        d_flag, W, kseq ? wsp : nullptr);
+    split_finalize<<<1, 1, 0, st>>>(nl, L.cap_nl, max_records, d_name_off, d_seq_off, nlen1, d_len, W, d_info, kseq);
     if (launches) *launches += 10;
     return cudaGetLastError();
 }

@@ -16,13 +16,16 @@ struct FqInfo {
     int32_t  fixed_len;     // fq->fixed_len: -1 nothing seen, L > 0 all reads L long, else 0
     uint32_t consumed;      // *last_offset: where the first record not taken starts
     uint32_t text_len;      // join: bytes of FASTQ text produced
+    uint32_t more;          // split, kseq mode: 1 = the block-size rule ended the block, 0 = the text ran out
 };
 
 size_t fq_split_scratch_bytes(uint32_t n, uint32_t max_records);
 cudaError_t fq_split_launch(const uint8_t *d_text, uint32_t n, uint8_t *d_name, uint8_t *d_seq, uint8_t *d_qual,
                             uint32_t name_cap, uint32_t seq_cap, uint32_t *d_len, uint32_t *d_flag,
                             uint32_t *d_name_off, uint32_t *d_seq_off, uint32_t max_records, uint8_t *d_scratch,
-                            FqInfo *d_info, cudaStream_t st, int *launches);
+                            FqInfo *d_info, cudaStream_t st, int *launches, int kseq = 0, uint32_t blk_size = 0);
+// kseq != 0: load_seqs_kseq's rules (fqzcomp5.c:423-623) for strict 4-line FASTQ -- kseq's name / comment
+// split, records taken while name.l + 1 + seq.l + qual.l sums to <= blk_size (one at least).
 
 size_t fq_join_scratch_bytes(uint32_t name_len, uint32_t num_records);
 cudaError_t fq_join_launch(const uint8_t *d_name, uint32_t name_len, const uint8_t *d_seq, const uint8_t *d_qual,

@@ -265,7 +265,31 @@ typedef struct {
     int32_t  fixed_len;     /* -1 nothing seen, L > 0 every read L long, else 0 */
     uint32_t consumed;      /* split: offset of the first byte not consumed */
     uint32_t text_len;      /* join: bytes of text produced */
+    uint32_t more;          /* split, kseq mode: 1 = the block-size rule ended the block (records are left for
+                               the next one), 0 = the text ran out first */
 } b200fq_info;
+
+/* The live loader, load_seqs_kseq (fqzcomp5.c:423-623; main() reaches only this one, through encode_gzip
+ * :3051): B200FQ_MODE_KSEQ applies its rules to strict 4-line FASTQ text --
+ *   - kseq's record (kseq.h:176-218): name = header up to its first isspace() byte, comment = the rest;
+ *     the stored name is name [+ ' ' + comment unless that is empty] (a tab becomes a space, a trailing
+ *     separator is dropped, fqzcomp5.c:485-510);
+ *   - a block takes records while name.l + 1 + seq.l + qual.l sums to <= blk_size, one at least
+ *     (:468-476); `consumed` is where the first record left for the next block starts, info.more tells
+ *     whether the rule or the end of the text stopped it;
+ *   - FQZ_FREAD2: stored name ends in "/2" (name longer than one byte) or equals the previous one (:512-520);
+ *   - fixed_len over the records taken (:536-541).
+ * Not handled, reported as status 1: multi-line records, FASTA ('>' headers or no quality line; the
+ * reference switches to is_fasta, :566-571), sequence lines starting with '@', '+' or '>', CRLF line
+ * ends, base / quality lengths that differ (kseq would read further quality lines or return -2), and a
+ * last record without its newline.  The record behind the last one taken is checked too, as the
+ * reference has parsed it before it keeps it for the next block. */
+#define B200FQ_MODE_LOAD_SEQS 0
+#define B200FQ_MODE_KSEQ      1
+int b200fq_split_mode(int mode, uint32_t blk_size, const unsigned char *text, uint32_t n,
+                      unsigned char *name, uint32_t name_cap,
+                      unsigned char *seq, unsigned char *qual, uint32_t seq_cap,
+                      uint32_t *len, uint32_t *flag, uint32_t max_records, b200fq_info *info);
 
 /* Host buffers (pinned for full PCIe rate).  name_cap / seq_cap bytes are
  * available in name / seq and qual; n bytes each are always enough.  len and
@@ -289,6 +313,11 @@ int b200fq_split_dev(void *stream, const unsigned char *d_text, uint32_t n,
                      unsigned char *d_seq, unsigned char *d_qual, uint32_t seq_cap,
                      uint32_t *d_len, uint32_t *d_flag, uint32_t *d_name_off, uint32_t *d_seq_off,
                      uint32_t max_records, void *d_scratch, size_t scratch_bytes, b200fq_info *d_info);
+int b200fq_split_dev_mode(void *stream, int mode, uint32_t blk_size, const unsigned char *d_text, uint32_t n,
+                          unsigned char *d_name, uint32_t name_cap,
+                          unsigned char *d_seq, unsigned char *d_qual, uint32_t seq_cap,
+                          uint32_t *d_len, uint32_t *d_flag, uint32_t *d_name_off, uint32_t *d_seq_off,
+                          uint32_t max_records, void *d_scratch, size_t scratch_bytes, b200fq_info *d_info);
 size_t b200fq_join_scratch_bytes(uint32_t name_len, uint32_t num_records);
 int b200fq_join_dev(void *stream, const unsigned char *d_name, uint32_t name_len,
                     const unsigned char *d_seq, const unsigned char *d_qual,
@@ -363,6 +392,8 @@ typedef struct {
     int name_methods[B200FQZ_MAX_METHODS], seq_methods[B200FQZ_MAX_METHODS], qual_methods[B200FQZ_MAX_METHODS];
     b200fqz_name_coder name_coder;
     void *name_user;
+    uint32_t kseq_blk_size;     /* 0: load_seqs' block rule (the text given IS the block); > 0: B200FQ_MODE_KSEQ
+                                   with this blk_size, rep->consumed tells where the next block starts */
 } b200fqz_block_opts;
 
 typedef struct {

@@ -136,7 +136,7 @@ def fastq_available(kind):
 class FqInfo(C.Structure):
     _fields_ = [("status", C.c_int32), ("num_records", C.c_uint32), ("name_len", C.c_uint32),
                 ("seq_len", C.c_uint32), ("qual_len", C.c_uint32), ("fixed_len", C.c_int32),
-                ("consumed", C.c_uint32), ("text_len", C.c_uint32)]
+                ("consumed", C.c_uint32), ("text_len", C.c_uint32), ("more", C.c_uint32)]
 
 
 class _RefFastq(C.Structure):          # `fastq`, fqzcomp5.c:235-249
@@ -167,11 +167,18 @@ class FastqChecker:
             L.fqo_split.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 5 + [C.POINTER(FqInfo)]
             L.fqo_join.argtypes = [C.c_void_p] * 4 + [C.c_uint32, C.c_int, C.c_void_p]
             L.fqo_join.restype = C.c_uint32
+            L.fqo_split_kseq.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32] + [C.c_void_p] * 5 + [C.POINTER(FqInfo)]
         else:
             L.load_seqs.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
             L.load_seqs.restype = C.POINTER(_RefFastq)
             L.fastq_free.argtypes = [C.POINTER(_RefFastq)]
             L.output_fastq.argtypes = [C.c_void_p, C.POINTER(_RefFastq), C.c_int]
+            L.load_seqs_kseq.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+            L.load_seqs_kseq.restype = C.POINTER(_RefFastq)
+            self.z = C.CDLL("libz.so.1")
+            self.z.gzopen.argtypes = [C.c_char_p, C.c_char_p]
+            self.z.gzopen.restype = C.c_void_p
+            self.z.gzclose.argtypes = [C.c_void_p]
             _libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
             _libc.fopen.restype = C.c_void_p
             _libc.fclose.argtypes = [C.c_void_p]
@@ -210,6 +217,67 @@ class FastqChecker:
                    flag=[f.flag[i] for i in range(R)], fixed_len=f.fixed_len, consumed=last.value)
         self.lib.fastq_free(fq)
         return out
+
+    def split_kseq(self, text, blk_size):
+        """The blocks the live loader (load_seqs_kseq, fqzcomp5.c:423-623) cuts `text` into with this
+        blk_size: a list of load_seqs-style dicts (`consumed` only from the oracle), or None where it fails."""
+        import numpy as np
+        import tempfile
+        text = bytes(text)
+        n = len(text)
+        blocks = []
+        if self.kind == "oracle":
+            src = C.create_string_buffer(text, max(n, 1))
+            pos = 0
+            while True:
+                m = n - pos
+                name = np.zeros(m + 16, np.uint8); seq = np.zeros(m + 16, np.uint8); qual = np.zeros(m + 16, np.uint8)
+                ln = np.zeros(m // 4 + 16, np.uint32); fl = np.zeros(m // 4 + 16, np.uint32)
+                info = FqInfo()
+                self.lib.fqo_split_kseq(C.addressof(src) + pos, m, blk_size, name.ctypes.data, seq.ctypes.data,
+                                        qual.ctypes.data, ln.ctypes.data, fl.ctypes.data, C.byref(info))
+                if info.status:
+                    return None
+                R = info.num_records
+                if R == 0:
+                    break
+                blocks.append(dict(num_records=R, name=name[:info.name_len].tobytes(),
+                                   seq=seq[:info.seq_len].tobytes(), qual=qual[:info.qual_len].tobytes(),
+                                   len=ln[:R].tolist(), flag=fl[:R].tolist(), fixed_len=info.fixed_len,
+                                   consumed=info.consumed, more=info.more))
+                pos += info.consumed
+                if not info.more:
+                    break
+            return blocks
+        with tempfile.NamedTemporaryFile(delete=False) as t:
+            t.write(text)
+            path = t.name
+        fp = self.z.gzopen(path.encode(), b"rb")
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(2)
+        os.dup2(devnull, 2)
+        try:
+            while True:
+                eof = C.c_int(0)
+                fq = self.lib.load_seqs_kseq(fp, blk_size, C.byref(eof))
+                if not fq:
+                    blocks = None
+                    break
+                f = fq.contents
+                R = f.num_records
+                if R:
+                    blocks.append(dict(num_records=R, name=C.string_at(f.name_buf, f.name_len),
+                                       seq=C.string_at(f.seq_buf, f.seq_len), qual=C.string_at(f.qual_buf, f.qual_len),
+                                       len=[f.len[i] for i in range(R)], flag=[f.flag[i] for i in range(R)],
+                                       fixed_len=f.fixed_len))
+                self.lib.fastq_free(fq)
+                if eof.value or not R:
+                    break
+        finally:
+            os.dup2(saved, 2); os.close(saved); os.close(devnull)
+            self.z.gzclose(fp)
+            os.unlink(path)
+        return blocks
 
     def join(self, name, seq, qual, lens, plus_name=0):
         import numpy as np

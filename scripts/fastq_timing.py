@@ -64,7 +64,7 @@ def main(argv):
     sb = int(L.b200fq_split_scratch_bytes(n, mr))
     d_scr = torch.empty(sb + 256, dtype=torch.uint8, device=dev)
     scr = (d_scr.data_ptr() + 255) & ~255
-    d_info = torch.zeros(8, dtype=torch.int32, device=dev)
+    d_info = torch.zeros(16, dtype=torch.int32, device=dev)
     d_back = torch.empty(n + 64, dtype=torch.uint8, device=dev)
     ts = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(ts)
@@ -86,7 +86,7 @@ def main(argv):
     sj = int(L.b200fq_join_scratch_bytes(name_len, nrec))
     d_scr2 = torch.empty(sj + 256, dtype=torch.uint8, device=dev)
     scr2 = (d_scr2.data_ptr() + 255) & ~255
-    d_info2 = torch.zeros(8, dtype=torch.int32, device=dev)
+    d_info2 = torch.zeros(16, dtype=torch.int32, device=dev)
 
 
     def join():

@@ -45,7 +45,11 @@ for r in rows:
     if not r: continue
     if r[0] == "Kernel Name":
         flush(); kernel = r[1]; agg = collections.defaultdict(lambda: [0, 0]); base = None
-        key = [k for d, k in dm.items() if d.replace("(bool)", "").replace(" ", "") == kernel.replace("(bool)", "").replace(" ", "")]
+        def base_name(x):       # "void b200::enc_kernel<(bool)1>(b200::EncJob *, ...)" -> "b200::enc_kernel<1>"
+            x = x.replace("(bool)", "").replace(" ", "")
+            m2 = re.match(r"(?:void)?([\w:]+(?:<[^()]*>)?)", x)
+            return m2.group(1) if m2 else x
+        key = [k for d, k in dm.items() if base_name(d) == base_name(kernel)]
         lm = linemap[key[0]] if key else {}
         continue
     if r[0] == "Address": hdr = r; continue

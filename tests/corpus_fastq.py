@@ -51,3 +51,37 @@ def edge_cases():
     cases.append(("long_reads", long_reads(12, seed=6)))
     cases.append(("illumina_8k_tile_edges", illumina(300, 150, seed=7)))
     return cases
+
+
+def kseq_cases():
+    """(label, text, blk_size) for the live loader's rules (load_seqs_kseq, fqzcomp5.c:423-623): strict
+    4-line FASTQ ending in a newline -- comments behind spaces and tabs, empty comments, /2 pairs, repeated
+    names, fixed and variable lengths, block sizes that cut after one record, mid-stream and never."""
+    rng = np.random.default_rng(12)
+    base = (b"@r1/1 first comment\nACGT\n+\nIIII\n@r1/2\tcomment after a tab\nACGTA\n+r1\nIIIII\n"
+            b"@dup\nAC\n+\n##\n@dup\nGG\n+\n!!\n@dup \nGG\n+\n!!\n@dup x\nGG\n+\n!!\n@dup\tx\nGG\n+\n!!\n"
+            b"@/2\nA\n+\nI\n@x/2\nAAAAAAAA\n+\nIIIIIIII\n@y c/2\nAC\n+\nII\n@2 /2\nAC\n+\nII\n"
+            b"@a  two spaces\nAC\n+\nII\n@ lead\nAC\n+\nII\n@\n\n+\n\n@e\n\n+\n\n@tab\t\nAC\n+\nII\n")
+    cases = [("kbase_all", base, 1 << 20)]
+    for blk in (1, 7, 12, 13, 14, 30, 31, 64, 200):
+        cases.append(("kbase_blk%d" % blk, base, blk))
+    il = illumina(400, 50, seed=21, paired=True)
+    for blk in (1000, 4096, 10000, len(il), 10 * len(il)):
+        cases.append(("kil_blk%d" % blk, il, blk))
+    var = []
+    for i in range(300):
+        n = int(rng.integers(1, 90))
+        var.append(b"@v%d/%d len=%d\n" % (i // 2, i % 2 + 1, n) + b"ACGT"[i % 4:i % 4 + 1] * n + b"\n+\n" +
+                   bytes(rng.integers(35, 70, n).astype(np.uint8)) + b"\n")
+    var = b"".join(var)
+    for blk in (333, 5000):
+        cases.append(("kvar_blk%d" % blk, var, blk))
+    cases.append(("klong", long_reads(15, seed=8), 30000))
+    cases.append(("kempty", b"", 100))
+    return cases
+
+
+def kseq_bad_cases():
+    """Texts the reference's kseq loader fails on as well (the strict reading reports status 1)."""
+    return [("kbad_qual_long", b"@r1\nAC\n+\nIII\n@r2\nAC\n+\nII\n", 1000),
+            ("kbad_qual_long_next_block", b"@r1\nAC\n+\nII\n@r2\nAC\n+\nIII\n", 3)]

@@ -93,3 +93,20 @@ def test_oracle_matches_reference_on_random_texts(fq_oracle, fq_ref):
         assert a == b, (it, t[:80])
         n_null += a is None
     assert 0 < n_null < 400
+
+
+def _same_blocks(a, b):
+    if a is None or b is None:
+        return a is None and b is None
+    keys = ("num_records", "name", "seq", "qual", "len", "flag", "fixed_len")
+    return len(a) == len(b) and all(all(x[k] == y[k] for k in keys) for x, y in zip(a, b))
+
+
+def test_kseq_oracle_matches_reference(fq_oracle, fq_ref):
+    """fqo_split_kseq against the unmodified load_seqs_kseq (fqzcomp5.c:423-623, the loader main() reaches),
+    called block after block on the same file as encode_gzip does (:3051)."""
+    for label, text, blk in corpus_fastq.kseq_cases() + corpus_fastq.kseq_bad_cases():
+        a, b = fq_oracle.split_kseq(text, blk), fq_ref.split_kseq(text, blk)
+        assert _same_blocks(a, b), (label, a if a is None else len(a), b if b is None else len(b))
+        if a:
+            assert sum(x["consumed"] for x in a) == len(text), label      # every byte of a well-formed file is taken

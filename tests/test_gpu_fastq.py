@@ -103,7 +103,7 @@ def test_device_resident_split_feeds_codec(gpu_codec, checker):
     sb = int(L.b200fq_split_scratch_bytes(n, mr))
     d_scr = torch.empty(sb + 256, dtype=torch.uint8, device=dev)
     scr = (d_scr.data_ptr() + 255) & ~255
-    d_info = torch.zeros(8, dtype=torch.int32, device=dev)
+    d_info = torch.zeros(16, dtype=torch.int32, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     rc = L.b200fq_split_dev(st, d_text.data_ptr(), n, d_name.data_ptr(), n, d_seq.data_ptr(), d_qual.data_ptr(), n,
                             d_len.data_ptr(), d_flag.data_ptr(), d_no.data_ptr(), d_so.data_ptr(), mr, scr, sb,
@@ -130,3 +130,58 @@ def test_device_resident_split_feeds_codec(gpu_codec, checker):
     out = d_out.cpu().numpy()
     for j in (0, k // 2, k - 1):
         assert out[off[j]:off[j] + sz[j]].tobytes() == checker.compress(want["qual"][j * S:(j + 1) * S], 5)
+
+
+def _gpu_kseq_blocks(gpu_codec, text, blk):
+    """load_seqs_kseq's blocks of a text, one GPU call per block, each fed from where the last one stopped
+    (and only as much text as a caller reading ahead would have: a little more than the block needs)."""
+    pos, out = 0, []
+    while True:
+        r = gpu_codec.load_seqs_kseq(text[pos:], blk)
+        if r is None:
+            return None
+        if r["num_records"] == 0:
+            break
+        out.append(r)
+        pos += r["consumed"]
+        if not r["more"]:
+            break
+    return out
+
+
+def test_kseq_mode_matches_live_loader(gpu_codec, fq_checker):
+    """B200FQ_MODE_KSEQ against load_seqs_kseq (fqzcomp5.c:423-623), the loader main() really reaches:
+    kseq's name / comment split and re-join, the block-size rule with its buffered record, READ2, fixed_len."""
+    keys = ("num_records", "name", "seq", "qual", "len", "flag", "fixed_len")
+    big = corpus_fastq.illumina(30000, 150, seed=31, paired=True)
+    cases = corpus_fastq.kseq_cases() + corpus_fastq.kseq_bad_cases() + [("kbig", big, 1 << 20), ("kbig_all", big, 1 << 30)]
+    for label, text, blk in cases:
+        want = fq_checker.split_kseq(text, blk)
+        got = _gpu_kseq_blocks(gpu_codec, text, blk)
+        if want is None or got is None:
+            assert want is None and got is None, label
+            continue
+        assert len(got) == len(want), (label, len(got), len(want))
+        for i, (g, w) in enumerate(zip(got, want)):
+            for k in keys:
+                assert g[k] == w[k], (label, i, k)
+        assert sum(g["consumed"] for g in got) == len(text), label
+
+
+def test_block_call_in_kseq_mode(gpu_codec, fq_checker):
+    """b200fqz_encode_block with kseq_blk_size: a file walked block by block as encode_gzip does (:3051-3077),
+    every block decoding back to the text it consumed (names without comments: join restores the header)."""
+    text = corpus_fastq.illumina(4000, 100, seed=41, paired=True)
+    blk = 150000
+    want = fq_checker.split_kseq(text, blk)
+    opts = gpu_codec.block_opts(slice_bytes=65536, x32=True)
+    opts.kseq_blk_size = blk
+    pos = 0
+    for i, w in enumerate(want):
+        block, rep = gpu_codec.encode_block(text[pos:pos + 2 * blk + 4096], opts)
+        assert rep.status == 0 and rep.num_records == w["num_records"], i
+        assert (rep.ulen[0], rep.ulen[1], rep.ulen[2]) == (len(w["name"]), len(w["seq"]), len(w["qual"])), i
+        back, drep = gpu_codec.decode_block(block, 3 * blk)
+        assert drep.status == 0 and back.tobytes() == text[pos:pos + rep.consumed], i
+        pos += rep.consumed
+    assert pos == len(text)
