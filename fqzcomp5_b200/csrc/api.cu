@@ -121,8 +121,9 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
     size_t o_jobs = L.take(njobs * sizeof(EncJob));
     size_t o_ctr = L.take(256);
     size_t o_par = L.take(stripes.size() * 4 + 4);
-    uint32_t n_o0 = 0, n_o1 = 0, n_o1w = 0, n_model = 0;
+    uint32_t n_o0 = 0, n_o1 = 0, n_o1w = 0, n_model = 0, n_prep = 0;
     size_t pool_bytes = 0;
+    const bool prep = use_prep();
     // ---- pass 2: place slots / work buffers
     auto place = [&](size_t j, const uint8_t *in, uint32_t isz, int ord, uint32_t cap, uint32_t item, bool parent) {
         EncJob &J = jobs[j];
@@ -136,8 +137,11 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
         if (inslot && item != 0xffffffffu) { J.slot = (uint8_t *)LO.take(slot_bytes, 256); in_out[j] = 1; }
         else J.slot = (uint8_t *)L.take(slot_bytes, 256);
         if (parent) return;
-        if (ord & (X_PACK | X_RLE)) J.work = (uint8_t *)L.take((size_t)isz * 4 + isz / 4 + 8192, 256);
-        else if (isz >= hist_min_bytes((ord & 1) != 0)) {
+        if (ord & (X_PACK | X_RLE)) {
+            J.work = (uint8_t *)L.take((size_t)isz * 4 + isz / 4 + 8192, 256);
+            // transforms, counts and the order-1 model by one CTA per stream, in front of the coder warp
+            if (prep && isz && !(ord & X_CAT)) { J.prep = (uint8_t *)(L.take(prep_area_bytes(isz), 256) + 1); n_prep++; }
+        } else if (isz >= hist_min_bytes((ord & 1) != 0)) {
             // big plain streams: counts come from hist_kernel (order-1: up to (isz+1)^2 or 256^2 pairs)
             size_t pairs = ((ord & 1) && isz >= 8) ? std::min<size_t>(65536, ((size_t)isz + 1) * (isz + 1)) : 0;
             J.model = (uint32_t *)(L.take((MODEL_HDR_WORDS + pairs) * 4, 256) + 1);   // +1: null stays null
@@ -146,14 +150,16 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
         if ((ord & 1) && isz >= 8) {
             // the order-1 kernel (larger shared memory per warp); transformed streams get the launch
             // with room for the partitioned pair count
-            J.route = (ord & (X_PACK | X_RLE)) ? ROUTE_O1_WIDE : ROUTE_O1;
+            J.route = ((ord & (X_PACK | X_RLE)) && !J.prep) ? ROUTE_O1_WIDE : ROUTE_O1;
             if (J.route == ROUTE_O1_WIDE) n_o1w++;
             n_o1++;
             // symbol table (16 B/pair), pair counts (4 B/pair), coded table scratch
-            // + 16-bit pair keys of the partitioned pair count (large alphabets without a model)
+            // + 16-bit pair keys of the partitioned pair count (large alphabets without a model);
+            // prepared streams bring their own areas
             const size_t m = std::min<size_t>(256, (size_t)isz + 1);       // alphabet of a short stream
-            pool_bytes += m * m * 12 + std::min<size_t>(300 * 1024, 5 * (size_t)isz + 8192) + 2048 +
-                          (J.model ? 0 : 2 * (size_t)isz + 2048);
+            if (!J.prep)
+                pool_bytes += m * m * 12 + std::min<size_t>(300 * 1024, 5 * (size_t)isz + 8192) + 2048 +
+                              (J.model ? 0 : 2 * (size_t)isz + 2048);
         } else n_o0++;
     };
     size_t si = 0;
@@ -195,6 +201,7 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
         J.slot = (in_out[j] ? d_out + out_adj : W) + (size_t)J.slot;
         if (J.work) J.work = W + (size_t)J.work;
         if (J.model) J.model = (uint32_t *)(W + ((size_t)J.model - 1));
+        if (J.prep) J.prep = W + ((size_t)J.prep - 1);
     }
     for (auto &sp : stripes)
         for (uint32_t s2 = 0; s2 < sp.nsub; s2++) {
@@ -218,6 +225,8 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
 
     // ---- STRIPE: transpose parents into their sub-stream inputs (one launch for all of them)
     if (npar) { CK(launch_stripe_split_batch(d_jobs, d_par, npar, max_stripe_in, st)); C.launches++; }
+    // ---- PACK / RLE streams: transforms, counts, order-1 models (one CTA per stream)
+    if (n_prep) { CK(launch_prep(d_jobs, (uint32_t)njobs, st)); C.launches++; }
     // ---- histograms of the plain streams at full occupancy
     if (n_model) { CK(launch_hist(d_jobs, (uint32_t)njobs, st)); C.launches++; }
     // ---- encode: order-0 streams on the lean kernel, the rest on the order-1 kernel

@@ -41,7 +41,8 @@ struct EncJob {
                             //     job at parent + 1 + i * stripe_nmeth + j
     uint32_t *model;        // counts precomputed by hist_kernel, or null (the coder counts itself):
                             //   [256] order-0 counts, [MODEL_HDR_WORDS..] order-1 pair counts in rank space
-    uint64_t pad2_;
+    uint8_t *prep;          // PACK / RLE streams: the area prep_kernel fills (prep.cuh), or null (the coder warp
+                            //   does the transforms and the model itself)
 };
 enum : uint32_t {
     ROUTE_O0 = 0,           // order-0 kernel

@@ -8,6 +8,7 @@
 #include "rans_decode.cuh"
 #include "rans_encode.cuh"
 #include "transforms.cuh"
+#include "prep.cuh"
 
 namespace b200 {
 
@@ -36,6 +37,8 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
     const uint8_t *in = J.in;
     uint32_t in_size = J.in_size;
     uint8_t *out = J.slot;
+    // PACK / RLE streams: transforms, counts and the order-1 model may have been done by prep_kernel (prep.cuh)
+    const Prep *P = (J.prep && ((const Prep *)J.prep)->state == 1) ? (const Prep *)J.prep : nullptr;
     CapCheck cc{J.cap, 1, J.cap != 0};            // (out && *out_size == 0) -> NULL (:1227)
     uint32_t status = ST_OK;
     uint32_t head_len = 0, tail_len = 0;
@@ -72,7 +75,9 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
         } else if (do_pack && in_size) {                                  // :1429-1459
             cc.require((uint64_t)meta + 256);
             uint32_t pmeta = 0, plen = 0;
-            bool packed = work && warp_pack(in, in_size, out + meta, &pmeta, work, &plen, smem, lane);
+            bool packed;
+            if (P) { packed = P->packed != 0; pmeta = P->pmeta; plen = P->plen; }
+            else packed = work && warp_pack(in, in_size, out + meta, &pmeta, work, &plen, smem, lane);
             if (!packed) flag &= ~X_PACK;
             else {
                 in = work; work += (plen + 15) & ~15u;
@@ -91,7 +96,8 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
             // work: [literals in_size][meta in_size+257+16]
             uint8_t *lits = work, *rmeta = work + ((in_size + 15) & ~15u);
             uint32_t rle_len = 0, rmeta_len = 0;
-            warp_rle_encode(in, in_size, lits, &rle_len, rmeta, &rmeta_len, smem, lane);
+            if (P) { rle_len = P->rle_len; rmeta_len = P->rmeta_len; }
+            else warp_rle_encode(in, in_size, lits, &rle_len, rmeta, &rmeta_len, smem, lane);
             if ((double)((uint64_t)rle_len + rmeta_len) >= .99 * (double)in_size) {
                 flag &= ~X_RLE; do_rle = 0;
             } else {
@@ -134,6 +140,7 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
         } else if (do_rle) flag &= ~X_RLE;
 
         if (in != J.in) model = nullptr;
+        if (P && P->model) model = P->F;                                  // counts of the data as it is now
         cc.require((uint64_t)meta + szq);                                 // :1538
         if (o1 && in_size < 8) { flag &= ~1u; o1 = 0; }                   // :1547
         cc.require((uint64_t)compress_bound(in_size, o1) - 20 + meta + szq);   // bound > *out_size in the coder
@@ -147,8 +154,14 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
                 EncO1Smem &S = *(EncO1Smem *)smem;
                 uint8_t *dyn = smem + sizeof(EncO1Smem);
                 uint32_t dynb = smem_bytes - (uint32_t)sizeof(EncO1Smem);
-                e = do_simd ? enc_o1<32>(in, in_size, out + meta, oend, &tab, &ptr, S, dyn, dynb, pool, lane, model)
-                            : enc_o1<4>(in, in_size, out + meta, oend, &tab, &ptr, S, dyn, dynb, pool, lane, model);
+                if (P && P->model == 2)
+                    e = do_simd ? enc_o1_prepped<32>(in, in_size, out + meta, oend, &tab, &ptr, S, dyn, dynb, *P, J.prep, J.in_size, lane)
+                                : enc_o1_prepped<4>(in, in_size, out + meta, oend, &tab, &ptr, S, dyn, dynb, *P, J.prep, J.in_size, lane);
+                else {
+                    if (P) model = nullptr;       // the order-1 coder's own model layout differs from Prep::F
+                    e = do_simd ? enc_o1<32>(in, in_size, out + meta, oend, &tab, &ptr, S, dyn, dynb, pool, lane, model)
+                                : enc_o1<4>(in, in_size, out + meta, oend, &tab, &ptr, S, dyn, dynb, pool, lane, model);
+                }
             } else if (o1) {
                 e = 3;      // order-1 stream routed to the order-0-only kernel: host bug
             } else {
@@ -556,6 +569,23 @@ hist_kernel(EncJob *jobs, uint32_t njobs) {
         __syncthreads();
         for (uint32_t j = tid; j < hw; j += HIST_THREADS) gH[j] = Hs[j];
     }
+}
+
+// PACK / RLE streams: one CTA per stream does everything in front of the state chains (prep.cuh)
+__global__ void __launch_bounds__(PREP_THREADS, 4)
+prep_kernel(EncJob *jobs, uint32_t njobs) {
+    __shared__ PrepSmem S;
+    const uint32_t j = blockIdx.x;
+    if (j >= njobs || !jobs[j].prep) return;
+    prep_stream(jobs[j], S);
+}
+
+size_t prep_area_bytes(uint32_t in_size) { return prep_plan(in_size).total; }
+
+cudaError_t launch_prep(EncJob *d_jobs, uint32_t n, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    prep_kernel<<<n, PREP_THREADS, 0, st>>>(d_jobs, n);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_hist(EncJob *d_jobs, uint32_t n, cudaStream_t st) {

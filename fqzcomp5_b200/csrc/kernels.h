@@ -20,6 +20,9 @@ constexpr uint32_t DEC_SMEM_O0 = 8192;     // DecO0Smem, 8 KiB aligned
 constexpr uint32_t DEC_SMEM_O1 = 8192;     // DecO1Smem header + 16-bit cumulative rows + 64-bucket index for <= 41 symbols (26 warps per SM: measured 1.35x over 15 KiB / 256 buckets)
 
 cudaError_t launch_hist(EncJob *d_jobs, uint32_t n, cudaStream_t st);
+// PACK / RLE streams with a prep area: transforms, counts and the order-1 model by one CTA per stream
+cudaError_t launch_prep(EncJob *d_jobs, uint32_t n, cudaStream_t st);
+size_t prep_area_bytes(uint32_t in_size);
 cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, uint32_t route, Pool pool, cudaStream_t st, bool inslot = false);
 cudaError_t launch_dec(DecJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStream_t st);
 // method trial: items first[k]..first[k+1]-1 are the candidates of input k -> sizes of all, first smallest kept

@@ -1,0 +1,750 @@
+// prep.cuh -- everything in front of the state chains of a PACK / RLE stream, done by a whole
+// CTA (8 warps) per stream instead of the stream's coder warp: PACK, the RLE symbol choice and
+// split, the order-0 counts and -- for order-1 streams -- the complete model: pair counts, the
+// precision decision, the 256 x normalise_freq, the serialised table and the encoder symbols.
+// The coder warp (enc_stream in kernels.cu) then only assembles the header and runs the chains
+// (run-length meta-data, table self-compression, payload).
+//
+// Reference behaviour restated here (never its code):
+//   pack.c:56-147 (hts_pack), rle.c:48-138 (symbol choice, encode),
+//   rANS_static16_int.h:312-421 (encode_freq1), rANS_static4x16pr.c:357-420 (rans_compute_shift),
+//   utils.h:279-357 (hist1_4).
+#pragma once
+#include "common.cuh"
+#include "rans_encode.cuh"
+
+namespace b200 {
+
+constexpr int PREP_THREADS = 256, PREP_WARPS = 8;
+constexpr uint32_t PREP_PAIRS = 6400;           // words of pair counters in shared memory (a group of context rows)
+
+// What the CTA leaves for the coder warp, at the head of the job's prep area (J.prep).
+struct __align__(16) Prep {
+    uint32_t state;         // 0: not prepared (the coder warp does everything itself), 1: ready
+    uint32_t packed;        // PACK: 1 applied (pack.c returned a buffer), 0 refused (> 16 symbols)
+    uint32_t pmeta, plen;   // PACK: bytes of its meta-data (already at slot + meta), packed length
+    uint32_t rle_len, rmeta_len;    // RLE: literals and meta-data bytes as hts_rle_encode returns them
+    uint32_t model;         // 0 none, 1 order-0 counts in F, 2 order-1 model (table, symbols, rank)
+    uint32_t nsym, shift, tl;       // order 1: alphabet size, precision, bytes of the uncompressed table
+    uint32_t err;           // order 1: normalise_freq failed (the reference returns NULL)
+    uint32_t pad_[5];
+    uint32_t F[256];        // order-0 counts of the data that reaches the coder
+    uint8_t  rank[256];     // order 1: symbol -> rank
+};
+// layout of the prep area behind the header
+struct PrepPlan { uint32_t o_H, o_sym, o_tbl, o_tmp, total; };
+__host__ __device__ inline PrepPlan prep_plan(uint32_t isz) {
+    const uint32_t m = isz + 1 < 256 ? isz + 1 : 256;                      // alphabet of a short stream
+    const uint32_t hw = m * m * 4;
+    const uint32_t tbl = (4 * (uint64_t)isz + 2048 < 257 * 257 * 3 + 4 ? 4 * isz + 2048 : 257 * 257 * 3 + 4) + 64;
+    PrepPlan p;
+    p.o_H = (uint32_t)((sizeof(Prep) + 255) & ~255u);
+    p.o_sym = p.o_H + ((hw + 255) & ~255u);
+    p.o_tbl = p.o_sym + ((hw + 255) & ~255u);
+    p.o_tmp = p.o_tbl + ((tbl + 255) & ~255u);                              // scratch of the table's order-0 coder
+    p.total = p.o_tmp + ((compress_bound(tbl, 0) + 64 + 255) & ~255u);
+    return p;
+}
+
+struct __align__(16) PrepSmem {
+    uint32_t Fw[PREP_WARPS][256];   // warp-private order-0 bins; PACK: byte flags / codes in Fw[0]; RLE: scores in Fw[1];
+                                    // order 1: per-warp scratch of the greedy shave
+    uint32_t Hs[PREP_PAIRS];        // pair counters of one group of context rows
+    uint32_t T[256];                // order-0 counts (symbol space), then row totals (rank space)
+    uint32_t rowlen[256];           // serialised row lengths, then offsets
+    uint16_t S16[256];              // stored total of each row
+    uint8_t  rank[256], sym[256];
+    uint32_t pres[8];               // alphabet bitmap (symbol space)
+    uint32_t wtot[PREP_WARPS];
+    double   red[2][PREP_WARPS];
+    uint32_t redu[PREP_WARPS];
+    // RLE chunk states
+    uint32_t c_nl[PREP_WARPS], c_nr[PREP_WARPS], c_open[PREP_WARPS], c_start[PREP_WARPS], c_first[PREP_WARPS];
+    uint32_t bc[8];                 // broadcast scalars
+};
+
+// rank of every set flag among 256 (thread t owns flag t); returns the number set
+__device__ __forceinline__ uint32_t cta_rank256(bool pres, uint32_t *wtot, uint32_t *my_rank) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t bal = __ballot_sync(FULL, pres);
+    if (lane == 0) wtot[wid] = __popc(bal);
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < PREP_WARPS; w++) { const uint32_t c = wtot[w]; if (w < wid) before += c; total += c; }
+    *my_rank = before + __popc(bal & lanemask_lt());
+    __syncthreads();
+    return total;
+}
+
+// ------------------------------------------------------------------ PACK (pack.c:56-147)
+__device__ inline bool cta_pack(const uint8_t *in, uint32_t n, uint8_t *meta, uint32_t *meta_len, uint8_t *out,
+                                uint32_t *out_len, PrepSmem &S) {
+    const int tid = threadIdx.x;
+    uint8_t *code = (uint8_t *)S.Fw[0];
+    if (tid < 64) ((uint32_t *)code)[tid] = 0;
+    __syncthreads();
+    uint32_t head = (uint32_t)((16 - ((uintptr_t)in & 15)) & 15);
+    if (head > n) head = n;
+    {   // presence flags (benign write races)
+        if ((uint32_t)tid < head) code[in[tid]] = 1;
+        const uint8_t *p = in + head;
+        const uint32_t rest = n - head, nv = rest >> 4;
+        const uint4 *v = (const uint4 *)p;
+        for (uint32_t i = tid; i < nv; i += PREP_THREADS) {
+            const uint4 q = __ldg(v + i);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) code[(w[a] >> (8 * b)) & 0xff] = 1;
+        }
+        for (uint32_t i = (nv << 4) + tid; i < rest; i += PREP_THREADS) code[p[i]] = 1;
+    }
+    __syncthreads();
+    const bool pres = code[tid] != 0;
+    uint32_t r;
+    const uint32_t nsym = cta_rank256(pres, S.wtot, &r);
+    if (pres) { meta[1 + r] = (uint8_t)tid; code[tid] = (uint8_t)r; }           // pack.c:65-70 writes every listed symbol
+    if (tid == 0) meta[0] = (uint8_t)nsym;                                      // 256 wraps to 0
+    __syncthreads();
+    if (nsym > 16) return false;
+    *meta_len = nsym + 1;
+    const uint32_t per = nsym > 4 ? 2 : nsym > 2 ? 4 : nsym > 1 ? 8 : 0;
+    if (!per) { *out_len = 0; return true; }
+    const uint32_t bits = 8 / per, olen = (n + per - 1) / per;
+    uint32_t jdone = 0;
+    if ((((uintptr_t)in) & 15) == 0) {
+        const uint4 *v = (const uint4 *)in;
+        const uint32_t nv = n >> 4, ob = 16 / per;
+        for (uint32_t vi = tid; vi < nv; vi += PREP_THREADS) {
+            const uint4 q = __ldg(v + vi);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            uint32_t c[16];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) c[4 * a + b] = code[(w[a] >> (8 * b)) & 0xff];
+            if (per == 4) {
+                uint32_t x = 0;
+#pragma unroll
+                for (int k = 0; k < 16; k++) x |= c[k] << (2 * k);
+                *(uint32_t *)(out + vi * 4) = x;
+            } else if (per == 2) {
+                uint32_t x0 = 0, x1 = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) { x0 |= c[k] << (4 * k); x1 |= c[8 + k] << (4 * k); }
+                *(uint2 *)(out + vi * 8) = make_uint2(x0, x1);
+            } else {
+                uint32_t x = 0;
+#pragma unroll
+                for (int k = 0; k < 16; k++) x |= c[k] << k;
+                *(uint16_t *)(out + vi * 2) = (uint16_t)x;
+            }
+        }
+        jdone = nv * ob;
+    }
+    for (uint32_t j = jdone + tid; j < olen; j += PREP_THREADS) {
+        uint32_t v = 0;
+        const uint32_t base = j * per;
+        for (uint32_t q = 0; q < per && base + q < n; q++) v |= (uint32_t)code[in[base + q]] << (q * bits);
+        out[j] = (uint8_t)v;
+    }
+    *out_len = olen;
+    __syncthreads();
+    return true;
+}
+
+// ------------------------------------------------------------------ RLE (rle.c:48-138)
+// A symbol is run-length coded iff it repeats its predecessor more often than not.  Literals: one byte per
+// maximal run of such a symbol, one byte per occurrence otherwise; (run length - 1) goes to a varint stream in
+// run order.  Each warp owns a contiguous chunk; a run still open at the end of a chunk is closed by the first
+// emitting position of a later chunk (its varint is the last one of the chunk that opened it).
+template <bool WRITE>
+__device__ __forceinline__ void rle_chunk(const uint8_t *in, uint32_t lo, uint32_t hi, const int32_t *score,
+                                          uint8_t *lits, uint8_t *runs, uint32_t &nl, uint32_t &nr, bool &open,
+                                          uint32_t &open_start, uint32_t &first, int lane) {
+    const uint32_t lt = lanemask_lt();
+    nl = 0; nr = 0; open = false; open_start = 0; first = 0xffffffffu;
+    for (uint32_t base = lo; base < hi; base += 32) {
+        const uint32_t p = base + lane;
+        const bool valid = p < hi;
+        const uint32_t c = valid ? in[p] : 0x100u;
+        const uint32_t pc = (valid && p) ? in[p - 1] : 0x200u;
+        const bool isr = valid && score[c & 0xff] > 0;
+        const bool cont = isr && p && pc == c;              // continues a run: emits nothing
+        const bool emit = valid && !cont;
+        const uint32_t E = __ballot_sync(FULL, emit);
+        const uint32_t R = __ballot_sync(FULL, emit && isr);
+        if (!E) continue;
+        if (first == 0xffffffffu) first = base + __ffs(E) - 1;
+        const uint32_t below = E & lt;
+        const bool prev_in = below != 0;
+        const int pl = 31 - __clz(below);
+        const bool prev_open = prev_in ? ((R >> pl) & 1) : open;
+        const uint32_t prev_pos = prev_in ? base + pl : open_start;
+        const bool closes = emit && prev_open;
+        const uint32_t rl = closes ? p - prev_pos - 1 : 0;
+        const uint32_t C = __ballot_sync(FULL, closes);
+        if (C) {
+            const uint32_t vs = closes ? var_size_u32(rl) : 0;
+            const uint32_t vincl = warp_incl_scan(vs, lane);
+            if (WRITE && closes) var_put_u32(runs + nr + vincl - vs, rl);
+            nr += __shfl_sync(FULL, vincl, 31);
+        }
+        if (WRITE && emit) lits[nl + __popc(E & lt)] = (uint8_t)c;
+        nl += __popc(E);
+        const int hl = 31 - __clz(E);
+        open = (R >> hl) & 1;
+        open_start = base + hl;
+    }
+}
+
+__device__ inline void cta_rle_encode(const uint8_t *in, uint32_t n, uint8_t *lits, uint32_t *lits_len, uint8_t *meta,
+                                      uint32_t *meta_len, PrepSmem &S) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int32_t *score = (int32_t *)S.Fw[1];
+    score[tid] = 0;
+    __syncthreads();
+    {   // score[c] += (in[p-1] == c) ? +1 : -1 over all positions (the first byte has no predecessor)
+        uint32_t done = 0;
+        if ((((uintptr_t)in) & 15) == 0) {
+            const uint4 *v = (const uint4 *)in;
+            const uint32_t nv = n >> 4;
+            for (uint32_t i = tid; i < nv; i += PREP_THREADS) {
+                const uint4 q = v[i];                       // (`in` may have been written by this kernel: plain loads)
+                const uint32_t prev = i ? in[16 * i - 1] : 0x100u;
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+                uint32_t cur = w[0] & 0xff;
+                int acc = cur == prev ? 1 : -1;
+#pragma unroll
+                for (int k = 1; k < 16; k++) {
+                    const uint32_t c = (w[k >> 2] >> (8 * (k & 3))) & 0xff;
+                    if (c == cur) acc++;
+                    else { atomicAdd(&score[cur], acc); cur = c; acc = -1; }
+                }
+                atomicAdd(&score[cur], acc);
+            }
+            done = nv << 4;
+        }
+        for (uint32_t p = done + tid; p < n; p += PREP_THREADS) {
+            const uint32_t c = in[p];
+            atomicAdd(&score[c], (p && in[p - 1] == c) ? 1 : -1);
+        }
+    }
+    __syncthreads();
+    uint32_t r;
+    const bool pr = score[tid] > 0;
+    const uint32_t nsyms = cta_rank256(pr, S.wtot, &r);
+    if (pr) meta[1 + r] = (uint8_t)tid;
+    if (tid == 0) meta[0] = (uint8_t)nsyms;
+    uint8_t *runs = meta + 1 + nsyms;
+    // chunks of whole 32-byte rounds
+    const uint32_t CH = (((n + PREP_WARPS - 1) / PREP_WARPS) + 31) & ~31u;
+    const uint32_t lo = min(n, (uint32_t)wid * CH), hi = min(n, lo + CH);
+    uint32_t nl, nr, ostart, first;
+    bool open;
+    rle_chunk<false>(in, lo, hi, score, nullptr, nullptr, nl, nr, open, ostart, first, lane);
+    if (lane == 0) { S.c_nl[wid] = nl; S.c_nr[wid] = nr; S.c_open[wid] = open; S.c_start[wid] = ostart; S.c_first[wid] = first; }
+    __syncthreads();
+    // the run open at the end of this chunk ends at the first emitter behind it (or at n)
+    uint32_t next_first = n, lit_off = 0, run_off = 0, lit_tot = 0, run_tot = 0;
+    for (int w = PREP_WARPS - 1; w > wid; w--) if (S.c_first[w] != 0xffffffffu) next_first = S.c_first[w];
+    const uint32_t tail_rl = open ? next_first - ostart - 1 : 0;
+    const uint32_t tail_sz = open ? var_size_u32(tail_rl) : 0;
+    __syncthreads();
+    if (lane == 0) S.c_nr[wid] = nr + tail_sz;
+    __syncthreads();
+    for (int w = 0; w < PREP_WARPS; w++) {
+        if (w < wid) { lit_off += S.c_nl[w]; run_off += S.c_nr[w]; }
+        lit_tot += S.c_nl[w]; run_tot += S.c_nr[w];
+    }
+    rle_chunk<true>(in, lo, hi, score, lits + lit_off, runs + run_off, nl, nr, open, ostart, first, lane);
+    if (open && lane == 0) var_put_u32(runs + run_off + nr, tail_rl);
+    *lits_len = lit_tot;
+    *meta_len = 1 + nsyms + run_tot;
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------ order-0 counts (utils.h:145-244)
+// into S.T (symbol space); warp-private bins, equal neighbours merged before an atomic
+__device__ inline void cta_hist8(const uint8_t *in, uint32_t n, PrepSmem &S) {
+    const int tid = threadIdx.x, wid = tid >> 5;
+    for (int j = tid; j < PREP_WARPS * 256; j += PREP_THREADS) (&S.Fw[0][0])[j] = 0;
+    __syncthreads();
+    uint32_t head = (uint32_t)((16 - ((uintptr_t)in & 15)) & 15);
+    if (head > n) head = n;
+    const uint8_t *p = in + head;
+    const uint32_t rest = n - head, nv = rest >> 4;
+    const uint4 *v = (const uint4 *)p;
+    uint32_t *F = S.Fw[wid];
+    if ((uint32_t)tid < head) atomicAdd(&F[in[tid]], 1u);
+    for (uint32_t i = tid; i < nv; i += PREP_THREADS) hist16(v[i], F);
+    for (uint32_t t = (nv << 4) + tid; t < rest; t += PREP_THREADS) atomicAdd(&F[p[t]], 1u);
+    __syncthreads();
+    uint32_t f = 0;
+#pragma unroll
+    for (int w = 0; w < PREP_WARPS; w++) f += S.Fw[w][tid];
+    S.T[tid] = f;
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------ order-1 model (rANS_static16_int.h:312-421)
+// Pair counts H[rank(prev)][rank(cur)] in global memory (the first byte follows symbol 0, utils.h:279-357): the
+// contexts are taken a group at a time, as many rows as fit the shared-memory counters, the data being read
+// once per group (it sits in L1 / L2 by then); no read-modify-write ever reaches global memory.
+__device__ inline void cta_pair_counts(const uint8_t *in, uint32_t n, uint32_t nsym, uint32_t *H, PrepSmem &S) {
+    const int tid = threadIdx.x;
+    const uint32_t rpp = min(nsym, PREP_PAIRS / nsym);          // rows per pass (nsym <= 256 -> at least 25)
+    const uint32_t Hs_s = (uint32_t)__cvta_generic_to_shared(S.Hs);
+    uint32_t head = (uint32_t)((16 - ((uintptr_t)in & 15)) & 15);
+    if (head > n) head = n;
+    const uint8_t *p = in + head;
+    const uint32_t rest = n - head, nv = rest >> 4;
+    const uint4 *v = (const uint4 *)p;
+    const uint8_t *rank = S.rank;
+    for (uint32_t c0 = 0; c0 < nsym; c0 += rpp) {
+        const uint32_t rows = min(rpp, nsym - c0), words = rows * nsym;
+        for (uint32_t j = tid; j < words; j += PREP_THREADS) S.Hs[j] = 0;
+        __syncthreads();
+        auto add1 = [&](uint32_t rp, uint32_t rc) {
+            const uint32_t q = rp - c0;
+            if (q < rows) atomicAdd(&S.Hs[q * nsym + rc], 1u);
+        };
+        if ((uint32_t)tid < head) add1(rank[tid ? in[tid - 1] : 0], rank[in[tid]]);
+        for (uint32_t i = tid; i < nv; i += PREP_THREADS) {
+            const uint4 q = v[i];
+            const uint32_t pb = (i || head) ? p[16 * (size_t)i - 1] : 0;
+            const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+            uint32_t rp = rank[pb], last = 0, cnt = 0;          // cnt == 0: adding it is harmless
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const uint32_t rc = rank[(w4[a] >> (8 * b)) & 0xff];
+                    const uint32_t qrow = rp - c0;
+                    const uint32_t idx = qrow < rows ? qrow * nsym + rc : 0xffffffffu;   // pairs of other groups: no counter
+                    // close the open stretch when the pair changes (predicated shared-memory reduction)
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, %1;\n\t@p red.shared.add.u32 [%2], %3;\n\t}"
+                                 ::"r"(idx), "r"(last), "r"(Hs_s + (last == 0xffffffffu ? 0u : last) * 4),
+                                   "r"(last == 0xffffffffu ? 0u : cnt) : "memory");
+                    cnt = (idx == last) ? cnt + 1 : 1;
+                    last = idx;
+                    rp = rc;
+                }
+            if (last != 0xffffffffu) atomicAdd(&S.Hs[last], cnt);
+        }
+        for (uint32_t t = (nv << 4) + tid; t < rest; t += PREP_THREADS) {
+            const uint32_t pos = head + t;
+            add1(rank[pos ? in[pos - 1] : 0], rank[in[pos]]);
+        }
+        __syncthreads();
+        uint32_t *dst = H + (size_t)c0 * nsym;
+        for (uint32_t j = tid; j < words; j += PREP_THREADS) dst[j] = S.Hs[j];
+        __syncthreads();
+    }
+}
+
+// load / store the 8 columns a lane owns of one row
+__device__ __forceinline__ void row_load8(const uint32_t *row, uint32_t nsym, uint32_t j0, uint32_t (&f)[8]) {
+    if ((nsym & 3) == 0 && j0 + 8 <= nsym) {
+        const uint4 a = *(const uint4 *)(row + j0), b = *(const uint4 *)(row + j0 + 4);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    } else {
+#pragma unroll
+        for (int t = 0; t < 8; t++) f[t] = j0 + t < nsym ? row[j0 + t] : 0;
+    }
+}
+__device__ __forceinline__ void row_store8(uint32_t *row, uint32_t nsym, uint32_t j0, const uint32_t (&f)[8]) {
+    if ((nsym & 3) == 0 && j0 + 8 <= nsym) {
+        *(uint4 *)(row + j0) = make_uint4(f[0], f[1], f[2], f[3]);
+        *(uint4 *)(row + j0 + 4) = make_uint4(f[4], f[5], f[6], f[7]);
+    } else {
+#pragma unroll
+        for (int t = 0; t < 8; t++) if (j0 + t < nsym) row[j0 + t] = f[t];
+    }
+}
+
+// Bytes of one serialised row (rANS_static16_int.h:278-306: a varint per non-zero count, 0x00,(z-1) per run of z
+// zeros) and, with out != null, the bytes themselves at out + off and the row's encoder symbols.  f = the row's
+// normalised counts, lane l holding columns 8l..8l+7.  Returns the row's length (uniform).
+__device__ __forceinline__ uint32_t row_emit(const uint32_t (&f)[8], uint32_t nsym, uint32_t mv, uint32_t shift,
+                                             uint8_t *out, uint32_t off, uint32_t *srow, int lane) {
+    const uint32_t j0 = (uint32_t)lane * 8;
+    // zero bitmap of the row: zb[u] covers columns 32u..32u+31 (columns >= nsym read as non-zero)
+    uint32_t m8 = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) if (j0 + t < nsym && !f[t]) m8 |= 1u << t;
+    uint32_t wz = m8 << (8 * (lane & 3));
+    wz |= __shfl_xor_sync(FULL, wz, 1);
+    wz |= __shfl_xor_sync(FULL, wz, 2);
+    uint32_t zb[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) zb[u] = __shfl_sync(FULL, wz, 4 * u);
+    uint32_t nz[9];                          // first non-zero column at or after the start of word u (256 if none)
+    nz[8] = 256;
+#pragma unroll
+    for (int u = 7; u >= 0; u--) nz[u] = ~zb[u] ? 32 * u + __ffs(~zb[u]) - 1 : nz[u + 1];
+    int sh = 0;
+    while ((mv << sh) < (1u << shift)) sh++;
+    const uint32_t myw = lane >> 2;
+    uint32_t zw = 0, nzn = 256, zprev = 0;
+#pragma unroll
+    for (int u = 0; u < 8; u++) if (myw == (uint32_t)u) { zw = zb[u]; nzn = nz[u + 1]; }
+#pragma unroll
+    for (int u = 1; u < 8; u++) if (myw == (uint32_t)u) zprev = zb[u - 1] >> 31;
+    uint32_t len[8], run[8], tot8 = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const uint32_t j = j0 + t, bit = j & 31;
+        uint32_t l = 0, r = 0;
+        if (j < nsym) {
+            if (f[t]) l = f[t] >= 128 ? 2 : 1;
+            else {
+                const uint32_t pz = bit ? (zw >> (bit - 1)) & 1 : zprev;
+                if (!pz) {                   // first zero of a run: one token for the whole run
+                    const uint32_t w = (~zw) >> bit;
+                    const uint32_t end = w ? j + __ffs(w) - 1 : nzn;
+                    l = 2;
+                    r = min(end, nsym) - j;
+                }
+            }
+        }
+        len[t] = l; run[t] = r;
+        tot8 += l | ((f[t] << sh) << 16);
+    }
+    uint32_t ex = warp_incl_scan(tot8, lane);
+    const uint32_t rowbytes = __shfl_sync(FULL, ex, 31) & 0xffff;
+    if (!out) return rowbytes;
+    ex -= tot8;
+    uint32_t o = off + (ex & 0xffff), x = ex >> 16;
+    uint32_t e8[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const uint32_t fs = f[t] << sh;
+        if (len[t]) {
+            if (f[t]) {
+                if (len[t] == 2) { out[o] = (uint8_t)(0x80 | (f[t] >> 7)); out[o + 1] = (uint8_t)(f[t] & 0x7f); }
+                else out[o] = (uint8_t)f[t];
+            } else { out[o] = 0; out[o + 1] = (uint8_t)(run[t] - 1); }
+            o += len[t];
+        }
+        e8[t] = enc_sym_make4(x, fs, shift);
+        x += fs;
+    }
+    row_store8(srow, nsym, j0, e8);
+    return rowbytes;
+}
+
+// The whole order-1 model of `in`: counts in S.T on entry (symbol space, cta_hist8).  Leaves the uncompressed
+// table (first byte = shift << 4) at tbl, the encoder symbols at symtab, the rank map in P.  N = lanes of the coder.
+__device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint32_t *H, uint32_t *symtab, uint8_t *tbl,
+                                    Prep &P, PrepSmem &S) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t seg = n / N;
+    // ---- alphabet = symbols present, plus 0 (:357-361)
+    const bool pres = S.T[tid] != 0 || tid == 0;
+    {
+        const uint32_t bal = __ballot_sync(FULL, pres);
+        if ((tid & 31) == 0) S.pres[tid >> 5] = bal;
+    }
+    uint32_t r;
+    const uint32_t nsym = cta_rank256(pres, S.wtot, &r);
+    S.rank[tid] = pres ? (uint8_t)r : 0xff;
+    if (pres) S.sym[r] = (uint8_t)tid;
+    P.rank[tid] = pres ? (uint8_t)r : 0xff;
+    __syncthreads();
+    // ---- pair counts, then the lane starts in context 0 (:325-327)
+    cta_pair_counts(in, n, nsym, H, S);
+    if (tid >= 1 && tid < N) atomicAdd(&H[(size_t)S.rank[0] * nsym + S.rank[in[(size_t)tid * seg]]], 1u);
+    __threadfence_block();
+    __syncthreads();
+    const uint32_t last_rank = S.rank[in[n - 1]];
+    const uint32_t j0 = (uint32_t)lane * 8;
+    // ---- sweep 1: row totals (the last symbol's gets one extra, utils.h:311,345) and the statistics of
+    // rans_compute_shift (rANS_static4x16pr.c:357-420); warp w takes rows w, w+8, ...
+    double e10 = 0, e12 = 0;
+    uint32_t max_tot = 0;
+    for (uint32_t i = wid; i < nsym; i += PREP_WARPS) {
+        uint32_t f[8], loc = 0;
+        row_load8(H + (size_t)i * nsym, nsym, j0, f);
+#pragma unroll
+        for (int t = 0; t < 8; t++) loc += f[t];
+        const uint32_t Ti = warp_sum(loc) + (i == last_rank ? 1u : 0u);
+        if (lane == 0) S.T[i] = Ti;
+        if (!Ti) { if (lane == 0) S.S16[i] = 0; continue; }
+        uint32_t max_val = round2(Ti);
+        uint32_t cnt = 0;                           // ns | sm10 << 10 | sm12 << 20
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            if (!f[t]) continue;
+            cnt += 1;
+            if ((uint64_t)f[t] * 1025 <= max_val) cnt += 1u << 10;     // max_val / f > 1024
+            if ((uint64_t)f[t] * 4097 <= max_val) cnt += 1u << 20;     // max_val / f > 4096
+        }
+        cnt = warp_sum(cnt);
+        const uint32_t ns = cnt & 1023, sm10 = (cnt >> 10) & 1023, sm12 = cnt >> 20;
+        const double l10 = log((double)(1024 + sm10)), l12 = log((double)(4096 + sm12));
+        const double T_slow = (double)4096 / Ti, T_fast = (double)1024 / Ti;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            if (!f[t]) continue;
+            const double a = f[t] * T_fast, b = f[t] * T_slow;
+            e10 -= f[t] * (fast_log(a > 1 ? a : 1) - l10);
+            e12 -= f[t] * (fast_log(b > 1 ? b : 1) - l12);
+            e10 += 1.3;
+            e12 += 4.7;
+        }
+        if (ns < 64 && max_val > 128) max_val /= 2;
+        if (max_val > 1024) max_val /= 2;
+        if (max_val > 4096) max_val = 4096;
+        if (lane == 0) S.S16[i] = (uint16_t)max_val;
+        if (max_tot < max_val) max_tot = max_val;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        e10 += __shfl_xor_sync(FULL, e10, o);
+        e12 += __shfl_xor_sync(FULL, e12, o);
+    }
+    if (lane == 0) { S.red[0][wid] = e10; S.red[1][wid] = e12; S.redu[wid] = max_tot; }
+    __syncthreads();
+    e10 = 0; e12 = 0; max_tot = 0;
+#pragma unroll
+    for (int w = 0; w < PREP_WARPS; w++) { e10 += S.red[0][w]; e12 += S.red[1][w]; max_tot = max(max_tot, S.redu[w]); }
+    const uint32_t shift = (e10 / e12 < 1.01 || max_tot <= 1024) ? 10 : 12;
+    __syncthreads();
+    // ---- sweep 2a: normalise_freq of every row (rANS_static16_int.h:97-146) to its stored total; the row stays
+    // normalised in H; its serialised length goes to rowlen
+    int err = 0;
+    uint32_t *shave = S.Fw[wid];
+    for (uint32_t i = wid; i < nsym; i += PREP_WARPS) {
+        const uint32_t Ti = S.T[i];
+        if (!Ti) { if (lane == 0) S.rowlen[i] = 0; continue; }
+        uint32_t *row = H + (size_t)i * nsym;
+        uint32_t f[8];
+        row_load8(row, nsym, j0, f);
+        uint32_t mv = S.S16[i];
+        if (shift == 10 && mv > 1024) mv = 1024;
+        uint32_t size = Ti;
+        for (int pass = 0; pass < 2; pass++) {
+            const uint64_t tr = ((uint64_t)mv << 31) / size + (uint32_t)((1 << 30) / (int)size);
+            uint32_t top = 0, arg = 0, sum = 0;
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                uint32_t v = f[t];
+                if (!v) continue;
+                if (top < v) { top = v; arg = j0 + t; }
+                v = (uint32_t)((v * tr) >> 31);
+                if (!v) v = 1;
+                f[t] = v;
+                sum += v;
+            }
+            sum = warp_sum(sum);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {      // max, ties -> lowest index
+                const uint32_t t2 = __shfl_xor_sync(FULL, top, o), a2 = __shfl_xor_sync(FULL, arg, o);
+                if (t2 > top || (t2 == top && a2 < arg)) { top = t2; arg = a2; }
+            }
+            const uint32_t big = top ? arg : 0;
+            uint32_t mine = 0;
+#pragma unroll
+            for (int t = 0; t < 8; t++) if ((big & 7) == (uint32_t)t) mine = f[t];
+            const uint32_t fb = __shfl_sync(FULL, mine, big >> 3);
+            int adjust = (int)mv - (int)sum;
+            const bool own = (big >> 3) == (uint32_t)lane;
+            if (adjust >= 0 || (fb > (uint32_t)-adjust && (pass == 1 || fb / 2 >= (uint32_t)-adjust))) {
+                if (own) {
+#pragma unroll
+                    for (int t = 0; t < 8; t++) if ((big & 7) == (uint32_t)t) f[t] += adjust;
+                }
+                break;
+            }
+            if (pass == 0) { size = sum; continue; }
+            // greedy shave (rare): serial over the row through the warp's scratch
+#pragma unroll
+            for (int t = 0; t < 8; t++) shave[j0 + t] = f[t];
+            __syncwarp();
+            if (lane == 0) {
+                adjust += (int)fb - 1;
+                shave[big] = 1;
+                for (uint32_t j = 0; adjust && j < nsym; j++) {
+                    if (shave[j] < 2) continue;
+                    const int d = (shave[j] > (uint32_t)-adjust) ? adjust : 1 - (int)shave[j];
+                    shave[j] += d;
+                    adjust -= d;
+                }
+                if (!shave[big]) err = 1;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < 8; t++) f[t] = shave[j0 + t];
+            __syncwarp();
+        }
+        row_store8(row, nsym, j0, f);
+        const uint32_t rb = row_emit(f, nsym, mv, shift, nullptr, 0, nullptr, lane);
+        if (lane == 0) { S.S16[i] = (uint16_t)mv; S.rowlen[i] = rb; }
+    }
+    err = __any_sync(FULL, err);
+    if (err && lane == 0) P.err = 1;
+    // ---- the alphabet of the contexts, 0 forced in (:357-361), then the rows' offsets
+    if (tid == 0) {
+        uint8_t *cp = tbl;
+        *cp++ = (uint8_t)(shift << 4);
+        auto present = [&](int s) { return (S.pres[s >> 5] >> (s & 31)) & 1; };
+        int j = 0;
+        while (j < 256) {
+            if (!present(j)) { j++; continue; }
+            *cp++ = (uint8_t)j;
+            if (j && present(j - 1)) {
+                int k = j + 1;
+                while (k < 256 && present(k)) k++;
+                *cp++ = (uint8_t)(k - (j + 1));
+                j = k;
+            } else j++;
+        }
+        *cp++ = 0;
+        S.bc[0] = (uint32_t)(cp - tbl);
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (wid == 0) {                              // exclusive scan of the row lengths (8 per lane)
+        uint32_t l8[8], loc = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) { l8[t] = j0 + t < nsym ? S.rowlen[j0 + t] : 0; loc += l8[t]; }
+        uint32_t x = S.bc[0] + warp_incl_scan(loc, lane) - loc;
+#pragma unroll
+        for (int t = 0; t < 8; t++) { if (j0 + t < nsym) S.rowlen[j0 + t] = x; x += l8[t]; }
+        if (lane == 31) S.bc[1] = x;             // total table length
+    }
+    __syncthreads();
+    // ---- sweep 2b: serialise (encode_freq_d, :278-306) and build the encoder symbols (rANS_word.h:201-272)
+    for (uint32_t i = wid; i < nsym; i += PREP_WARPS) {
+        if (!S.T[i]) continue;
+        uint32_t f[8];
+        row_load8(H + (size_t)i * nsym, nsym, j0, f);
+        row_emit(f, nsym, S.S16[i], shift, tbl, S.rowlen[i], symtab + (size_t)i * nsym, lane);
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (tid == 0) { P.nsym = nsym; P.shift = shift; P.tl = S.bc[1]; }
+}
+
+// ------------------------------------------------------------------ the coder warp's side
+// Order-1 stream whose model the CTA built: the table goes to `out` raw or, when longer than 1000 bytes and it
+// pays, through the 4-lane order-0 coder (rANS_static16_int.h:396-412); then the state chains.
+template <int N>
+__device__ int enc_o1_prepped(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_end, uint32_t *tab_len,
+                              uint8_t **ptr_out, EncO1Smem &S, uint8_t *dyn, uint32_t dyn_bytes, const Prep &P,
+                              const uint8_t *prep_base, uint32_t prep_isz, int lane) {
+    *tab_len = 0;
+    *ptr_out = out_end;
+    if (P.err) return 1;
+    const PrepPlan pl = prep_plan(prep_isz);
+    const uint32_t *gsym = (const uint32_t *)(prep_base + pl.o_sym);
+    const uint8_t *tbl = prep_base + pl.o_tbl;
+    uint8_t *tmp = const_cast<uint8_t *>(prep_base) + pl.o_tmp;
+    const uint32_t nsym = P.nsym, shift = P.shift;
+    uint32_t tl = P.tl;
+    ((uint2 *)S.rank)[lane] = ((const uint2 *)P.rank)[lane];
+    __syncwarp();
+    bool raw = true;
+    if (tl > 1000) {
+        const uint32_t usz = tl - 1;
+        const uint32_t cb = (compress_bound(usz, 0) - 20) & ~1u;
+        uint32_t ctab = 0;
+        uint8_t *cptr = nullptr;
+        if (enc_o0<4>(tbl + 1, usz, tmp, tmp + cb, &ctab, &cptr, *(EncO0Smem *)dyn, lane) == 0) {
+            const uint32_t pay = (uint32_t)(tmp + cb - cptr), csz = ctab + pay;
+            if (csz + 6 < tl) {
+                uint32_t h = 1;
+                if (lane == 0) {
+                    out[0] = tbl[0] | 1;
+                    h += var_put_u32(out + h, usz);
+                    h += var_put_u32(out + h, csz);
+                }
+                h = __shfl_sync(FULL, h, 0);
+                __syncwarp();
+                warp_copy(out + h, tmp, ctab, lane);
+                warp_copy(out + h + ctab, cptr, pay, lane);
+                tl = h + csz;
+                raw = false;
+            }
+        }
+        __syncwarp();
+    }
+    if (raw) warp_copy(out, tbl, tl, lane);
+    *tab_len = tl;
+    // encoder symbols: into shared memory when they fit (the order-0 scratch is dead by now)
+    const uint32_t hw = nsym * nsym;
+    const bool sym_smem = hw * 4 <= dyn_bytes;
+    const uint32_t *symtab = gsym;
+    if (sym_smem) {
+        uint32_t *d = (uint32_t *)dyn;
+        for (uint32_t j = lane; j < hw; j += 32) d[j] = gsym[j];
+        symtab = d;
+    }
+    __syncwarp();
+    enc_o1_payload<N>(in, n, out, out_end, ptr_out, S, symtab, nsym, shift, sym_smem, lane);
+    return 0;
+}
+
+// The CTA's work for one stream: mirrors the decisions of enc_stream (kernels.cu) up to the coder.
+__device__ inline void prep_stream(EncJob &J, PrepSmem &S) {
+    Prep *Pp = (Prep *)J.prep;
+    const int tid = threadIdx.x;
+    int order = J.order;
+    uint32_t in_size = J.in_size;
+    const uint8_t *in = J.in;
+    if ((order & ORDER_SIMD_AUTO) && in_size >= 50000 && !(order & X_STRIPE)) order |= X_32;
+    if (in_size <= 20) order &= ~X_STRIPE;
+    if (in_size <= 1000) order &= ~X_32;
+    const bool skip = in_size > 0x7fffffffu || (order & (X_STRIPE | X_CAT)) || !in_size || !J.work ||
+                      !(order & (X_PACK | X_RLE));
+    if (skip) { if (tid == 0) Pp->state = 0; return; }
+    Prep &P = *Pp;
+    if (tid == 0) P.err = 0;
+    const int do_pack = order & X_PACK, no_size = order & X_NOSZ, do_rle = order & X_RLE;
+    int do_simd = order & X_32, o1 = order & 1;
+    const uint32_t meta = 1 + (no_size ? 0 : var_size_u32(in_size));
+    uint8_t *work = J.work;
+    uint32_t packed = 0, pmeta = 0, plen = 0, rle_len = 0, rmeta_len = 0;
+    if (do_pack) {                                                        // rANS_static4x16pr.c:1429-1459
+        packed = cta_pack(in, in_size, J.slot + meta, &pmeta, work, &plen, S) ? 1u : 0u;
+        if (packed) {
+            in = work; work += (plen + 15) & ~15u;
+            in_size = plen;
+            if (do_simd && in_size < 32) do_simd = 0;
+        }
+    }
+    if (do_rle && in_size) {                                              // :1464-1533
+        uint8_t *lits = work, *rmeta = work + ((in_size + 15) & ~15u);
+        cta_rle_encode(in, in_size, lits, &rle_len, rmeta, &rmeta_len, S);
+        if (!((double)((uint64_t)rle_len + rmeta_len) >= .99 * (double)in_size)) {
+            if (do_simd && (rmeta_len < 32 || rle_len < 32)) do_simd = 0;
+            in = lits; in_size = rle_len;
+        }
+    }
+    if (o1 && in_size < 8) o1 = 0;                                        // :1547
+    uint32_t model = 0;
+    if (in_size) {
+        cta_hist8(in, in_size, S);
+        P.F[tid] = S.T[tid];
+        model = 1;
+        const int N = do_simd ? 32 : 4;
+        if (o1 && !(N == 32 && in_size < 32)) {
+            const PrepPlan pl = prep_plan(J.in_size);
+            uint8_t *base = (uint8_t *)Pp;
+            cta_o1_model(in, in_size, N, (uint32_t *)(base + pl.o_H), (uint32_t *)(base + pl.o_sym), base + pl.o_tbl, P, S);
+            model = 2;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        P.packed = packed; P.pmeta = pmeta; P.plen = plen; P.rle_len = rle_len; P.rmeta_len = rmeta_len;
+        P.model = model;
+        __threadfence();
+        P.state = 1;
+    }
+}
+
+}  // namespace b200

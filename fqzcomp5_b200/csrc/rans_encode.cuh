@@ -864,6 +864,143 @@ __device__ inline void pair_counts_partitioned(const uint8_t *in, uint32_t n, ui
     __syncwarp();
 }
 
+// ------------------------------------------------------------------------
+// The order-1 state chains (rANS_static32x16pr.c:457-525, rANS_static4x16pr.c:460-518): lane z owns
+// [z*seg,(z+1)*seg); lane N-1 also the tail; every symbol is coded in the context of its predecessor, a
+// lane's first symbol in context 0.  symtab = 4-byte encoder symbols indexed (rank(ctx), rank(sym)), in
+// shared memory when sym_smem; S.rank maps symbols to ranks; the output ring is S.ring.
+// ------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void enc_o1_payload(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_end,
+                                               uint8_t **ptr_out, EncO1Smem &S, const uint32_t *symtab, uint32_t nsym,
+                                               uint32_t shift, bool sym_smem, int lane) {
+    const uint32_t seg = n / N;
+    const bool act = lane < N;
+    OutRing w;
+    w.init(out, out_end, S.ring);
+    uint32_t R = RANS_L;
+    const uint8_t *rank = S.rank;
+    {   // tail on lane N-1, from the end down to N*seg
+        const bool lastl = lane == N - 1;
+        for (uint32_t p = n - 1; p >= N * seg && p > 0; p--) {
+            uint4 e = make_uint4(0, 0, 0, 0);
+            if (lastl) e = enc_sym_unpack(symtab[rank[in[p - 1]] * nsym + rank[in[p]]], shift);
+            w.maybe_flush(lane);
+            R = enc_step(R, lastl, e, w, lane);
+        }
+    }
+    const uint8_t *q = in + (size_t)(act ? lane : 0) * seg;
+    uint32_t rs = act && seg ? rank[q[seg - 1]] : 0;         // rank of the symbol being coded
+    uint32_t kstart = seg;
+    __syncwarp();                                            // enter the hot loop converged
+    if (N == 32 && sym_smem && seg >= 32 && ((((uintptr_t)in) | seg) & 15) == 0) {
+        // Hot loop: lane segments are 16-byte aligned, so every lane reads its symbols with
+        // 128-bit loads (one group of 16 ahead) and the encoder symbols come from shared memory.
+        const uint32_t rank_s = (uint32_t)__cvta_generic_to_shared(S.rank);
+        const uint32_t sym_s = (uint32_t)__cvta_generic_to_shared(symtab);
+        const uint4 *v = (const uint4 *)q;
+        const uint32_t J = seg >> 4;
+        uint4 cur = ldg_u128(v + J - 1), nxt = ldg_u128(v + J - 2);
+        auto byte_of = [](const uint4 &x, int b) {
+            uint32_t w = b < 4 ? x.x : b < 8 ? x.y : b < 12 ? x.z : x.w;
+            return (w >> (8 * (b & 3))) & 0xff;
+        };
+        auto lds_sym = [&](uint32_t a) {
+            uint32_t r;
+            asm("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
+            return enc_sym_unpack(r, shift);
+        };
+        auto rank_of = [&](uint32_t b) {
+            uint32_t r;
+            asm("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(rank_s + b));
+            return r;
+        };
+        // the encoder symbol of the NEXT step is fetched (rank look-up, table look-up, unpack)
+        // while the current step runs: none of it depends on the state
+        uint32_t rc = rank_of(byte_of(cur, 14));
+        uint4 e = lds_sym(sym_s + (rc * nsym + rs) * 4);
+        for (uint32_t j = J - 1; j >= 1; j--) {
+            uint4 nn = j >= 2 ? ldg_u128(v + j - 2) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int b = 15; b >= 0; b--) {
+                // next step codes byte b-1 in the context of byte b-2 (crossing into nxt at the low end)
+                uint32_t nb = b >= 2 ? byte_of(cur, b - 2) : byte_of(nxt, 14 + b);
+                uint32_t rn = rank_of(nb);
+                uint4 en = lds_sym(sym_s + (rn * nsym + rc) * 4);
+                if ((b & 3) == 3) w.maybe_flush(lane);
+                R = enc_step(R, true, e, w, lane);
+                e = en;
+                rs = rc;
+                rc = rn;
+            }
+            cur = nxt;
+            nxt = nn;
+        }
+#pragma unroll
+        for (int b = 15; b >= 1; b--) {                      // group 0: its byte 0 is the lane's first symbol
+            uint32_t rn = b >= 2 ? rank_of(byte_of(cur, b - 2)) : 0;
+            uint4 en = b >= 2 ? lds_sym(sym_s + (rn * nsym + rc) * 4) : e;
+            if ((b & 3) == 3) w.maybe_flush(lane);
+            R = enc_step(R, true, e, w, lane);
+            e = en;
+            rs = rc;
+            rc = rn;
+        }
+        kstart = 1;
+    } else if (N == 32 && seg >= 32) {
+        // Encoder symbols in global memory (large alphabets): the 16 symbols of a group are
+        // requested together before the group's 16 steps run, so one L2/DRAM round trip is paid
+        // per group instead of per step.  Groups are counted from the END of the lane's segment
+        // (any alignment, any length); the seg % 16 bytes at its start go through the loop below.
+        const uint32_t rank_s = (uint32_t)__cvta_generic_to_shared(S.rank);
+        const uint32_t J = seg >> 4, lead = seg & 15;
+        const uint8_t *g0 = q + lead;                          // group j = bytes g0[16j .. 16j+15]
+        auto rank_of = [&](uint32_t b) {
+            uint32_t r;
+            asm("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(rank_s + b));
+            return r;
+        };
+        const uint32_t rank0 = rank_of(0);
+        uint4 cur = ld16_any(g0 + 16 * (J - 1));
+        for (uint32_t j = J; j-- > 0;) {
+            uint4 prv = j ? ld16_any(g0 + 16 * (j - 1)) : make_uint4(0, 0, 0, 0);
+            const uint32_t w4[4] = {cur.x, cur.y, cur.z, cur.w};
+            uint32_t rk[17];
+            rk[0] = j ? rank_of(prv.w >> 24) : (lead ? rank_of(g0[-1]) : rank0);
+#pragma unroll
+            for (int b = 0; b < 16; b++) rk[b + 1] = rank_of((w4[b >> 2] >> (8 * (b & 3))) & 0xff);
+            uint32_t ev[16];
+#pragma unroll
+            for (int b = 0; b < 16; b++) ev[b] = symtab[rk[b] * nsym + rk[b + 1]];      // (written by this kernel: no ld.nc)
+#pragma unroll
+            for (int b = 15; b >= 0; b--) {
+                if (b == 0 && j == 0 && !lead) break;        // the lane's first symbol is coded below
+                if ((b & 3) == 3) w.maybe_flush(lane);
+                R = enc_step(R, true, enc_sym_unpack(ev[b], shift), w, lane);
+            }
+            rs = lead ? rk[0] : rk[1];                       // rank of the next symbol to code
+            cur = prv;
+        }
+        kstart = lead ? lead : 1;
+    }
+    for (uint32_t k = kstart; k-- > 1;) {
+        uint32_t rc = rank[q[k - 1]];
+        uint4 e = enc_sym_unpack(symtab[rc * nsym + rs], shift);
+        w.maybe_flush(lane);
+        R = enc_step(R, act, e, w, lane);
+        rs = rc;
+    }
+    if (seg) {
+        uint4 e = enc_sym_unpack(symtab[rank[0] * nsym + rs], shift);
+        w.maybe_flush(lane);
+        R = enc_step(R, act, e, w, lane);
+    }
+    enc_flush(R, act, N, w, lane);
+    *ptr_out = w.slot + w.off;
+    __syncwarp();
+}
+
+
 template <int N>
 __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_end,
                       uint32_t *tab_len, uint8_t **ptr_out, EncO1Smem &S, uint8_t *dyn, uint32_t dyn_bytes,
@@ -1154,131 +1291,7 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
     if (pool_fail) return 2;
     *tab_len = tl;
 
-    // ---- encode.  Lane z owns [z*seg,(z+1)*seg); lane N-1 also the tail; every
-    // symbol is coded in the context of its predecessor, lane starts in context 0.
-    const bool act = lane < N;
-    OutRing w;
-    w.init(out, out_end, S.ring);
-    uint32_t R = RANS_L;
-    const uint8_t *rank = S.rank;
-    {   // tail on lane N-1, from the end down to N*seg
-        const bool lastl = lane == N - 1;
-        for (uint32_t p = n - 1; p >= N * seg && p > 0; p--) {
-            uint4 e = make_uint4(0, 0, 0, 0);
-            if (lastl) e = enc_sym_unpack(symtab[rank[in[p - 1]] * nsym + rank[in[p]]], shift);
-            w.maybe_flush(lane);
-            R = enc_step(R, lastl, e, w, lane);
-        }
-    }
-    const uint8_t *q = in + (size_t)(act ? lane : 0) * seg;
-    uint32_t rs = act && seg ? rank[q[seg - 1]] : 0;         // rank of the symbol being coded
-    uint32_t kstart = seg;
-    __syncwarp();                                            // enter the hot loop converged
-    if (N == 32 && sym_smem && seg >= 32 && ((((uintptr_t)in) | seg) & 15) == 0) {
-        // Hot loop: lane segments are 16-byte aligned, so every lane reads its symbols with
-        // 128-bit loads (one group of 16 ahead) and the encoder symbols come from shared memory.
-        const uint32_t rank_s = (uint32_t)__cvta_generic_to_shared(S.rank);
-        const uint32_t sym_s = (uint32_t)__cvta_generic_to_shared(symtab);
-        const uint4 *v = (const uint4 *)q;
-        const uint32_t J = seg >> 4;
-        uint4 cur = ldg_u128(v + J - 1), nxt = ldg_u128(v + J - 2);
-        auto byte_of = [](const uint4 &x, int b) {
-            uint32_t w = b < 4 ? x.x : b < 8 ? x.y : b < 12 ? x.z : x.w;
-            return (w >> (8 * (b & 3))) & 0xff;
-        };
-        auto lds_sym = [&](uint32_t a) {
-            uint32_t r;
-            asm("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
-            return enc_sym_unpack(r, shift);
-        };
-        auto rank_of = [&](uint32_t b) {
-            uint32_t r;
-            asm("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(rank_s + b));
-            return r;
-        };
-        // the encoder symbol of the NEXT step is fetched (rank look-up, table look-up, unpack)
-        // while the current step runs: none of it depends on the state
-        uint32_t rc = rank_of(byte_of(cur, 14));
-        uint4 e = lds_sym(sym_s + (rc * nsym + rs) * 4);
-        for (uint32_t j = J - 1; j >= 1; j--) {
-            uint4 nn = j >= 2 ? ldg_u128(v + j - 2) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-            for (int b = 15; b >= 0; b--) {
-                // next step codes byte b-1 in the context of byte b-2 (crossing into nxt at the low end)
-                uint32_t nb = b >= 2 ? byte_of(cur, b - 2) : byte_of(nxt, 14 + b);
-                uint32_t rn = rank_of(nb);
-                uint4 en = lds_sym(sym_s + (rn * nsym + rc) * 4);
-                if ((b & 3) == 3) w.maybe_flush(lane);
-                R = enc_step(R, true, e, w, lane);
-                e = en;
-                rs = rc;
-                rc = rn;
-            }
-            cur = nxt;
-            nxt = nn;
-        }
-#pragma unroll
-        for (int b = 15; b >= 1; b--) {                      // group 0: its byte 0 is the lane's first symbol
-            uint32_t rn = b >= 2 ? rank_of(byte_of(cur, b - 2)) : 0;
-            uint4 en = b >= 2 ? lds_sym(sym_s + (rn * nsym + rc) * 4) : e;
-            if ((b & 3) == 3) w.maybe_flush(lane);
-            R = enc_step(R, true, e, w, lane);
-            e = en;
-            rs = rc;
-            rc = rn;
-        }
-        kstart = 1;
-    } else if (N == 32 && seg >= 32) {
-        // Encoder symbols in global memory (large alphabets): the 16 symbols of a group are
-        // requested together before the group's 16 steps run, so one L2/DRAM round trip is paid
-        // per group instead of per step.  Groups are counted from the END of the lane's segment
-        // (any alignment, any length); the seg % 16 bytes at its start go through the loop below.
-        const uint32_t rank_s = (uint32_t)__cvta_generic_to_shared(S.rank);
-        const uint32_t J = seg >> 4, lead = seg & 15;
-        const uint8_t *g0 = q + lead;                          // group j = bytes g0[16j .. 16j+15]
-        auto rank_of = [&](uint32_t b) {
-            uint32_t r;
-            asm("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(rank_s + b));
-            return r;
-        };
-        const uint32_t rank0 = rank_of(0);
-        uint4 cur = ld16_any(g0 + 16 * (J - 1));
-        for (uint32_t j = J; j-- > 0;) {
-            uint4 prv = j ? ld16_any(g0 + 16 * (j - 1)) : make_uint4(0, 0, 0, 0);
-            const uint32_t w4[4] = {cur.x, cur.y, cur.z, cur.w};
-            uint32_t rk[17];
-            rk[0] = j ? rank_of(prv.w >> 24) : (lead ? rank_of(g0[-1]) : rank0);
-#pragma unroll
-            for (int b = 0; b < 16; b++) rk[b + 1] = rank_of((w4[b >> 2] >> (8 * (b & 3))) & 0xff);
-            uint32_t ev[16];
-#pragma unroll
-            for (int b = 0; b < 16; b++) ev[b] = symtab[rk[b] * nsym + rk[b + 1]];      // (written by this kernel: no ld.nc)
-#pragma unroll
-            for (int b = 15; b >= 0; b--) {
-                if (b == 0 && j == 0 && !lead) break;        // the lane's first symbol is coded below
-                if ((b & 3) == 3) w.maybe_flush(lane);
-                R = enc_step(R, true, enc_sym_unpack(ev[b], shift), w, lane);
-            }
-            rs = lead ? rk[0] : rk[1];                       // rank of the next symbol to code
-            cur = prv;
-        }
-        kstart = lead ? lead : 1;
-    }
-    for (uint32_t k = kstart; k-- > 1;) {
-        uint32_t rc = rank[q[k - 1]];
-        uint4 e = enc_sym_unpack(symtab[rc * nsym + rs], shift);
-        w.maybe_flush(lane);
-        R = enc_step(R, act, e, w, lane);
-        rs = rc;
-    }
-    if (seg) {
-        uint4 e = enc_sym_unpack(symtab[rank[0] * nsym + rs], shift);
-        w.maybe_flush(lane);
-        R = enc_step(R, act, e, w, lane);
-    }
-    enc_flush(R, act, N, w, lane);
-    *ptr_out = w.slot + w.off;
-    __syncwarp();
+    enc_o1_payload<N>(in, n, out, out_end, ptr_out, S, symtab, nsym, shift, sym_smem, lane);
     return 0;
 }
 

@@ -80,6 +80,9 @@ inline uint32_t hist_min_bytes(bool o1) {
     static uint32_t v1 = (uint32_t)env_int("B200RANS_HIST_MIN_O1", 4096, 0, 0x7fffffff);
     return o1 ? v1 : v0;
 }
+// PACK / RLE streams: transforms, counts and order-1 model by one CTA per stream (prep_kernel) in front of the
+// coder warp; 0 = the coder warp does everything itself (kept for measurement)
+inline bool use_prep() { static int v = env_int("B200RANS_PREP", 1, 0, 1); return v != 0; }
 inline size_t chunk_bytes() { static size_t v = (size_t)env_int("B200RANS_CHUNK_MB", 48, 1, 1024) << 20; return v; }
 inline int chunk_min_streams() { static int v = env_int("B200RANS_CHUNK_STREAMS", 256, 1, 16384); return v; }
 
