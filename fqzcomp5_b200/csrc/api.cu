@@ -121,7 +121,7 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
     size_t o_jobs = L.take(njobs * sizeof(EncJob));
     size_t o_ctr = L.take(256);
     size_t o_par = L.take(stripes.size() * 4 + 4);
-    uint32_t n_o0 = 0, n_o1 = 0, n_o1w = 0, n_model = 0, n_prep = 0;
+    uint32_t n_o0 = 0, n_o1 = 0, n_o1w = 0, n_o1p = 0, n_model = 0, n_prep = 0;
     size_t pool_bytes = 0;
     const bool prep = use_prep();
     // ---- pass 2: place slots / work buffers
@@ -150,8 +150,9 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
         if ((ord & 1) && isz >= 8) {
             // the order-1 kernel (larger shared memory per warp); transformed streams get the launch
             // with room for the partitioned pair count
-            J.route = ((ord & (X_PACK | X_RLE)) && !J.prep) ? ROUTE_O1_WIDE : ROUTE_O1;
+            J.route = J.prep ? ROUTE_O1_PREP : (ord & (X_PACK | X_RLE)) ? ROUTE_O1_WIDE : ROUTE_O1;
             if (J.route == ROUTE_O1_WIDE) n_o1w++;
+            if (J.route == ROUTE_O1_PREP) n_o1p++;
             n_o1++;
             // symbol table (16 B/pair), pair counts (4 B/pair), coded table scratch
             // + 16-bit pair keys of the partitioned pair count (large alphabets without a model);
@@ -234,12 +235,12 @@ int enc_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
     {
         // streams of different routes are independent: their launches go to side streams so that the
         // few long PACK / RLE order-1 streams of a mixed batch (a method trial) overlap the rest
-        const uint32_t routes[3] = {ROUTE_O1_WIDE, ROUTE_O1, ROUTE_O0};        // longest first
-        const bool have[3] = {n_o1w != 0, n_o1 > n_o1w, n_o0 != 0};
-        const int nr = (int)have[0] + have[1] + have[2];
+        const uint32_t routes[4] = {ROUTE_O1_PREP, ROUTE_O1_WIDE, ROUTE_O1, ROUTE_O0};        // longest first
+        const bool have[4] = {n_o1p != 0, n_o1w != 0, n_o1 > n_o1w + n_o1p, n_o0 != 0};
+        const int nr = (int)have[0] + have[1] + have[2] + have[3];
         if (nr > 1) CK(cudaEventRecord(Ln.fork, st));
         int used = 0;
-        for (int i = 0; i < 3; i++) {
+        for (int i = 0; i < 4; i++) {
             if (!have[i]) continue;
             cudaStream_t s2 = used == 0 ? st : Ln.aux[used - 1];
             if (used) CK(cudaStreamWaitEvent(s2, Ln.fork, 0));

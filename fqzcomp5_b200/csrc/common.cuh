@@ -49,6 +49,7 @@ enum : uint32_t {
     ROUTE_O1 = 1,           // order-1 kernel
     ROUTE_NONE = 2,         // not coded (STRIPE parent, assembled by stripe_select)
     ROUTE_O1_WIDE = 3,      // order-1 kernel with more shared memory per stream (PACK / RLE in front)
+    ROUTE_O1_PREP = 4,      // order-1 stream prepared by prep_kernel: the lean chains-only kernel
 };
 constexpr uint32_t MODEL_HDR_WORDS = 260;   // 256 counts, nsym, 3 pad
 constexpr uint32_t STRIPE_LIST_BYTES = 1024;  // 255 job indices behind a STRIPE parent's slot

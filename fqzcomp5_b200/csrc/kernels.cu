@@ -31,7 +31,9 @@ struct CapCheck {
 // inslot: leave the finished stream contiguous inside its slot (head moved up against the payload,
 // as the reference's memmove at rANS_static32x16pr.c:249-251 does the other way round) and report it
 // as tail / tail_len with head_len 0, so that no packing pass is needed.
-template <bool O1>
+// PREPPED: the stream went through prep_kernel (prep.cuh); the in-warp transforms and model building are
+// compiled out, which leaves a kernel with fewer registers and less shared memory per stream.
+template <bool O1, bool PREPPED = false>
 __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const Pool &pool, int lane, bool inslot) {
     int order = J.order;
     const uint8_t *in = J.in;
@@ -40,7 +42,7 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
     // PACK / RLE streams: transforms, counts and the order-1 model may have been done by prep_kernel (prep.cuh)
     const Prep *P = (J.prep && ((const Prep *)J.prep)->state == 1) ? (const Prep *)J.prep : nullptr;
     CapCheck cc{J.cap, 1, J.cap != 0};            // (out && *out_size == 0) -> NULL (:1227)
-    uint32_t status = ST_OK;
+    uint32_t status = (PREPPED && !P) ? ST_UNSUPPORTED : ST_OK;      // routed here without a prep area: host bug
     uint32_t head_len = 0, tail_len = 0;
     const uint8_t *tail = nullptr;
 
@@ -76,8 +78,8 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
             cc.require((uint64_t)meta + 256);
             uint32_t pmeta = 0, plen = 0;
             bool packed;
-            if (P) { packed = P->packed != 0; pmeta = P->pmeta; plen = P->plen; }
-            else packed = work && warp_pack(in, in_size, out + meta, &pmeta, work, &plen, smem, lane);
+            if (PREPPED || P) { packed = P->packed != 0; pmeta = P->pmeta; plen = P->plen; }
+            else if constexpr (!PREPPED) packed = work && warp_pack(in, in_size, out + meta, &pmeta, work, &plen, smem, lane);
             if (!packed) flag &= ~X_PACK;
             else {
                 in = work; work += (plen + 15) & ~15u;
@@ -96,8 +98,8 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
             // work: [literals in_size][meta in_size+257+16]
             uint8_t *lits = work, *rmeta = work + ((in_size + 15) & ~15u);
             uint32_t rle_len = 0, rmeta_len = 0;
-            if (P) { rle_len = P->rle_len; rmeta_len = P->rmeta_len; }
-            else warp_rle_encode(in, in_size, lits, &rle_len, rmeta, &rmeta_len, smem, lane);
+            if (PREPPED || P) { rle_len = P->rle_len; rmeta_len = P->rmeta_len; }
+            else if constexpr (!PREPPED) warp_rle_encode(in, in_size, lits, &rle_len, rmeta, &rmeta_len, smem, lane);
             if ((double)((uint64_t)rle_len + rmeta_len) >= .99 * (double)in_size) {
                 flag &= ~X_RLE; do_rle = 0;
             } else {
@@ -155,8 +157,9 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
                 uint8_t *dyn = smem + sizeof(EncO1Smem);
                 uint32_t dynb = smem_bytes - (uint32_t)sizeof(EncO1Smem);
                 if (P && P->model == 2)
-                    e = do_simd ? enc_o1_prepped<32>(in, in_size, out + meta, oend, &tab, &ptr, S, dyn, dynb, *P, J.prep, J.in_size, lane)
-                                : enc_o1_prepped<4>(in, in_size, out + meta, oend, &tab, &ptr, S, dyn, dynb, *P, J.prep, J.in_size, lane);
+                    e = do_simd ? enc_o1_prepped<32>(in, in_size, out + meta, oend, &tab, &ptr, smem, smem_bytes, *P, J.prep, J.in_size, lane)
+                                : enc_o1_prepped<4>(in, in_size, out + meta, oend, &tab, &ptr, smem, smem_bytes, *P, J.prep, J.in_size, lane);
+                else if constexpr (PREPPED) e = 1;          // N == 32 with fewer than 32 bytes: the reference fails too
                 else {
                     if (P) model = nullptr;       // the order-1 coder's own model layout differs from Prep::F
                     e = do_simd ? enc_o1<32>(in, in_size, out + meta, oend, &tab, &ptr, S, dyn, dynb, pool, lane, model)
@@ -204,14 +207,17 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
     __syncwarp();
 }
 
-template <bool O1>
-__global__ void __launch_bounds__((O1 ? ENC_WARPS_O1 : ENC_WARPS) * 32, O1 ? 11 : 7)   // O1: 22 warps per SM (<= 92 registers); O0: 28 warps (<= 72) so that the 3815 streams of a 1 GB block are one wave (unbounded the compiler takes 179 registers and residency collapses)
+// O1: 22 warps per SM (<= 92 registers); O0: 28 warps (<= 72) so that the 3815 streams of a 1 GB block are one
+// wave (unbounded the compiler takes 179 registers and residency collapses); order-1 streams that went through
+// prep_kernel: 28 warps (<= 72 registers, 7.5 KiB of shared memory each), one wave as well
+template <bool O1, bool PREPPED>
+__global__ void __launch_bounds__((O1 ? ENC_WARPS_O1 : ENC_WARPS) * 32, PREPPED ? 14 : O1 ? 11 : 7)
 enc_kernel(EncJob *jobs, uint32_t njobs, uint32_t warp_smem, Pool pool, uint32_t route, uint32_t inslot) {
     extern __shared__ __align__(16) uint8_t smem_all[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t j = blockIdx.x * (O1 ? ENC_WARPS_O1 : ENC_WARPS) + wid;
     if (j >= njobs || jobs[j].route != route) return;   // another launch's stream, or a STRIPE parent
-    enc_stream<O1>(jobs[j], smem_all + (size_t)wid * warp_smem, warp_smem, pool, lane, inslot != 0);
+    enc_stream<O1, PREPPED>(jobs[j], smem_all + (size_t)wid * warp_smem, warp_smem, pool, lane, inslot != 0);
 }
 
 // ------------------------------------------------------------------------
@@ -619,20 +625,24 @@ cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, uint32_t route, Pool pool, cu
     if (!n) return cudaSuccess;
     const bool o1 = route != ROUTE_O0;
     if (o1) { cudaError_t e = ensure_rcp_table(st); if (e != cudaSuccess) return e; }
-    uint32_t ws = route == ROUTE_O1_WIDE ? ENC_SMEM_O1_WIDE : o1 ? ENC_SMEM_O1 : ENC_SMEM_O0;
-    if (o1) {                              // tuning knob: shared memory per order-1 stream
+    uint32_t ws = route == ROUTE_O1_WIDE ? ENC_SMEM_O1_WIDE : route == ROUTE_O1_PREP ? ENC_SMEM_O1_PREP
+                : o1 ? ENC_SMEM_O1 : ENC_SMEM_O0;
+    if (o1 && route != ROUTE_O1_PREP) {    // tuning knob: shared memory per order-1 stream
         static const char *e = getenv("B200RANS_ENC_O1_SMEM");
         static const char *ew = getenv("B200RANS_ENC_O1_WIDE_SMEM");
         const char *k = route == ROUTE_O1_WIDE ? ew : e;
         if (k && atoi(k) >= 8192 && atoi(k) <= 100000) ws = (uint32_t)atoi(k) & ~15u;
     }
     size_t sm = (size_t)ws * (o1 ? ENC_WARPS_O1 : ENC_WARPS);
-    if (o1) {
-        cudaFuncSetAttribute(enc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        enc_kernel<true><<<cdiv(n, ENC_WARPS_O1), ENC_WARPS_O1 * 32, sm, st>>>(d_jobs, n, ws, pool, route, inslot ? 1u : 0u);
+    if (route == ROUTE_O1_PREP) {
+        cudaFuncSetAttribute(enc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        enc_kernel<true, true><<<cdiv(n, ENC_WARPS_O1), ENC_WARPS_O1 * 32, sm, st>>>(d_jobs, n, ws, pool, route, inslot ? 1u : 0u);
+    } else if (o1) {
+        cudaFuncSetAttribute(enc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        enc_kernel<true, false><<<cdiv(n, ENC_WARPS_O1), ENC_WARPS_O1 * 32, sm, st>>>(d_jobs, n, ws, pool, route, inslot ? 1u : 0u);
     } else {
-        cudaFuncSetAttribute(enc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        enc_kernel<false><<<cdiv(n, ENC_WARPS), ENC_WARPS * 32, sm, st>>>(d_jobs, n, ws, pool, route, inslot ? 1u : 0u);
+        cudaFuncSetAttribute(enc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        enc_kernel<false, false><<<cdiv(n, ENC_WARPS), ENC_WARPS * 32, sm, st>>>(d_jobs, n, ws, pool, route, inslot ? 1u : 0u);
     }
     return cudaGetLastError();
 }

@@ -16,6 +16,9 @@ constexpr uint32_t ENC_SMEM_O1 = 9856;     // EncO1Smem header + 4-byte encoder 
 // order-1 streams that are PACKed / RLEd first (their alphabet is usually all 256 byte values):
 // room for the 8 x 256 counters of the partitioned pair count behind the EncO1Smem header
 constexpr uint32_t ENC_SMEM_O1_WIDE = 11520;
+// order-1 streams prepared by prep_kernel: ring + rank map (1280 bytes) + 4-byte encoder symbols for <= 40 symbols;
+// the order-0 coder of the run-length meta-data and of the table (6 KiB) uses the same bytes first.  28 warps per SM.
+constexpr uint32_t ENC_SMEM_O1_PREP = 7680;
 constexpr uint32_t DEC_SMEM_O0 = 8192;     // DecO0Smem, 8 KiB aligned
 constexpr uint32_t DEC_SMEM_O1 = 8192;     // DecO1Smem header + 16-bit cumulative rows + 64-bucket index for <= 41 symbols (26 warps per SM: measured 1.35x over 15 KiB / 256 buckets)
 

@@ -16,7 +16,6 @@
 namespace b200 {
 
 constexpr int PREP_THREADS = 256, PREP_WARPS = 8;
-constexpr uint32_t PREP_PAIRS = 6400;           // words of pair counters in shared memory (a group of context rows)
 
 // What the CTA leaves for the coder warp, at the head of the job's prep area (J.prep).
 struct __align__(16) Prep {
@@ -32,15 +31,17 @@ struct __align__(16) Prep {
     uint8_t  rank[256];     // order 1: symbol -> rank
 };
 // layout of the prep area behind the header
-struct PrepPlan { uint32_t o_H, o_sym, o_tbl, o_tmp, total; };
+constexpr uint32_t PREP_ROW_STRIDE = 768;      // a serialised row: at most 2 bytes per column plus a closing run token
+struct PrepPlan { uint32_t o_bkt, o_rows, o_sym, o_tbl, o_tmp, total; };
 __host__ __device__ inline PrepPlan prep_plan(uint32_t isz) {
     const uint32_t m = isz + 1 < 256 ? isz + 1 : 256;                      // alphabet of a short stream
     const uint32_t hw = m * m * 4;
     const uint32_t tbl = (4 * (uint64_t)isz + 2048 < 257 * 257 * 3 + 4 ? 4 * isz + 2048 : 257 * 257 * 3 + 4) + 64;
     PrepPlan p;
-    p.o_H = (uint32_t)((sizeof(Prep) + 255) & ~255u);
-    p.o_sym = p.o_H + ((hw + 255) & ~255u);
-    p.o_tbl = p.o_sym + ((hw + 255) & ~255u);
+    p.o_bkt = (uint32_t)((sizeof(Prep) + 255) & ~255u);                     // pairs dealt by context: isz + 32 bytes
+    p.o_rows = p.o_bkt + ((isz + 64 + 255) & ~255u);                        // serialised rows before they are packed
+    p.o_sym = p.o_rows + ((m * PREP_ROW_STRIDE + 255) & ~255u);             // encoder symbols
+    p.o_tbl = p.o_sym + ((hw + 255) & ~255u);                               // the table, uncompressed
     p.o_tmp = p.o_tbl + ((tbl + 255) & ~255u);                              // scratch of the table's order-0 coder
     p.total = p.o_tmp + ((compress_bound(tbl, 0) + 64 + 255) & ~255u);
     return p;
@@ -49,7 +50,8 @@ __host__ __device__ inline PrepPlan prep_plan(uint32_t isz) {
 struct __align__(16) PrepSmem {
     uint32_t Fw[PREP_WARPS][256];   // warp-private order-0 bins; PACK: byte flags / codes in Fw[0]; RLE: scores in Fw[1];
                                     // order 1: per-warp scratch of the greedy shave
-    uint32_t Hs[PREP_PAIRS];        // pair counters of one group of context rows
+    uint32_t Hs[256];               // bucket cursors of the pair dealing
+    uint32_t bstart[260];           // first byte of every context's bucket (and the end of the last)
     uint32_t T[256];                // order-0 counts (symbol space), then row totals (rank space)
     uint32_t rowlen[256];           // serialised row lengths, then offsets
     uint16_t S16[256];              // stored total of each row
@@ -158,20 +160,33 @@ __device__ inline bool cta_pack(const uint8_t *in, uint32_t n, uint8_t *meta, ui
 // ------------------------------------------------------------------ RLE (rle.c:48-138)
 // A symbol is run-length coded iff it repeats its predecessor more often than not.  Literals: one byte per
 // maximal run of such a symbol, one byte per occurrence otherwise; (run length - 1) goes to a varint stream in
-// run order.  Each warp owns a contiguous chunk; a run still open at the end of a chunk is closed by the first
-// emitting position of a later chunk (its varint is the last one of the chunk that opened it).
-template <bool WRITE>
+// run order.  Each warp owns a contiguous chunk and writes its literals and varints to staging areas in ONE pass;
+// a run still open at the end of a chunk is closed by the first emitting position of a later chunk (its varint
+// is the last one of the chunk that opened it); the pieces are then copied to their final, packed places.
 __device__ __forceinline__ void rle_chunk(const uint8_t *in, uint32_t lo, uint32_t hi, const int32_t *score,
                                           uint8_t *lits, uint8_t *runs, uint32_t &nl, uint32_t &nr, bool &open,
                                           uint32_t &open_start, uint32_t &first, int lane) {
     const uint32_t lt = lanemask_lt();
     nl = 0; nr = 0; open = false; open_start = 0; first = 0xffffffffu;
+    if (lo >= hi) return;
+    uint32_t carry = lo ? in[lo - 1] : 0x200u;              // byte in front of the round
+    uint32_t cn = lo + lane < hi ? in[lo + lane] : 0x100u;  // next round's bytes, one round ahead
     for (uint32_t base = lo; base < hi; base += 32) {
         const uint32_t p = base + lane;
         const bool valid = p < hi;
-        const uint32_t c = valid ? in[p] : 0x100u;
-        const uint32_t pc = (valid && p) ? in[p - 1] : 0x200u;
+        const uint32_t c = cn;
+        cn = base + 32 + lane < hi ? in[base + 32 + lane] : 0x100u;
+        uint32_t pc = __shfl_up_sync(FULL, c, 1);
+        if (lane == 0) pc = carry;
+        carry = __shfl_sync(FULL, c, 31);
         const bool isr = valid && score[c & 0xff] > 0;
+        const uint32_t anyr = __ballot_sync(FULL, isr);
+        if (!anyr && !open) {                               // nothing run-length coded here: every byte is a literal
+            if (first == 0xffffffffu) first = base;
+            if (valid) lits[nl + lane] = (uint8_t)c;
+            nl += min(32u, hi - base);
+            continue;
+        }
         const bool cont = isr && p && pc == c;              // continues a run: emits nothing
         const bool emit = valid && !cont;
         const uint32_t E = __ballot_sync(FULL, emit);
@@ -189,10 +204,10 @@ __device__ __forceinline__ void rle_chunk(const uint8_t *in, uint32_t lo, uint32
         if (C) {
             const uint32_t vs = closes ? var_size_u32(rl) : 0;
             const uint32_t vincl = warp_incl_scan(vs, lane);
-            if (WRITE && closes) var_put_u32(runs + nr + vincl - vs, rl);
+            if (closes) var_put_u32(runs + nr + vincl - vs, rl);
             nr += __shfl_sync(FULL, vincl, 31);
         }
-        if (WRITE && emit) lits[nl + __popc(E & lt)] = (uint8_t)c;
+        if (emit) lits[nl + __popc(E & lt)] = (uint8_t)c;
         nl += __popc(E);
         const int hl = 31 - __clz(E);
         open = (R >> hl) & 1;
@@ -200,6 +215,7 @@ __device__ __forceinline__ void rle_chunk(const uint8_t *in, uint32_t lo, uint32
     }
 }
 
+// lits / meta: final buffers; meta has room for 1 + 256 + 64 + 2 * (n + 64) bytes behind it (staging)
 __device__ inline void cta_rle_encode(const uint8_t *in, uint32_t n, uint8_t *lits, uint32_t *lits_len, uint8_t *meta,
                                       uint32_t *meta_len, PrepSmem &S) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -239,28 +255,34 @@ __device__ inline void cta_rle_encode(const uint8_t *in, uint32_t n, uint8_t *li
     if (pr) meta[1 + r] = (uint8_t)tid;
     if (tid == 0) meta[0] = (uint8_t)nsyms;
     uint8_t *runs = meta + 1 + nsyms;
-    // chunks of whole 32-byte rounds
+    // chunks of whole 32-byte rounds; staging: chunk w's varints at stage_r + lo + 8w, its literals at stage_l + lo
     const uint32_t CH = (((n + PREP_WARPS - 1) / PREP_WARPS) + 31) & ~31u;
     const uint32_t lo = min(n, (uint32_t)wid * CH), hi = min(n, lo + CH);
+    uint8_t *stage_r = meta + 384, *stage_l = meta + 384 + ((n + 64 + 64 + 15) & ~15u);
     uint32_t nl, nr, ostart, first;
     bool open;
-    rle_chunk<false>(in, lo, hi, score, nullptr, nullptr, nl, nr, open, ostart, first, lane);
-    if (lane == 0) { S.c_nl[wid] = nl; S.c_nr[wid] = nr; S.c_open[wid] = open; S.c_start[wid] = ostart; S.c_first[wid] = first; }
+    rle_chunk(in, lo, hi, score, stage_l + lo, stage_r + lo + 8 * wid, nl, nr, open, ostart, first, lane);
+    if (lane == 0) { S.c_nl[wid] = nl; S.c_nr[wid] = nr; S.c_first[wid] = first; }
     __syncthreads();
     // the run open at the end of this chunk ends at the first emitter behind it (or at n)
-    uint32_t next_first = n, lit_off = 0, run_off = 0, lit_tot = 0, run_tot = 0;
+    uint32_t next_first = n;
     for (int w = PREP_WARPS - 1; w > wid; w--) if (S.c_first[w] != 0xffffffffu) next_first = S.c_first[w];
-    const uint32_t tail_rl = open ? next_first - ostart - 1 : 0;
-    const uint32_t tail_sz = open ? var_size_u32(tail_rl) : 0;
+    if (open) {
+        const uint32_t tail_rl = next_first - ostart - 1;
+        if (lane == 0) var_put_u32(stage_r + lo + 8 * wid + nr, tail_rl);
+        nr += var_size_u32(tail_rl);
+    }
     __syncthreads();
-    if (lane == 0) S.c_nr[wid] = nr + tail_sz;
+    if (lane == 0) S.c_nr[wid] = nr;
     __syncthreads();
+    uint32_t lit_off = 0, run_off = 0, lit_tot = 0, run_tot = 0;
     for (int w = 0; w < PREP_WARPS; w++) {
         if (w < wid) { lit_off += S.c_nl[w]; run_off += S.c_nr[w]; }
         lit_tot += S.c_nl[w]; run_tot += S.c_nr[w];
     }
-    rle_chunk<true>(in, lo, hi, score, lits + lit_off, runs + run_off, nl, nr, open, ostart, first, lane);
-    if (open && lane == 0) var_put_u32(runs + run_off + nr, tail_rl);
+    __syncwarp();
+    warp_copy(lits + lit_off, stage_l + lo, nl, lane);
+    warp_copy(runs + run_off, stage_r + lo + 8 * wid, nr, lane);
     *lits_len = lit_tot;
     *meta_len = 1 + nsyms + run_tot;
     __syncthreads();
@@ -290,59 +312,76 @@ __device__ inline void cta_hist8(const uint8_t *in, uint32_t n, PrepSmem &S) {
 }
 
 // ------------------------------------------------------------------ order-1 model (rANS_static16_int.h:312-421)
-// Pair counts H[rank(prev)][rank(cur)] in global memory (the first byte follows symbol 0, utils.h:279-357): the
-// contexts are taken a group at a time, as many rows as fit the shared-memory counters, the data being read
-// once per group (it sits in L1 / L2 by then); no read-modify-write ever reaches global memory.
-__device__ inline void cta_pair_counts(const uint8_t *in, uint32_t n, uint32_t nsym, uint32_t *H, PrepSmem &S) {
-    const int tid = threadIdx.x;
-    const uint32_t rpp = min(nsym, PREP_PAIRS / nsym);          // rows per pass (nsym <= 256 -> at least 25)
-    const uint32_t Hs_s = (uint32_t)__cvta_generic_to_shared(S.Hs);
+// Pair counts without a 256 x 256 table: the number of pairs per context follows from the order-0 counts, so
+// every byte is dealt into its CONTEXT's bucket (a counting sort on the previous byte; the first byte follows
+// symbol 0, utils.h:279-357).  Row i of the matrix is then the histogram of bucket i -- about n / nsym bytes --
+// which a warp takes in its private 256 shared-memory bins whenever it needs the row.
+//   bucket: n (+ N) bytes of symbol ranks grouped by context rank;  S.rowlen[r] = first byte of bucket r (the
+//   start of bucket nsym closes the last one);  the lane starts (:325-327) are appended to the bucket of symbol 0.
+__device__ inline void cta_pair_buckets(const uint8_t *in, uint32_t n, int N, uint32_t nsym, uint8_t *bucket,
+                                        PrepSmem &S) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t seg = n / N;
+    // bucket sizes in rank space: occurrences of the symbol except as the last byte, the virtual 0 in front of the
+    // first byte, and the N-1 lane starts for symbol 0
+    uint32_t sz = 0;
+    if ((uint32_t)tid < nsym) {
+        const uint32_t s = S.sym[tid];
+        sz = S.T[s] - (s == in[n - 1] ? 1u : 0u) + (s == 0 ? (uint32_t)N : 0u);
+    }
+    uint32_t incl = warp_incl_scan(sz, lane);
+    if (lane == 31) S.wtot[wid] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+#pragma unroll
+    for (int w = 0; w < PREP_WARPS; w++) if (w < wid) before += S.wtot[w];
+    const uint32_t start = before + incl - sz;
+    uint32_t *cur = S.Hs;                       // cursors, then (rowlen) the bucket starts
+    cur[tid] = start;
+    S.rowlen[tid] = start;
+    __syncthreads();
+    auto deal = [&](uint32_t rp, uint32_t rc) { bucket[atomicAdd(&cur[rp], 1u)] = (uint8_t)rc; };
+    const uint8_t *rank = S.rank;
     uint32_t head = (uint32_t)((16 - ((uintptr_t)in & 15)) & 15);
     if (head > n) head = n;
+    if ((uint32_t)tid < head) deal(rank[tid ? in[tid - 1] : 0], rank[in[tid]]);
     const uint8_t *p = in + head;
     const uint32_t rest = n - head, nv = rest >> 4;
     const uint4 *v = (const uint4 *)p;
-    const uint8_t *rank = S.rank;
-    for (uint32_t c0 = 0; c0 < nsym; c0 += rpp) {
-        const uint32_t rows = min(rpp, nsym - c0), words = rows * nsym;
-        for (uint32_t j = tid; j < words; j += PREP_THREADS) S.Hs[j] = 0;
-        __syncthreads();
-        auto add1 = [&](uint32_t rp, uint32_t rc) {
-            const uint32_t q = rp - c0;
-            if (q < rows) atomicAdd(&S.Hs[q * nsym + rc], 1u);
-        };
-        if ((uint32_t)tid < head) add1(rank[tid ? in[tid - 1] : 0], rank[in[tid]]);
-        for (uint32_t i = tid; i < nv; i += PREP_THREADS) {
-            const uint4 q = v[i];
-            const uint32_t pb = (i || head) ? p[16 * (size_t)i - 1] : 0;
-            const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
-            uint32_t rp = rank[pb], last = 0, cnt = 0;          // cnt == 0: adding it is harmless
+    for (uint32_t i = tid; i < nv; i += PREP_THREADS) {
+        const uint4 q = v[i];
+        const uint32_t pb = (i || head) ? p[16 * (size_t)i - 1] : 0;
+        const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+        uint32_t rp = rank[pb];
 #pragma unroll
-            for (int a = 0; a < 4; a++)
+        for (int a = 0; a < 4; a++)
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const uint32_t rc = rank[(w4[a] >> (8 * b)) & 0xff];
-                    const uint32_t qrow = rp - c0;
-                    const uint32_t idx = qrow < rows ? qrow * nsym + rc : 0xffffffffu;   // pairs of other groups: no counter
-                    // close the open stretch when the pair changes (predicated shared-memory reduction)
-                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, %1;\n\t@p red.shared.add.u32 [%2], %3;\n\t}"
-                                 ::"r"(idx), "r"(last), "r"(Hs_s + (last == 0xffffffffu ? 0u : last) * 4),
-                                   "r"(last == 0xffffffffu ? 0u : cnt) : "memory");
-                    cnt = (idx == last) ? cnt + 1 : 1;
-                    last = idx;
-                    rp = rc;
-                }
-            if (last != 0xffffffffu) atomicAdd(&S.Hs[last], cnt);
-        }
-        for (uint32_t t = (nv << 4) + tid; t < rest; t += PREP_THREADS) {
-            const uint32_t pos = head + t;
-            add1(rank[pos ? in[pos - 1] : 0], rank[in[pos]]);
-        }
-        __syncthreads();
-        uint32_t *dst = H + (size_t)c0 * nsym;
-        for (uint32_t j = tid; j < words; j += PREP_THREADS) dst[j] = S.Hs[j];
-        __syncthreads();
+            for (int b = 0; b < 4; b++) {
+                const uint32_t rc = rank[(w4[a] >> (8 * b)) & 0xff];
+                deal(rp, rc);
+                rp = rc;
+            }
     }
+    for (uint32_t t = (nv << 4) + tid; t < rest; t += PREP_THREADS) {
+        const uint32_t pos = head + t;
+        deal(rank[pos ? in[pos - 1] : 0], rank[in[pos]]);
+    }
+    if (tid >= 1 && tid < N) deal(rank[0], rank[in[(size_t)tid * seg]]);      // lanes 1..N-1 start in context 0
+    __threadfence_block();
+    __syncthreads();
+}
+
+// the counts of context row i, lane l getting columns 8l..8l+7: histogram of bucket i in the warp's bins
+__device__ __forceinline__ void row_from_bucket(const uint8_t *bucket, uint32_t b0, uint32_t b1, uint32_t *bins,
+                                                uint32_t (&f)[8], int lane) {
+    uint4 *z = (uint4 *)bins;
+    z[lane] = make_uint4(0, 0, 0, 0); z[lane + 32] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    for (uint32_t k = b0 + lane; k < b1; k += 32) atomicAdd(&bins[bucket[k]], 1u);
+    __syncwarp();
+    const uint4 a = z[2 * lane], b = z[2 * lane + 1];
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    __syncwarp();
 }
 
 // load / store the 8 columns a lane owns of one row
@@ -438,10 +477,9 @@ __device__ __forceinline__ uint32_t row_emit(const uint32_t (&f)[8], uint32_t ns
 
 // The whole order-1 model of `in`: counts in S.T on entry (symbol space, cta_hist8).  Leaves the uncompressed
 // table (first byte = shift << 4) at tbl, the encoder symbols at symtab, the rank map in P.  N = lanes of the coder.
-__device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint32_t *H, uint32_t *symtab, uint8_t *tbl,
-                                    Prep &P, PrepSmem &S) {
+__device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint8_t *bucket, uint8_t *rowstage,
+                                    uint32_t *symtab, uint8_t *tbl, Prep &P, PrepSmem &S) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint32_t seg = n / N;
     // ---- alphabet = symbols present, plus 0 (:357-361)
     const bool pres = S.T[tid] != 0 || tid == 0;
     {
@@ -454,25 +492,25 @@ __device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint32
     if (pres) S.sym[r] = (uint8_t)tid;
     P.rank[tid] = pres ? (uint8_t)r : 0xff;
     __syncthreads();
-    // ---- pair counts, then the lane starts in context 0 (:325-327)
-    cta_pair_counts(in, n, nsym, H, S);
-    if (tid >= 1 && tid < N) atomicAdd(&H[(size_t)S.rank[0] * nsym + S.rank[in[(size_t)tid * seg]]], 1u);
-    __threadfence_block();
+    // ---- pairs dealt into their contexts' buckets (the lane starts of :325-327 included)
+    cta_pair_buckets(in, n, N, nsym, bucket, S);
+    S.bstart[tid] = S.rowlen[tid];
+    if (tid == 0) S.bstart[256] = n + (uint32_t)N - 1;
     __syncthreads();
     const uint32_t last_rank = S.rank[in[n - 1]];
     const uint32_t j0 = (uint32_t)lane * 8;
+    uint32_t *bins = S.Fw[wid];
     // ---- sweep 1: row totals (the last symbol's gets one extra, utils.h:311,345) and the statistics of
     // rans_compute_shift (rANS_static4x16pr.c:357-420); warp w takes rows w, w+8, ...
     double e10 = 0, e12 = 0;
     uint32_t max_tot = 0;
     for (uint32_t i = wid; i < nsym; i += PREP_WARPS) {
-        uint32_t f[8], loc = 0;
-        row_load8(H + (size_t)i * nsym, nsym, j0, f);
-#pragma unroll
-        for (int t = 0; t < 8; t++) loc += f[t];
-        const uint32_t Ti = warp_sum(loc) + (i == last_rank ? 1u : 0u);
+        uint32_t f[8];
+        const uint32_t b0 = S.bstart[i], b1 = S.bstart[i + 1];
+        const uint32_t Ti = b1 - b0 + (i == last_rank ? 1u : 0u);
         if (lane == 0) S.T[i] = Ti;
         if (!Ti) { if (lane == 0) S.S16[i] = 0; continue; }
+        row_from_bucket(bucket, b0, b1, bins, f, lane);
         uint32_t max_val = round2(Ti);
         uint32_t cnt = 0;                           // ns | sm10 << 10 | sm12 << 20
 #pragma unroll
@@ -513,16 +551,14 @@ __device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint32
     for (int w = 0; w < PREP_WARPS; w++) { e10 += S.red[0][w]; e12 += S.red[1][w]; max_tot = max(max_tot, S.redu[w]); }
     const uint32_t shift = (e10 / e12 < 1.01 || max_tot <= 1024) ? 10 : 12;
     __syncthreads();
-    // ---- sweep 2a: normalise_freq of every row (rANS_static16_int.h:97-146) to its stored total; the row stays
-    // normalised in H; its serialised length goes to rowlen
+    // ---- sweep 2: normalise_freq of every row (rANS_static16_int.h:97-146) to its stored total, serialise it
+    // (encode_freq_d, :278-306) into its staging slot and build its encoder symbols (rANS_word.h:201-272)
     int err = 0;
-    uint32_t *shave = S.Fw[wid];
     for (uint32_t i = wid; i < nsym; i += PREP_WARPS) {
         const uint32_t Ti = S.T[i];
         if (!Ti) { if (lane == 0) S.rowlen[i] = 0; continue; }
-        uint32_t *row = H + (size_t)i * nsym;
         uint32_t f[8];
-        row_load8(row, nsym, j0, f);
+        row_from_bucket(bucket, S.bstart[i], S.bstart[i + 1], bins, f, lane);
         uint32_t mv = S.S16[i];
         if (shift == 10 && mv > 1024) mv = 1024;
         uint32_t size = Ti;
@@ -560,29 +596,29 @@ __device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint32
                 break;
             }
             if (pass == 0) { size = sum; continue; }
-            // greedy shave (rare): serial over the row through the warp's scratch
+            // greedy shave (rare): serial over the row through the warp's bins
 #pragma unroll
-            for (int t = 0; t < 8; t++) shave[j0 + t] = f[t];
+            for (int t = 0; t < 8; t++) bins[j0 + t] = f[t];
             __syncwarp();
             if (lane == 0) {
                 adjust += (int)fb - 1;
-                shave[big] = 1;
+                bins[big] = 1;
                 for (uint32_t j = 0; adjust && j < nsym; j++) {
-                    if (shave[j] < 2) continue;
-                    const int d = (shave[j] > (uint32_t)-adjust) ? adjust : 1 - (int)shave[j];
-                    shave[j] += d;
+                    if (bins[j] < 2) continue;
+                    const int d = (bins[j] > (uint32_t)-adjust) ? adjust : 1 - (int)bins[j];
+                    bins[j] += d;
                     adjust -= d;
                 }
-                if (!shave[big]) err = 1;
+                if (!bins[big]) err = 1;
             }
             __syncwarp();
 #pragma unroll
-            for (int t = 0; t < 8; t++) f[t] = shave[j0 + t];
+            for (int t = 0; t < 8; t++) f[t] = bins[j0 + t];
             __syncwarp();
         }
-        row_store8(row, nsym, j0, f);
-        const uint32_t rb = row_emit(f, nsym, mv, shift, nullptr, 0, nullptr, lane);
-        if (lane == 0) { S.S16[i] = (uint16_t)mv; S.rowlen[i] = rb; }
+        const uint32_t rb = row_emit(f, nsym, mv, shift, rowstage + (size_t)i * PREP_ROW_STRIDE, 0,
+                                     symtab + (size_t)i * nsym, lane);
+        if (lane == 0) S.rowlen[i] = rb;
     }
     err = __any_sync(FULL, err);
     if (err && lane == 0) P.err = 1;
@@ -607,23 +643,20 @@ __device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint32
     }
     __threadfence_block();
     __syncthreads();
-    if (wid == 0) {                              // exclusive scan of the row lengths (8 per lane)
-        uint32_t l8[8], loc = 0;
+    uint32_t mylen = (uint32_t)tid < nsym ? S.rowlen[tid] : 0;      // thread t owns row t
+    {
+        const uint32_t incl = warp_incl_scan(mylen, lane);
+        if (lane == 31) S.wtot[wid] = incl;
+        __syncthreads();
+        uint32_t before = S.bc[0];
 #pragma unroll
-        for (int t = 0; t < 8; t++) { l8[t] = j0 + t < nsym ? S.rowlen[j0 + t] : 0; loc += l8[t]; }
-        uint32_t x = S.bc[0] + warp_incl_scan(loc, lane) - loc;
-#pragma unroll
-        for (int t = 0; t < 8; t++) { if (j0 + t < nsym) S.rowlen[j0 + t] = x; x += l8[t]; }
-        if (lane == 31) S.bc[1] = x;             // total table length
+        for (int w = 0; w < PREP_WARPS; w++) if (w < wid) before += S.wtot[w];
+        S.bstart[tid] = before + incl - mylen;          // (the bucket starts are dead: row offsets in the table)
+        if (tid == PREP_THREADS - 1) S.bc[1] = before + incl;
     }
     __syncthreads();
-    // ---- sweep 2b: serialise (encode_freq_d, :278-306) and build the encoder symbols (rANS_word.h:201-272)
-    for (uint32_t i = wid; i < nsym; i += PREP_WARPS) {
-        if (!S.T[i]) continue;
-        uint32_t f[8];
-        row_load8(H + (size_t)i * nsym, nsym, j0, f);
-        row_emit(f, nsym, S.S16[i], shift, tbl, S.rowlen[i], symtab + (size_t)i * nsym, lane);
-    }
+    for (uint32_t i = wid; i < nsym; i += PREP_WARPS)
+        warp_copy(tbl + S.bstart[i], rowstage + (size_t)i * PREP_ROW_STRIDE, S.rowlen[i], lane);
     __threadfence_block();
     __syncthreads();
     if (tid == 0) { P.nsym = nsym; P.shift = shift; P.tl = S.bc[1]; }
@@ -632,9 +665,15 @@ __device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint32
 // ------------------------------------------------------------------ the coder warp's side
 // Order-1 stream whose model the CTA built: the table goes to `out` raw or, when longer than 1000 bytes and it
 // pays, through the 4-lane order-0 coder (rANS_static16_int.h:396-412); then the state chains.
+// Shared memory of a warp in the chains-only kernel: [ring ORING][rank 256][encoder symbols when they fit]; the
+// order-0 coder of the table (and of the run-length meta-data before it) uses the same bytes from the start.
+struct __align__(16) EncPrepSmem {
+    uint8_t ring[ORING];
+    uint8_t rank[256];
+};
 template <int N>
 __device__ int enc_o1_prepped(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_end, uint32_t *tab_len,
-                              uint8_t **ptr_out, EncO1Smem &S, uint8_t *dyn, uint32_t dyn_bytes, const Prep &P,
+                              uint8_t **ptr_out, uint8_t *smem, uint32_t smem_bytes, const Prep &P,
                               const uint8_t *prep_base, uint32_t prep_isz, int lane) {
     *tab_len = 0;
     *ptr_out = out_end;
@@ -645,15 +684,13 @@ __device__ int enc_o1_prepped(const uint8_t *in, uint32_t n, uint8_t *out, uint8
     uint8_t *tmp = const_cast<uint8_t *>(prep_base) + pl.o_tmp;
     const uint32_t nsym = P.nsym, shift = P.shift;
     uint32_t tl = P.tl;
-    ((uint2 *)S.rank)[lane] = ((const uint2 *)P.rank)[lane];
-    __syncwarp();
     bool raw = true;
     if (tl > 1000) {
         const uint32_t usz = tl - 1;
         const uint32_t cb = (compress_bound(usz, 0) - 20) & ~1u;
         uint32_t ctab = 0;
         uint8_t *cptr = nullptr;
-        if (enc_o0<4>(tbl + 1, usz, tmp, tmp + cb, &ctab, &cptr, *(EncO0Smem *)dyn, lane) == 0) {
+        if (enc_o0<4>(tbl + 1, usz, tmp, tmp + cb, &ctab, &cptr, *(EncO0Smem *)smem, lane) == 0) {
             const uint32_t pay = (uint32_t)(tmp + cb - cptr), csz = ctab + pay;
             if (csz + 6 < tl) {
                 uint32_t h = 1;
@@ -674,17 +711,19 @@ __device__ int enc_o1_prepped(const uint8_t *in, uint32_t n, uint8_t *out, uint8
     }
     if (raw) warp_copy(out, tbl, tl, lane);
     *tab_len = tl;
-    // encoder symbols: into shared memory when they fit (the order-0 scratch is dead by now)
+    // the chains: rank map and, when they fit, the encoder symbols in shared memory (the order-0 scratch is dead)
+    EncPrepSmem &S = *(EncPrepSmem *)smem;
+    ((uint2 *)S.rank)[lane] = ((const uint2 *)P.rank)[lane];
     const uint32_t hw = nsym * nsym;
-    const bool sym_smem = hw * 4 <= dyn_bytes;
+    const bool sym_smem = sizeof(EncPrepSmem) + hw * 4 <= smem_bytes;
     const uint32_t *symtab = gsym;
     if (sym_smem) {
-        uint32_t *d = (uint32_t *)dyn;
+        uint32_t *d = (uint32_t *)(smem + sizeof(EncPrepSmem));
         for (uint32_t j = lane; j < hw; j += 32) d[j] = gsym[j];
         symtab = d;
     }
     __syncwarp();
-    enc_o1_payload<N>(in, n, out, out_end, ptr_out, S, symtab, nsym, shift, sym_smem, lane);
+    enc_o1_payload<N>(in, n, out, out_end, ptr_out, S.ring, S.rank, symtab, nsym, shift, sym_smem, lane);
     return 0;
 }
 
@@ -734,7 +773,8 @@ __device__ inline void prep_stream(EncJob &J, PrepSmem &S) {
         if (o1 && !(N == 32 && in_size < 32)) {
             const PrepPlan pl = prep_plan(J.in_size);
             uint8_t *base = (uint8_t *)Pp;
-            cta_o1_model(in, in_size, N, (uint32_t *)(base + pl.o_H), (uint32_t *)(base + pl.o_sym), base + pl.o_tbl, P, S);
+            cta_o1_model(in, in_size, N, base + pl.o_bkt, base + pl.o_rows, (uint32_t *)(base + pl.o_sym),
+                         base + pl.o_tbl, P, S);
             model = 2;
         }
     }

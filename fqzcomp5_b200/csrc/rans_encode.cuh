@@ -868,18 +868,18 @@ __device__ inline void pair_counts_partitioned(const uint8_t *in, uint32_t n, ui
 // The order-1 state chains (rANS_static32x16pr.c:457-525, rANS_static4x16pr.c:460-518): lane z owns
 // [z*seg,(z+1)*seg); lane N-1 also the tail; every symbol is coded in the context of its predecessor, a
 // lane's first symbol in context 0.  symtab = 4-byte encoder symbols indexed (rank(ctx), rank(sym)), in
-// shared memory when sym_smem; S.rank maps symbols to ranks; the output ring is S.ring.
+// shared memory when sym_smem; rank (shared memory) maps symbols to ranks; ring = ORING bytes of output staging.
 // ------------------------------------------------------------------------
 template <int N>
 __device__ __forceinline__ void enc_o1_payload(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_end,
-                                               uint8_t **ptr_out, EncO1Smem &S, const uint32_t *symtab, uint32_t nsym,
-                                               uint32_t shift, bool sym_smem, int lane) {
+                                               uint8_t **ptr_out, uint8_t *ring, const uint8_t *rank,
+                                               const uint32_t *symtab, uint32_t nsym, uint32_t shift, bool sym_smem,
+                                               int lane) {
     const uint32_t seg = n / N;
     const bool act = lane < N;
     OutRing w;
-    w.init(out, out_end, S.ring);
+    w.init(out, out_end, ring);
     uint32_t R = RANS_L;
-    const uint8_t *rank = S.rank;
     {   // tail on lane N-1, from the end down to N*seg
         const bool lastl = lane == N - 1;
         for (uint32_t p = n - 1; p >= N * seg && p > 0; p--) {
@@ -896,7 +896,7 @@ __device__ __forceinline__ void enc_o1_payload(const uint8_t *in, uint32_t n, ui
     if (N == 32 && sym_smem && seg >= 32 && ((((uintptr_t)in) | seg) & 15) == 0) {
         // Hot loop: lane segments are 16-byte aligned, so every lane reads its symbols with
         // 128-bit loads (one group of 16 ahead) and the encoder symbols come from shared memory.
-        const uint32_t rank_s = (uint32_t)__cvta_generic_to_shared(S.rank);
+        const uint32_t rank_s = (uint32_t)__cvta_generic_to_shared(rank);
         const uint32_t sym_s = (uint32_t)__cvta_generic_to_shared(symtab);
         const uint4 *v = (const uint4 *)q;
         const uint32_t J = seg >> 4;
@@ -952,7 +952,7 @@ __device__ __forceinline__ void enc_o1_payload(const uint8_t *in, uint32_t n, ui
         // requested together before the group's 16 steps run, so one L2/DRAM round trip is paid
         // per group instead of per step.  Groups are counted from the END of the lane's segment
         // (any alignment, any length); the seg % 16 bytes at its start go through the loop below.
-        const uint32_t rank_s = (uint32_t)__cvta_generic_to_shared(S.rank);
+        const uint32_t rank_s = (uint32_t)__cvta_generic_to_shared(rank);
         const uint32_t J = seg >> 4, lead = seg & 15;
         const uint8_t *g0 = q + lead;                          // group j = bytes g0[16j .. 16j+15]
         auto rank_of = [&](uint32_t b) {
@@ -1291,7 +1291,7 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
     if (pool_fail) return 2;
     *tab_len = tl;
 
-    enc_o1_payload<N>(in, n, out, out_end, ptr_out, S, symtab, nsym, shift, sym_smem, lane);
+    enc_o1_payload<N>(in, n, out, out_end, ptr_out, S.ring, S.rank, symtab, nsym, shift, sym_smem, lane);
     return 0;
 }
 

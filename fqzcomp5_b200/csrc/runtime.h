@@ -91,8 +91,8 @@ inline int chunk_min_streams() { static int v = env_int("B200RANS_CHUNK_STREAMS"
 // chunk, the kernels of the previous and the D2H copy of the one before overlap.
 struct Lane {
     cudaStream_t st = nullptr;
-    cudaStream_t aux[2] = {nullptr, nullptr};   // side streams: coder launches of different routes run side by side
-    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // side streams: coder launches of different routes run side by side
+    cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
     Arena work;                 // device: jobs, slots, scratch, pool
     Arena io;                   // device: staged inputs / outputs of the host-buffer API
     Arena crc;                  // device: CRC-32 tables and tile values (kept apart from `work`, which an
