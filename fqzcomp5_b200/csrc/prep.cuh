@@ -215,7 +215,7 @@ __device__ __forceinline__ void rle_chunk(const uint8_t *in, uint32_t lo, uint32
     }
 }
 
-// lits / meta: final buffers; meta has room for 1 + 256 + 64 + 2 * (n + 64) bytes behind it (staging)
+// lits / meta: final buffers; meta has room for 3 * n + 1024 bytes (its own n + 321 at most, then the two staging areas)
 __device__ inline void cta_rle_encode(const uint8_t *in, uint32_t n, uint8_t *lits, uint32_t *lits_len, uint8_t *meta,
                                       uint32_t *meta_len, PrepSmem &S) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -258,7 +258,9 @@ __device__ inline void cta_rle_encode(const uint8_t *in, uint32_t n, uint8_t *li
     // chunks of whole 32-byte rounds; staging: chunk w's varints at stage_r + lo + 8w, its literals at stage_l + lo
     const uint32_t CH = (((n + PREP_WARPS - 1) / PREP_WARPS) + 31) & ~31u;
     const uint32_t lo = min(n, (uint32_t)wid * CH), hi = min(n, lo + CH);
-    uint8_t *stage_r = meta + 384, *stage_l = meta + 384 + ((n + 64 + 64 + 15) & ~15u);
+    // (both staging areas lie behind everything the final meta-data can occupy: a warp packing its piece must
+    // not write over the staged piece of another)
+    uint8_t *stage_r = meta + ((n + 400 + 15) & ~15u), *stage_l = stage_r + ((n + 128 + 15) & ~15u);
     uint32_t nl, nr, ostart, first;
     bool open;
     rle_chunk(in, lo, hi, score, stage_l + lo, stage_r + lo + 8 * wid, nl, nr, open, ostart, first, lane);
