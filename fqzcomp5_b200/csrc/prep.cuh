@@ -26,22 +26,28 @@ struct __align__(16) Prep {
     uint32_t model;         // 0 none, 1 order-0 counts in F, 2 order-1 model (table, symbols, rank)
     uint32_t nsym, shift, tl;       // order 1: alphabet size, precision, bytes of the uncompressed table
     uint32_t err;           // order 1: normalise_freq failed (the reference returns NULL)
-    uint32_t pad_[5];
+    uint32_t stream_syms;   // order 1: 1 = encoder symbols per position (E), 0 = symbol table
+    uint32_t pad_[4];
     uint32_t F[256];        // order-0 counts of the data that reaches the coder
     uint8_t  rank[256];     // order 1: symbol -> rank
 };
 // layout of the prep area behind the header
 constexpr uint32_t PREP_ROW_STRIDE = 768;      // a serialised row: at most 2 bytes per column plus a closing run token
-struct PrepPlan { uint32_t o_bkt, o_rows, o_sym, o_tbl, o_tmp, total; };
+// Alphabets whose nsym x nsym encoder symbols fit the coder warp's shared memory keep a symbol table; larger ones
+// get the encoder symbol of every POSITION instead (a 4-byte stream the chains read sequentially: a 256 x 256 table
+// per stream, looked up at random, is a DRAM sector per symbol).
+constexpr uint32_t PREP_SYM_MAX = 40;
+struct PrepPlan { uint32_t o_bkt, o_bpos, o_rows, o_sym, o_E, o_tbl, o_tmp, total; };
 __host__ __device__ inline PrepPlan prep_plan(uint32_t isz) {
     const uint32_t m = isz + 1 < 256 ? isz + 1 : 256;                      // alphabet of a short stream
-    const uint32_t hw = m * m * 4;
     const uint32_t tbl = (4 * (uint64_t)isz + 2048 < 257 * 257 * 3 + 4 ? 4 * isz + 2048 : 257 * 257 * 3 + 4) + 64;
     PrepPlan p;
     p.o_bkt = (uint32_t)((sizeof(Prep) + 255) & ~255u);                     // pairs dealt by context: isz + 32 bytes
-    p.o_rows = p.o_bkt + ((isz + 64 + 255) & ~255u);                        // serialised rows before they are packed
-    p.o_sym = p.o_rows + ((m * PREP_ROW_STRIDE + 255) & ~255u);             // encoder symbols
-    p.o_tbl = p.o_sym + ((hw + 255) & ~255u);                               // the table, uncompressed
+    p.o_bpos = p.o_bkt + ((isz + 64 + 255) & ~255u);                        // ... and where each came from (4 bytes)
+    p.o_rows = p.o_bpos + ((4 * (isz + 64) + 255) & ~255u);                 // serialised rows before they are packed
+    p.o_sym = p.o_rows + ((m * PREP_ROW_STRIDE + 255) & ~255u);             // encoder symbols, small alphabets
+    p.o_E = p.o_sym + ((PREP_SYM_MAX * PREP_SYM_MAX * 4 + 255) & ~255u);    // encoder symbol of every position
+    p.o_tbl = p.o_E + ((4 * (isz + 64) + 255) & ~255u);                     // the table, uncompressed
     p.o_tmp = p.o_tbl + ((tbl + 255) & ~255u);                              // scratch of the table's order-0 coder
     p.total = p.o_tmp + ((compress_bound(tbl, 0) + 64 + 255) & ~255u);
     return p;
@@ -321,7 +327,7 @@ __device__ inline void cta_hist8(const uint8_t *in, uint32_t n, PrepSmem &S) {
 //   bucket: n (+ N) bytes of symbol ranks grouped by context rank;  S.rowlen[r] = first byte of bucket r (the
 //   start of bucket nsym closes the last one);  the lane starts (:325-327) are appended to the bucket of symbol 0.
 __device__ inline void cta_pair_buckets(const uint8_t *in, uint32_t n, int N, uint32_t nsym, uint8_t *bucket,
-                                        PrepSmem &S) {
+                                        uint32_t *bpos, PrepSmem &S) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t seg = n / N;
     // bucket sizes in rank space: occurrences of the symbol except as the last byte, the virtual 0 in front of the
@@ -342,11 +348,17 @@ __device__ inline void cta_pair_buckets(const uint8_t *in, uint32_t n, int N, ui
     cur[tid] = start;
     S.rowlen[tid] = start;
     __syncthreads();
-    auto deal = [&](uint32_t rp, uint32_t rc) { bucket[atomicAdd(&cur[rp], 1u)] = (uint8_t)rc; };
+    // bpos (large alphabets only): the position the pair belongs to -- p for the pair (in[p-1], in[p]), n + z for the
+    // start of lane z
+    auto deal = [&](uint32_t rp, uint32_t rc, uint32_t pos) {
+        const uint32_t k = atomicAdd(&cur[rp], 1u);
+        bucket[k] = (uint8_t)rc;
+        if (bpos) bpos[k] = pos;
+    };
     const uint8_t *rank = S.rank;
     uint32_t head = (uint32_t)((16 - ((uintptr_t)in & 15)) & 15);
     if (head > n) head = n;
-    if ((uint32_t)tid < head) deal(rank[tid ? in[tid - 1] : 0], rank[in[tid]]);
+    if ((uint32_t)tid < head) deal(rank[tid ? in[tid - 1] : 0], rank[in[tid]], (uint32_t)tid);
     const uint8_t *p = in + head;
     const uint32_t rest = n - head, nv = rest >> 4;
     const uint4 *v = (const uint4 *)p;
@@ -360,15 +372,15 @@ __device__ inline void cta_pair_buckets(const uint8_t *in, uint32_t n, int N, ui
 #pragma unroll
             for (int b = 0; b < 4; b++) {
                 const uint32_t rc = rank[(w4[a] >> (8 * b)) & 0xff];
-                deal(rp, rc);
+                deal(rp, rc, head + 16 * i + 4 * a + b);
                 rp = rc;
             }
     }
     for (uint32_t t = (nv << 4) + tid; t < rest; t += PREP_THREADS) {
         const uint32_t pos = head + t;
-        deal(rank[pos ? in[pos - 1] : 0], rank[in[pos]]);
+        deal(rank[pos ? in[pos - 1] : 0], rank[in[pos]], pos);
     }
-    if (tid >= 1 && tid < N) deal(rank[0], rank[in[(size_t)tid * seg]]);      // lanes 1..N-1 start in context 0
+    if (tid >= 1 && tid < N) deal(rank[0], rank[in[(size_t)tid * seg]], n + (uint32_t)tid);   // lanes 1..N-1 start in context 0
     __threadfence_block();
     __syncthreads();
 }
@@ -379,7 +391,12 @@ __device__ __forceinline__ void row_from_bucket(const uint8_t *bucket, uint32_t 
     uint4 *z = (uint4 *)bins;
     z[lane] = make_uint4(0, 0, 0, 0); z[lane + 32] = make_uint4(0, 0, 0, 0);
     __syncwarp();
-    for (uint32_t k = b0 + lane; k < b1; k += 32) atomicAdd(&bins[bucket[k]], 1u);
+    uint32_t k = b0 + lane;
+    for (; k + 96 < b1; k += 128) {                 // four byte loads in flight per lane
+        const uint32_t s0 = bucket[k], s1 = bucket[k + 32], s2 = bucket[k + 64], s3 = bucket[k + 96];
+        atomicAdd(&bins[s0], 1u); atomicAdd(&bins[s1], 1u); atomicAdd(&bins[s2], 1u); atomicAdd(&bins[s3], 1u);
+    }
+    for (; k < b1; k += 32) atomicAdd(&bins[bucket[k]], 1u);
     __syncwarp();
     const uint4 a = z[2 * lane], b = z[2 * lane + 1];
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
@@ -479,8 +496,9 @@ __device__ __forceinline__ uint32_t row_emit(const uint32_t (&f)[8], uint32_t ns
 
 // The whole order-1 model of `in`: counts in S.T on entry (symbol space, cta_hist8).  Leaves the uncompressed
 // table (first byte = shift << 4) at tbl, the encoder symbols at symtab, the rank map in P.  N = lanes of the coder.
-__device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint8_t *bucket, uint8_t *rowstage,
-                                    uint32_t *symtab, uint8_t *tbl, Prep &P, PrepSmem &S) {
+__device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint8_t *bucket, uint32_t *bpos,
+                                    uint8_t *rowstage, uint32_t *symtab, uint32_t *E, uint8_t *tbl, Prep &P,
+                                    PrepSmem &S) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // ---- alphabet = symbols present, plus 0 (:357-361)
     const bool pres = S.T[tid] != 0 || tid == 0;
@@ -495,7 +513,8 @@ __device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint8_
     P.rank[tid] = pres ? (uint8_t)r : 0xff;
     __syncthreads();
     // ---- pairs dealt into their contexts' buckets (the lane starts of :325-327 included)
-    cta_pair_buckets(in, n, N, nsym, bucket, S);
+    const bool stream_syms = nsym > PREP_SYM_MAX;       // encoder symbols per position instead of a table
+    cta_pair_buckets(in, n, N, nsym, bucket, stream_syms ? bpos : nullptr, S);
     S.bstart[tid] = S.rowlen[tid];
     if (tid == 0) S.bstart[256] = n + (uint32_t)N - 1;
     __syncthreads();
@@ -618,9 +637,22 @@ __device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint8_
             for (int t = 0; t < 8; t++) f[t] = bins[j0 + t];
             __syncwarp();
         }
-        const uint32_t rb = row_emit(f, nsym, mv, shift, rowstage + (size_t)i * PREP_ROW_STRIDE, 0,
-                                     symtab + (size_t)i * nsym, lane);
+        // the row's encoder symbols go to the warp's bins (the counts are in registers by now) ...
+        const uint32_t rb = row_emit(f, nsym, mv, shift, rowstage + (size_t)i * PREP_ROW_STRIDE, 0, bins, lane);
         if (lane == 0) S.rowlen[i] = rb;
+        __syncwarp();
+        if (stream_syms) {      // ... and from there to every position that is coded in this context
+            const uint32_t b0 = S.bstart[i], b1 = S.bstart[i + 1];
+            uint32_t k = b0 + lane;
+            for (; k + 32 < b1; k += 64) {
+                const uint32_t s0 = bucket[k], s1 = bucket[k + 32], p0 = bpos[k], p1 = bpos[k + 32];
+                E[p0] = bins[s0]; E[p1] = bins[s1];
+            }
+            for (; k < b1; k += 32) E[bpos[k]] = bins[bucket[k]];
+        } else {                // ... or to the stream's symbol table
+            for (uint32_t j = lane; j < nsym; j += 32) symtab[(size_t)i * nsym + j] = bins[j];
+        }
+        __syncwarp();
     }
     err = __any_sync(FULL, err);
     if (err && lane == 0) P.err = 1;
@@ -661,7 +693,7 @@ __device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint8_
         warp_copy(tbl + S.bstart[i], rowstage + (size_t)i * PREP_ROW_STRIDE, S.rowlen[i], lane);
     __threadfence_block();
     __syncthreads();
-    if (tid == 0) { P.nsym = nsym; P.shift = shift; P.tl = S.bc[1]; }
+    if (tid == 0) { P.nsym = nsym; P.shift = shift; P.tl = S.bc[1]; P.stream_syms = stream_syms ? 1u : 0u; }
 }
 
 // ------------------------------------------------------------------ the coder warp's side
@@ -673,6 +705,67 @@ struct __align__(16) EncPrepSmem {
     uint8_t ring[ORING];
     uint8_t rank[256];
 };
+// The order-1 state chains over a stream of per-position encoder symbols: E[p] codes in[p] in the context of
+// in[p-1] (E[0]: context 0), E[n + z] codes the first symbol of lane z >= 1 in context 0 (rANS_static32x16pr.c:
+// 457-525).  Lane z owns [z*seg, (z+1)*seg), lane N-1 also the tail; everything runs backwards.
+template <int N>
+__device__ __forceinline__ void enc_o1_payload_stream(const uint32_t *E, uint32_t n, uint8_t *out, uint8_t *out_end,
+                                                      uint8_t **ptr_out, uint8_t *ring, uint32_t shift, int lane) {
+    const uint32_t seg = n / N;
+    const bool act = lane < N;
+    OutRing w;
+    w.init(out, out_end, ring);
+    uint32_t R = RANS_L;
+    {   // tail on lane N-1, from the end down to N*seg
+        const bool lastl = lane == N - 1;
+        for (uint32_t p = n - 1; p >= N * seg && p > 0; p--) {
+            uint4 e = make_uint4(0, 0, 0, 0);
+            if (lastl) e = enc_sym_unpack(E[p], shift);
+            w.maybe_flush(lane);
+            R = enc_step(R, lastl, e, w, lane);
+        }
+    }
+    const uint32_t *q = E + (size_t)(act ? lane : 0) * seg;
+    uint32_t k = seg;                                        // positions q[1 .. k) are still to be coded
+    __syncwarp();
+    if (N == 32 && seg >= 8 && (seg & 3) == 0) {
+        // whole 16-byte groups per lane, one group ahead of the chain
+        const uint4 *v = (const uint4 *)q;
+        uint32_t j = seg >> 2;
+        uint4 cur = v[j - 1];
+        while (j > 1) {
+            const uint4 nxt = v[j - 2];
+            w.maybe_flush(lane);
+            R = enc_step(R, true, enc_sym_unpack(cur.w, shift), w, lane);
+            R = enc_step(R, true, enc_sym_unpack(cur.z, shift), w, lane);
+            R = enc_step(R, true, enc_sym_unpack(cur.y, shift), w, lane);
+            R = enc_step(R, true, enc_sym_unpack(cur.x, shift), w, lane);
+            cur = nxt;
+            j--;
+        }
+        w.maybe_flush(lane);                                 // group 0: its first entry is the lane's first symbol
+        R = enc_step(R, true, enc_sym_unpack(cur.w, shift), w, lane);
+        R = enc_step(R, true, enc_sym_unpack(cur.z, shift), w, lane);
+        R = enc_step(R, true, enc_sym_unpack(cur.y, shift), w, lane);
+        k = 1;
+    }
+    for (; k > 1; k--) {
+        uint4 e = make_uint4(0, 0, 0, 0);
+        if (act) e = enc_sym_unpack(q[k - 1], shift);
+        w.maybe_flush(lane);
+        R = enc_step(R, act, e, w, lane);
+    }
+    if (seg) {                                               // every lane's first symbol: context 0
+        uint4 e = make_uint4(0, 0, 0, 0);
+        if (act) e = enc_sym_unpack(lane ? E[n + lane] : E[0], shift);
+        w.maybe_flush(lane);
+        R = enc_step(R, act, e, w, lane);
+    }
+    enc_flush(R, act, N, w, lane);
+    *ptr_out = w.slot + w.off;
+    __syncwarp();
+}
+
 template <int N>
 __device__ int enc_o1_prepped(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_end, uint32_t *tab_len,
                               uint8_t **ptr_out, uint8_t *smem, uint32_t smem_bytes, const Prep &P,
@@ -716,6 +809,11 @@ __device__ int enc_o1_prepped(const uint8_t *in, uint32_t n, uint8_t *out, uint8
     // the chains: rank map and, when they fit, the encoder symbols in shared memory (the order-0 scratch is dead)
     EncPrepSmem &S = *(EncPrepSmem *)smem;
     ((uint2 *)S.rank)[lane] = ((const uint2 *)P.rank)[lane];
+    if (P.stream_syms) {
+        __syncwarp();
+        enc_o1_payload_stream<N>((const uint32_t *)(prep_base + pl.o_E), n, out, out_end, ptr_out, S.ring, shift, lane);
+        return 0;
+    }
     const uint32_t hw = nsym * nsym;
     const bool sym_smem = sizeof(EncPrepSmem) + hw * 4 <= smem_bytes;
     const uint32_t *symtab = gsym;
@@ -775,8 +873,8 @@ __device__ inline void prep_stream(EncJob &J, PrepSmem &S) {
         if (o1 && !(N == 32 && in_size < 32)) {
             const PrepPlan pl = prep_plan(J.in_size);
             uint8_t *base = (uint8_t *)Pp;
-            cta_o1_model(in, in_size, N, base + pl.o_bkt, base + pl.o_rows, (uint32_t *)(base + pl.o_sym),
-                         base + pl.o_tbl, P, S);
+            cta_o1_model(in, in_size, N, base + pl.o_bkt, (uint32_t *)(base + pl.o_bpos), base + pl.o_rows,
+                         (uint32_t *)(base + pl.o_sym), (uint32_t *)(base + pl.o_E), base + pl.o_tbl, P, S);
             model = 2;
         }
     }
