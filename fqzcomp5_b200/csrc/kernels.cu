@@ -590,7 +590,11 @@ size_t prep_area_bytes(uint32_t in_size) { return prep_plan(in_size).total; }
 
 cudaError_t launch_prep(EncJob *d_jobs, uint32_t n, cudaStream_t st) {
     if (!n) return cudaSuccess;
-    prep_kernel<<<n, PREP_THREADS, 0, st>>>(d_jobs, n);
+    // tuning knob: unused dynamic shared memory per CTA, i.e. fewer streams in flight per SM (their tables share L2)
+    static const char *e = getenv("B200RANS_PREP_PAD_KB");
+    const size_t pad = e ? (size_t)atoi(e) << 10 : 0;
+    if (pad) cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+    prep_kernel<<<n, PREP_THREADS, pad, st>>>(d_jobs, n);
     return cudaGetLastError();
 }
 

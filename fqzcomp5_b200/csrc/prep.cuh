@@ -33,20 +33,21 @@ struct __align__(16) Prep {
 };
 // layout of the prep area behind the header
 constexpr uint32_t PREP_ROW_STRIDE = 768;      // a serialised row: at most 2 bytes per column plus a closing run token
-// Alphabets whose nsym x nsym encoder symbols fit the coder warp's shared memory keep a symbol table; larger ones
-// get the encoder symbol of every POSITION instead (a 4-byte stream the chains read sequentially: a 256 x 256 table
-// per stream, looked up at random, is a DRAM sector per symbol).
+// Alphabets whose nsym x nsym encoder symbols fit the coder warp's shared memory keep only the symbol table; for
+// larger ones the CTA also looks up the encoder symbol of every POSITION while its table is still hot in L2
+// (all 256 threads, 16 look-ups in flight each) and leaves them as a 4-byte stream the chains read sequentially:
+// looked up from the chains, much later, a 256 x 256 table per stream is a DRAM sector per symbol.
 constexpr uint32_t PREP_SYM_MAX = 40;
-struct PrepPlan { uint32_t o_bkt, o_bpos, o_rows, o_sym, o_E, o_tbl, o_tmp, total; };
+struct PrepPlan { uint32_t o_bkt, o_rows, o_sym, o_E, o_tbl, o_tmp, total; };
 __host__ __device__ inline PrepPlan prep_plan(uint32_t isz) {
     const uint32_t m = isz + 1 < 256 ? isz + 1 : 256;                      // alphabet of a short stream
+    const uint32_t hw = m * m * 4;
     const uint32_t tbl = (4 * (uint64_t)isz + 2048 < 257 * 257 * 3 + 4 ? 4 * isz + 2048 : 257 * 257 * 3 + 4) + 64;
     PrepPlan p;
     p.o_bkt = (uint32_t)((sizeof(Prep) + 255) & ~255u);                     // pairs dealt by context: isz + 32 bytes
-    p.o_bpos = p.o_bkt + ((isz + 64 + 255) & ~255u);                        // ... and where each came from (4 bytes)
-    p.o_rows = p.o_bpos + ((4 * (isz + 64) + 255) & ~255u);                 // serialised rows before they are packed
-    p.o_sym = p.o_rows + ((m * PREP_ROW_STRIDE + 255) & ~255u);             // encoder symbols, small alphabets
-    p.o_E = p.o_sym + ((PREP_SYM_MAX * PREP_SYM_MAX * 4 + 255) & ~255u);    // encoder symbol of every position
+    p.o_rows = p.o_bkt + ((isz + 64 + 255) & ~255u);                        // serialised rows before they are packed
+    p.o_sym = p.o_rows + ((m * PREP_ROW_STRIDE + 255) & ~255u);             // encoder symbols (rank(ctx), rank(sym))
+    p.o_E = p.o_sym + ((hw + 255) & ~255u);                                 // encoder symbol of every position
     p.o_tbl = p.o_E + ((4 * (isz + 64) + 255) & ~255u);                     // the table, uncompressed
     p.o_tmp = p.o_tbl + ((tbl + 255) & ~255u);                              // scratch of the table's order-0 coder
     p.total = p.o_tmp + ((compress_bound(tbl, 0) + 64 + 255) & ~255u);
@@ -327,7 +328,7 @@ __device__ inline void cta_hist8(const uint8_t *in, uint32_t n, PrepSmem &S) {
 //   bucket: n (+ N) bytes of symbol ranks grouped by context rank;  S.rowlen[r] = first byte of bucket r (the
 //   start of bucket nsym closes the last one);  the lane starts (:325-327) are appended to the bucket of symbol 0.
 __device__ inline void cta_pair_buckets(const uint8_t *in, uint32_t n, int N, uint32_t nsym, uint8_t *bucket,
-                                        uint32_t *bpos, PrepSmem &S) {
+                                        PrepSmem &S) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t seg = n / N;
     // bucket sizes in rank space: occurrences of the symbol except as the last byte, the virtual 0 in front of the
@@ -348,17 +349,11 @@ __device__ inline void cta_pair_buckets(const uint8_t *in, uint32_t n, int N, ui
     cur[tid] = start;
     S.rowlen[tid] = start;
     __syncthreads();
-    // bpos (large alphabets only): the position the pair belongs to -- p for the pair (in[p-1], in[p]), n + z for the
-    // start of lane z
-    auto deal = [&](uint32_t rp, uint32_t rc, uint32_t pos) {
-        const uint32_t k = atomicAdd(&cur[rp], 1u);
-        bucket[k] = (uint8_t)rc;
-        if (bpos) bpos[k] = pos;
-    };
+    auto deal = [&](uint32_t rp, uint32_t rc) { bucket[atomicAdd(&cur[rp], 1u)] = (uint8_t)rc; };
     const uint8_t *rank = S.rank;
     uint32_t head = (uint32_t)((16 - ((uintptr_t)in & 15)) & 15);
     if (head > n) head = n;
-    if ((uint32_t)tid < head) deal(rank[tid ? in[tid - 1] : 0], rank[in[tid]], (uint32_t)tid);
+    if ((uint32_t)tid < head) deal(rank[tid ? in[tid - 1] : 0], rank[in[tid]]);
     const uint8_t *p = in + head;
     const uint32_t rest = n - head, nv = rest >> 4;
     const uint4 *v = (const uint4 *)p;
@@ -372,15 +367,15 @@ __device__ inline void cta_pair_buckets(const uint8_t *in, uint32_t n, int N, ui
 #pragma unroll
             for (int b = 0; b < 4; b++) {
                 const uint32_t rc = rank[(w4[a] >> (8 * b)) & 0xff];
-                deal(rp, rc, head + 16 * i + 4 * a + b);
+                deal(rp, rc);
                 rp = rc;
             }
     }
     for (uint32_t t = (nv << 4) + tid; t < rest; t += PREP_THREADS) {
         const uint32_t pos = head + t;
-        deal(rank[pos ? in[pos - 1] : 0], rank[in[pos]], pos);
+        deal(rank[pos ? in[pos - 1] : 0], rank[in[pos]]);
     }
-    if (tid >= 1 && tid < N) deal(rank[0], rank[in[(size_t)tid * seg]], n + (uint32_t)tid);   // lanes 1..N-1 start in context 0
+    if (tid >= 1 && tid < N) deal(rank[0], rank[in[(size_t)tid * seg]]);      // lanes 1..N-1 start in context 0
     __threadfence_block();
     __syncthreads();
 }
@@ -496,9 +491,8 @@ __device__ __forceinline__ uint32_t row_emit(const uint32_t (&f)[8], uint32_t ns
 
 // The whole order-1 model of `in`: counts in S.T on entry (symbol space, cta_hist8).  Leaves the uncompressed
 // table (first byte = shift << 4) at tbl, the encoder symbols at symtab, the rank map in P.  N = lanes of the coder.
-__device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint8_t *bucket, uint32_t *bpos,
-                                    uint8_t *rowstage, uint32_t *symtab, uint32_t *E, uint8_t *tbl, Prep &P,
-                                    PrepSmem &S) {
+__device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint8_t *bucket, uint8_t *rowstage,
+                                    uint32_t *symtab, uint32_t *E, uint8_t *tbl, Prep &P, PrepSmem &S) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // ---- alphabet = symbols present, plus 0 (:357-361)
     const bool pres = S.T[tid] != 0 || tid == 0;
@@ -514,7 +508,7 @@ __device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint8_
     __syncthreads();
     // ---- pairs dealt into their contexts' buckets (the lane starts of :325-327 included)
     const bool stream_syms = nsym > PREP_SYM_MAX;       // encoder symbols per position instead of a table
-    cta_pair_buckets(in, n, N, nsym, bucket, stream_syms ? bpos : nullptr, S);
+    cta_pair_buckets(in, n, N, nsym, bucket, S);
     S.bstart[tid] = S.rowlen[tid];
     if (tid == 0) S.bstart[256] = n + (uint32_t)N - 1;
     __syncthreads();
@@ -637,22 +631,9 @@ __device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint8_
             for (int t = 0; t < 8; t++) f[t] = bins[j0 + t];
             __syncwarp();
         }
-        // the row's encoder symbols go to the warp's bins (the counts are in registers by now) ...
-        const uint32_t rb = row_emit(f, nsym, mv, shift, rowstage + (size_t)i * PREP_ROW_STRIDE, 0, bins, lane);
+        const uint32_t rb = row_emit(f, nsym, mv, shift, rowstage + (size_t)i * PREP_ROW_STRIDE, 0,
+                                     symtab + (size_t)i * nsym, lane);
         if (lane == 0) S.rowlen[i] = rb;
-        __syncwarp();
-        if (stream_syms) {      // ... and from there to every position that is coded in this context
-            const uint32_t b0 = S.bstart[i], b1 = S.bstart[i + 1];
-            uint32_t k = b0 + lane;
-            for (; k + 32 < b1; k += 64) {
-                const uint32_t s0 = bucket[k], s1 = bucket[k + 32], p0 = bpos[k], p1 = bpos[k + 32];
-                E[p0] = bins[s0]; E[p1] = bins[s1];
-            }
-            for (; k < b1; k += 32) E[bpos[k]] = bins[bucket[k]];
-        } else {                // ... or to the stream's symbol table
-            for (uint32_t j = lane; j < nsym; j += 32) symtab[(size_t)i * nsym + j] = bins[j];
-        }
-        __syncwarp();
     }
     err = __any_sync(FULL, err);
     if (err && lane == 0) P.err = 1;
@@ -693,6 +674,36 @@ __device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint8_
         warp_copy(tbl + S.bstart[i], rowstage + (size_t)i * PREP_ROW_STRIDE, S.rowlen[i], lane);
     __threadfence_block();
     __syncthreads();
+    if (stream_syms) {
+        // E[p] = symbol of in[p] in the context of in[p-1] (E[0]: context 0); E[n + z] = first symbol of lane z in
+        // context 0.  16 positions per thread and trip: one 16-byte load of the data, 16 look-ups, four 16-byte stores.
+        const uint8_t *rank = S.rank;
+        const uint32_t r0 = rank[0], seg = n / N;
+        uint32_t done = 0;
+        if ((((uintptr_t)in) & 15) == 0) {
+            const uint4 *v = (const uint4 *)in;
+            const uint32_t nv = n >> 4;
+            for (uint32_t i = tid; i < nv; i += PREP_THREADS) {
+                const uint4 q = v[i];
+                const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+                uint32_t rp = i ? rank[in[16 * i - 1]] : r0, e[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const uint32_t rc = rank[(w4[k >> 2] >> (8 * (k & 3))) & 0xff];
+                    e[k] = symtab[rp * nsym + rc];
+                    rp = rc;
+                }
+                uint4 *d = (uint4 *)(E + 16 * (size_t)i);
+                d[0] = make_uint4(e[0], e[1], e[2], e[3]); d[1] = make_uint4(e[4], e[5], e[6], e[7]);
+                d[2] = make_uint4(e[8], e[9], e[10], e[11]); d[3] = make_uint4(e[12], e[13], e[14], e[15]);
+            }
+            done = nv << 4;
+        }
+        for (uint32_t p2 = done + tid; p2 < n; p2 += PREP_THREADS)
+            E[p2] = symtab[(p2 ? rank[in[p2 - 1]] : r0) * nsym + rank[in[p2]]];
+        if (tid >= 1 && tid < N) E[n + tid] = symtab[r0 * nsym + rank[in[(size_t)tid * seg]]];
+        __syncthreads();
+    }
     if (tid == 0) { P.nsym = nsym; P.shift = shift; P.tl = S.bc[1]; P.stream_syms = stream_syms ? 1u : 0u; }
 }
 
@@ -873,8 +884,8 @@ __device__ inline void prep_stream(EncJob &J, PrepSmem &S) {
         if (o1 && !(N == 32 && in_size < 32)) {
             const PrepPlan pl = prep_plan(J.in_size);
             uint8_t *base = (uint8_t *)Pp;
-            cta_o1_model(in, in_size, N, base + pl.o_bkt, (uint32_t *)(base + pl.o_bpos), base + pl.o_rows,
-                         (uint32_t *)(base + pl.o_sym), (uint32_t *)(base + pl.o_E), base + pl.o_tbl, P, S);
+            cta_o1_model(in, in_size, N, base + pl.o_bkt, base + pl.o_rows, (uint32_t *)(base + pl.o_sym),
+                         (uint32_t *)(base + pl.o_E), base + pl.o_tbl, P, S);
             model = 2;
         }
     }
