@@ -387,6 +387,17 @@ def test_randomised_differential(gpu_codec, checker):
     assert "cases 400 mismatches 0" in out, out[-2000:]
 
 
+def test_precision_decision_at_its_boundary(gpu_codec, checker):
+    """rans_compute_shift (rANS_static4x16pr.c:357-420) is taken on the device in double precision; inputs whose
+    e10 / e12 sits within 1e-3 of the 1.01 threshold (found by bisection on the length, scripts/gpu_fuzz_shift.py)
+    must still give the reference's bytes."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "gpu_fuzz_shift.py"), "6", "7"],
+                         capture_output=True, text=True, timeout=900).stdout
+    assert "mismatches 0" in out and "boundary cases 0 " not in out, out[-2000:]
+
+
 # ---------------------------------------------------------------- method trial (SURVEY 8f-1)
 def _cpu_trial(checker, data, methods):
     """compress_with_methods restated on the CPU checker (fqzcomp5.c:1989-2106, rANS members):
