@@ -603,6 +603,8 @@ def run_blocks(args, env, seq, qual, ngpu):
                         "qual": ["(150<<8)+9" if m < 0 else m | (4 if x32 else 0) for m in M3_QUAL]},
             "wins": {"seq": [int(x) for x in list(r0.wins[1])[:len(M3_SEQ)]],
                      "qual": [int(x) for x in list(r0.wins[2])[:len(M3_QUAL)]]},
+            "encode_phase_ms_per_block": {k: float(np.mean([r.ms[i] for r in reps])) for i, k in enumerate(
+                ("copy_in_split", "plan_and_queue", "wait_trials", "frame_crc_copy_out"))},
         }
         variants[vname]["_last"] = (reps, live)
     # ---- parity on the timed data + CPU codec-only baseline: the same serial trial loop on the host

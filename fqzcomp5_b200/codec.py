@@ -589,7 +589,8 @@ class BlockReport(C.Structure):
     _fields_ = [("status", C.c_int32), ("num_records", C.c_uint32), ("consumed", C.c_uint32),
                 ("fixed_len", C.c_int32), ("ulen", C.c_uint32 * 3), ("clen", C.c_uint32 * 3),
                 ("nslices", C.c_uint32 * 3), ("csize", (C.c_uint64 * MAX_METHODS) * 3),
-                ("wins", (C.c_uint32 * MAX_METHODS) * 3), ("block_len", C.c_uint32), ("crc", C.c_uint32)]
+                ("wins", (C.c_uint32 * MAX_METHODS) * 3), ("block_len", C.c_uint32), ("crc", C.c_uint32),
+                ("ms", C.c_float * 4)]
 
 
 # fqzcomp5 -3 (fqzcomp5.c:4893-4900), the rANS members of its seq / qual method sets; names: the codec half

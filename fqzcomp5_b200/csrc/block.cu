@@ -10,6 +10,7 @@
 //   * tok3's method tables for C callers (tokenise_name3.c:1283-1357).
 // No codec arithmetic happens on the host.
 #include <limits.h>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <memory>
@@ -109,6 +110,9 @@ int run_on_workers(int ngpu, int slots, const std::function<int(int, int)> &fn) 
     return rc;
 }
 
+inline double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 inline void put32(uint8_t *p, uint32_t v) { memcpy(p, &v, 4); }
 inline uint32_t get32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
 inline int host_var_put(uint8_t *p, uint32_t v) {            // varint.h:205-237, most significant group first
@@ -148,6 +152,7 @@ int encode_block_impl(const unsigned char *text, uint32_t n, const b200fqz_block
         return B200RANS_EINVAL;
     Lane &Ln = C->dlane;
     cudaStream_t st = Ln.st;
+    const double t0 = now_ms();
 
     // ---- 1. one layout for everything the block needs, then text to the device and the split
     // (load_seqs, fqzcomp5.c:279-410).  Sections total at most n bytes; with a fixed read length a slice
@@ -197,6 +202,7 @@ int encode_block_impl(const unsigned char *text, uint32_t n, const b200fqz_block
     rep->num_records = info.num_records; rep->consumed = info.consumed; rep->fixed_len = info.fixed_len;
     const uint32_t R = info.num_records;
     uint8_t *D = C->blk.p;
+    const double t1 = now_ms();
 
     // ---- 2. plan the slices and their method lists
     Sec sec[3];
@@ -267,6 +273,7 @@ int encode_block_impl(const unsigned char *text, uint32_t n, const b200fqz_block
         if (R) CK(cudaMemcpyAsync(H + h_len, D + o_len, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
     }
     CK(cudaEventRecord(C->ev_blk, st));              // names, flags and lengths are on the host once this has passed
+    const double t2 = now_ms();
 
     // ---- 4. the method trial over every slice of every section: one batch
     if (ninputs) {
@@ -284,6 +291,7 @@ int encode_block_impl(const unsigned char *text, uint32_t n, const b200fqz_block
         CK(cudaMemcpyAsync(H + h_best, D + o_best, (size_t)ninputs * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(H + h_cs, D + o_cs, mm * 4, cudaMemcpyDeviceToHost, st));
     }
+    const double t2b = now_ms();                     // everything is queued; from here on the host only waits
     // ---- 5. the caller's name coder runs on this thread while the device works
     unsigned char *name_sec = nullptr;
     uint32_t name_sec_len = 0;
@@ -294,6 +302,7 @@ int encode_block_impl(const unsigned char *text, uint32_t n, const b200fqz_block
         if (e || !name_sec) { free(name_sec); cudaStreamSynchronize(st); return B200RANS_EINVAL; }
     }
     CK(cudaStreamSynchronize(st));
+    const double t3 = now_ms();
 
     // ---- 6. framing: [u32 size][u32 num_records][u32 crc] + sections (fqzcomp5.c:2147-2280)
     const uint32_t *hs = (const uint32_t *)(H + h_sz);
@@ -391,6 +400,9 @@ int encode_block_impl(const unsigned char *text, uint32_t n, const b200fqz_block
     free(name_sec);
     rep->block_len = (uint32_t)total;
     rep->crc = get32(H);
+    const double t4 = now_ms();
+    (void)t2;
+    rep->ms[0] = (float)(t1 - t0); rep->ms[1] = (float)(t2b - t1); rep->ms[2] = (float)(t3 - t2b); rep->ms[3] = (float)(t4 - t3);
     return 0;
 }
 

@@ -406,6 +406,9 @@ typedef struct {
     uint32_t wins[3][B200FQZ_MAX_METHODS];    /* per method: slices it won */
     uint32_t block_len;             /* encode: bytes of block produced; decode: bytes of text produced */
     uint32_t crc;
+    float    ms[4];                 /* encode, host wall time of the call's phases: copy in + split; planning and
+                                       queueing the trials; waiting for them (+ the name coder); framing + CRC +
+                                       copy out */
 } b200fqz_block_report;
 
 /* Host buffers (pinned for full PCIe rate).  text[0, n) holds FASTQ text; the block is written to
