@@ -983,6 +983,20 @@ __device__ __forceinline__ void enc_o1_payload(const uint8_t *in, uint32_t n, ui
         }
         kstart = lead ? lead : 1;
     }
+    if (kstart > 1 && kstart <= 16 && seg >= 16) {
+        // the few bytes left at the start of the segment: fetched with one load, not one dependent global
+        // byte load per step (short streams -- STRIPE sub-streams -- spend most of their steps here)
+        const uint4 h16 = ld16_any(q);
+        const uint32_t w4[4] = {h16.x, h16.y, h16.z, h16.w};
+        for (uint32_t k = kstart; k-- > 1;) {
+            const uint32_t rc = rank[(w4[(k - 1) >> 2] >> (8 * ((k - 1) & 3))) & 0xff];
+            uint4 e = enc_sym_unpack(symtab[rc * nsym + rs], shift);
+            w.maybe_flush(lane);
+            R = enc_step(R, act, e, w, lane);
+            rs = rc;
+        }
+        kstart = 1;
+    }
     for (uint32_t k = kstart; k-- > 1;) {
         uint32_t rc = rank[q[k - 1]];
         uint4 e = enc_sym_unpack(symtab[rc * nsym + rs], shift);
