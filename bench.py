@@ -100,6 +100,22 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def pcie_ceiling(world):
+    """Round-trip ceiling of the host-buffer path at `world` GPUs from the committed probe of this pool's boxes
+    (scripts/pcie_probe.py -> profiles/pcie_probe.jsonl): a step moves the block in (encode) and out again
+    (decode), so GB/s <= 1 / (1 / H2D_total + 1 / D2H_total).  None when no probe is committed."""
+    try:
+        rows = [json.loads(l) for l in open(os.path.join(ROOT, "profiles", "pcie_probe.jsonl")) if l.strip().startswith("{")]
+        r = [x for x in rows if x["gpus"] == world]
+        if not r:
+            return None
+        h, d = r[0]["h2d_gbs_total"], r[0]["d2h_gbs_total"]
+        return {"h2d_gbs_total": h, "d2h_gbs_total": d, "round_trip_ceiling_gbs": 1.0 / (1.0 / h + 1.0 / d),
+                "source": "profiles/pcie_probe.jsonl"}
+    except Exception:
+        return None
+
+
 def codec_config(workload, order, U, S, n, world, ratio):
     """`config` of a codec workload: the same dict in the b200 and the reference arm."""
     return {"workload": workload, "description": WORKLOADS[workload][3], "order": hex(order), "block_bytes": U,
@@ -479,6 +495,10 @@ def codec_entry(name, r, world, ms_enc, ms_dec, e2e_ms):
         "roofline": r["roofline"], "roofline_enc": r["roofline_enc"], "roofline_dec": r["roofline_dec"],
         "roofline_step": r["roofline_step"], "clocks": r["clocks"], "wall_s_timed_region": r["wall_s_timed_region"],
     }
+    pc = pcie_ceiling(world)
+    if pc:
+        out["e2e"]["pcie"] = pc
+        out["e2e"]["frac_of_pcie_ceiling"] = out["e2e"]["value"] / pc["round_trip_ceiling_gbs"]
     for k in ("cpu_baseline", "parity_checked_slices"):
         if k in r:
             out[k] = r[k]

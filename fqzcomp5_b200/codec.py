@@ -227,7 +227,7 @@ def compress_batch(buf, offsets, sizes, orders, out=None, ngpu=1, block_of=None,
     sizes = np.ascontiguousarray(sizes, np.uint32)
     orders = np.ascontiguousarray(orders, np.int32)
     if out is None:
-        cap = int(L.b200rans_compress_batch_dev_bound(n, _addr(sizes), _addr(orders))) + 256 * max(ngpu, 1)
+        cap = int(L.b200rans_compress_batch_dev_bound(n, _addr(sizes), _addr(orders))) + 1024 * max(ngpu, 1)
         out = np.empty(cap, np.uint8)
     out_off = np.zeros(n, np.uint64)
     out_size = np.zeros(n, np.uint32)
