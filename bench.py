@@ -627,6 +627,50 @@ def run_blocks(args, env, seq, qual, ngpu):
                 ("copy_in_split", "plan_and_queue", "wait_trials", "frame_crc_copy_out"))},
         }
         variants[vname]["_last"] = (reps, live)
+        # ---- the same blocks as fqzcomp5 -3 really codes them: its learner (metrics_method / metrics_update,
+        # fqzcomp5.c:1899-1958) tries every method on METRICS_TRIAL = 3 blocks, then uses the best one alone for
+        # the next METRICS_REVIEW = 100
+        tl, tdl, picked = [], [], None
+        for it in range(1 + max(1, min(args.steps, 2))):
+            L = bc.Learner()
+            t0 = time.perf_counter()
+            ntr = min(3, nb)
+            o_tr = [L.methods(opts) for _ in range(ntr)]
+            reps_a = bc.encode_blocks_multi(ngpu, tlist[:ntr], o_tr[0], olist[:ntr])
+            for o, r in zip(o_tr, reps_a):
+                L.update(o, r)
+            o_st = [L.methods(opts) for _ in range(nb - ntr)]
+            reps_b = bc.encode_blocks_multi(ngpu, tlist[ntr:], o_st[0], olist[:nb - ntr]) if nb > ntr else []
+            t1 = time.perf_counter()
+            assert all(r.status == 0 for r in list(reps_a) + list(reps_b)), "a block failed to encode"
+            m = nb - ntr
+            last = {}
+            for b in range(m):
+                last[slot(b)] = b
+            live = sorted(last.values())
+            t2 = time.perf_counter()
+            dr = bc.decode_blocks_multi(ngpu, [olist[b] for b in live], [reps_b[b].block_len for b in live],
+                                        [blist[b] for b in live]) if m else []
+            t3 = time.perf_counter()
+            assert all(r.status == 0 for r in dr), "a block failed to decode"
+            for j, b in enumerate(live):
+                assert dr[j].block_len == n and np.array_equal(blist[b][:n], tlist[ntr + b]), "block round trip mismatch"
+            if it:
+                tl.append(t1 - t0)
+                tdl.append((t3 - t2) * nb / max(len(live), 1))
+            if m:
+                picked = {"seq": int(o_st[0].seq_methods[0]), "qual": int(o_st[0].qual_methods[0]),
+                          "n_seq": int(o_st[0].n_seq_methods), "n_qual": int(o_st[0].n_qual_methods),
+                          "steady_block_out_bytes": int(reps_b[0].block_len),
+                          "steady_phase_ms_per_block": {k: float(np.mean([r.ms[i] for r in reps_b])) for i, k in
+                                                        enumerate(("copy_in_split", "plan_and_queue", "wait_trials",
+                                                                   "frame_crc_copy_out"))}}
+        tl_m, tdl_m = float(np.mean(tl)), float(np.mean(tdl))
+        variants[vname + "_learner"] = {
+            "value": nb * n / (tl_m + tdl_m) / 1e9, "unit": "GB/s of FASTQ text, round trip, host buffers",
+            "enc_gbs": nb * n / tl_m / 1e9, "dec_gbs": nb * n / tdl_m / 1e9, "enc_s": tl_m, "dec_s_scaled": tdl_m,
+            "blocks": nb, "trial_blocks": min(3, nb), "block_bytes": n, "picked": picked,
+            "note": "fqzcomp5's learner: METRICS_TRIAL = 3 blocks try every method, the rest use the best one alone"}
     # ---- parity on the timed data + CPU codec-only baseline: the same serial trial loop on the host
     cores = os.cpu_count() or 1
     res = {"metric": "fqzcomp5 -3 block pipeline GB/s of FASTQ text (split + method trials + framing + CRC; "
@@ -688,9 +732,10 @@ def run_blocks(args, env, seq, qual, ngpu):
     for v in variants.values():
         v.pop("_last", None)
     res["variants"] = variants
-    res["value"] = variants["x32"]["value"]
+    res["value"] = variants["x32_learner"]["value"]
+    res["value_is"] = "x32_learner"
     vx = variants["x32"]
-    res["e2e"] = {"value": vx["value"], "unit": "GB/s",
+    res["e2e"] = {"value": variants["x32_learner"]["value"], "unit": "GB/s", "all_methods_every_block": vx["value"],
                   "h2d_bytes_per_step": nb * n + int(vx["block_out_bytes"]) * vx["blocks_decoded_per_pass"],
                   "d2h_bytes_per_step": nb * int(vx["block_out_bytes"]) + n * vx["blocks_decoded_per_pass"],
                   "note": "the block calls take and return host buffers: this IS the end-to-end number"}

@@ -40,6 +40,7 @@ EXPORTS = [
     "b200fq_split_mode", "b200fq_split_dev_mode",
     "b200fqz_block_bound", "b200fqz_encode_block", "b200fqz_decode_block",
     "b200fqz_encode_blocks_multi", "b200fqz_decode_blocks_multi",
+    "b200fqz_learner_init", "b200fqz_learner_methods", "b200fqz_learner_update",
 ]
 
 _lib = None
@@ -116,6 +117,11 @@ def lib():
         L.b200fqz_decode_block.argtypes = [vp, u32, i32, vp, sz, vp]
         L.b200fqz_encode_blocks_multi.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
         L.b200fqz_decode_blocks_multi.argtypes = [i32, i32, vp, vp, i32, vp, vp, vp]
+        L.b200fqz_learner_init.argtypes = [vp]
+        L.b200fqz_learner_methods.argtypes = [vp, vp, vp]
+        L.b200fqz_learner_update.argtypes = [vp, vp, vp]
+        for f in (L.b200fqz_learner_init, L.b200fqz_learner_methods, L.b200fqz_learner_update):
+            f.restype = None
         L.b200rans_launch_count.restype = C.c_uint64
         L.b200rans_version.restype = C.c_char_p
         L.b200rans_set_profiling.argtypes = [i32]
@@ -591,6 +597,26 @@ class BlockReport(C.Structure):
                 ("nslices", C.c_uint32 * 3), ("csize", (C.c_uint64 * MAX_METHODS) * 3),
                 ("wins", (C.c_uint32 * MAX_METHODS) * 3), ("block_len", C.c_uint32), ("crc", C.c_uint32),
                 ("ms", C.c_float * 4)]
+
+
+class Learner(C.Structure):
+    """b200fqz_learner: metrics_method / metrics_update (fqzcomp5.c:1899-1958) per section."""
+    _fields_ = [("review", C.c_int32 * 3), ("trial", C.c_int32 * 3), ("used", C.c_int32 * 3),
+                ("usize", (C.c_uint64 * MAX_METHODS) * 3), ("csize", (C.c_uint64 * MAX_METHODS) * 3),
+                ("on_trial", C.c_int32 * 3)]
+
+    def __init__(self):
+        super().__init__()
+        lib().b200fqz_learner_init(C.addressof(self))
+
+    def methods(self, all_opts):
+        """The options this block is coded with (every method while a trial is on, else the best one)."""
+        out = BlockOpts()
+        lib().b200fqz_learner_methods(C.addressof(self), C.addressof(all_opts), C.addressof(out))
+        return out
+
+    def update(self, used_opts, rep):
+        lib().b200fqz_learner_update(C.addressof(self), C.addressof(used_opts), C.addressof(rep))
 
 
 # fqzcomp5 -3 (fqzcomp5.c:4893-4900), the rANS members of its seq / qual method sets; names: the codec half

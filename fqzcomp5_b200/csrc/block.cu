@@ -740,6 +740,73 @@ API int b200rans_uncompress_batch_multi(int ngpu, int n, const unsigned char *co
     });
 }
 
+// ============================================================ the method learner (host logic only)
+// metrics_method / metrics_update of fqzcomp5.c:1899-1958, per section
+API void b200fqz_learner_init(b200fqz_learner *L) {
+    if (!L) return;
+    memset(L, 0, sizeof(*L));                        // review <= 0: the first call starts a trial
+    for (int s = 0; s < 3; s++) L->trial[s] = -99999;
+}
+
+static const int *sec_list(const b200fqz_block_opts *o, int s, int *n) {
+    *n = s == 0 ? o->n_name_methods : s == 1 ? o->n_seq_methods : o->n_qual_methods;
+    return s == 0 ? o->name_methods : s == 1 ? o->seq_methods : o->qual_methods;
+}
+
+API void b200fqz_learner_methods(b200fqz_learner *L, const b200fqz_block_opts *all, b200fqz_block_opts *out) {
+    if (!L || !all || !out) return;
+    *out = *all;
+    for (int s = 0; s < 3; s++) {
+        int n;
+        const int *lst = sec_list(all, s, &n);
+        if (n <= 1) { L->on_trial[s] = 0; continue; }
+        if (L->review[s] <= 0) {                                     // :1902-1908
+            L->review[s] = 100;                                      // METRICS_REVIEW
+            L->trial[s] = 3;                                         // METRICS_TRIAL
+            memset(L->usize[s], 0, sizeof(L->usize[s]));
+            memset(L->csize[s], 0, sizeof(L->csize[s]));
+        }
+        L->on_trial[s] = 0;
+        if (L->trial[s] > 0) {                                       // under evaluation: all methods
+            L->on_trial[s] = 1;
+            continue;
+        }
+        if (L->trial[s] > -99999) {                                  // trial finished: pick the best (:1916-1931)
+            int best = 0;
+            double best_sz = 1e30;
+            for (int m = 0; m < n; m++)
+                if (L->usize[s][m] && best_sz > (L->csize[s][m] + 1.0) / L->usize[s][m]) {
+                    best_sz = (L->csize[s][m] + 1.0) / L->usize[s][m];
+                    best = m;
+                }
+            L->used[s] = best;
+            L->trial[s] = -99999;
+        } else L->review[s]--;                                       // :1938-1940
+        int *dst = s == 0 ? out->name_methods : s == 1 ? out->seq_methods : out->qual_methods;
+        dst[0] = lst[L->used[s]];
+        if (s == 0) out->n_name_methods = 1; else if (s == 1) out->n_seq_methods = 1; else out->n_qual_methods = 1;
+    }
+}
+
+API void b200fqz_learner_update(b200fqz_learner *L, const b200fqz_block_opts *out, const b200fqz_block_report *rep) {
+    if (!L || !out || !rep || rep->status) return;
+    for (int s = 0; s < 3; s++) {
+        if (!L->on_trial[s] || L->trial[s] <= 0) continue;           // :1951-1952
+        int n;
+        sec_list(out, s, &n);
+        // a RANSXN1 placeholder that was skipped (reads of different lengths) leaves a hole: the report's sizes
+        // are indexed by the RESOLVED list, the learner's by the caller's
+        const int *lst = sec_list(out, s, &n);
+        int k = 0;
+        for (int m = 0; m < n; m++) {
+            if (lst[m] == B200FQZ_RANSXN1 && rep->fixed_len <= 0) continue;
+            L->usize[s][m] += rep->ulen[s];
+            L->csize[s][m] += rep->csize[s][k++];
+        }
+        L->trial[s]--;                                               // compress_with_methods, :2131
+    }
+}
+
 // ============================================================ C ABI: part 5 (blocks)
 API size_t b200fqz_block_bound(uint32_t n) {
     // sections cannot grow beyond their bound; names may be coded by the caller (2x + 1000, fqzcomp5.c:1412)

@@ -411,6 +411,25 @@ typedef struct {
                                        copy out */
 } b200fqz_block_report;
 
+/* The learner that decides which methods a block is coded with (metrics_method / metrics_update,
+ * fqzcomp5.c:1899-1958; METRICS_TRIAL = 3 and METRICS_REVIEW = 100 at :151-152), kept per section
+ * (0 names, 1 seq, 2 qual) as the reference keeps stats[sec]: while a trial is on every method of the
+ * caller's list is tried and the sizes are accumulated; when it ends the method with the smallest
+ * (csize + 1) / usize is used alone for the next METRICS_REVIEW blocks, then the next trial starts.
+ * Plain host logic, no device involved:
+ *   b200fqz_learner_methods(L, all, out)  copies *all to *out with each section's list cut down to what
+ *                                         metrics_method returns for this block;
+ *   b200fqz_learner_update(L, out, rep)   feeds the sizes of the finished block back (sections that were
+ *                                         on trial for it); `out` is what that block was coded with. */
+typedef struct {
+    int32_t  review[3], trial[3], used[3];          /* used: index into the caller's full method list */
+    uint64_t usize[3][B200FQZ_MAX_METHODS], csize[3][B200FQZ_MAX_METHODS];
+    int32_t  on_trial[3];                           /* set by _methods: this block's sizes count */
+} b200fqz_learner;
+void b200fqz_learner_init(b200fqz_learner *L);
+void b200fqz_learner_methods(b200fqz_learner *L, const b200fqz_block_opts *all, b200fqz_block_opts *out);
+void b200fqz_learner_update(b200fqz_learner *L, const b200fqz_block_opts *out, const b200fqz_block_report *rep);
+
 /* Host buffers (pinned for full PCIe rate).  text[0, n) holds FASTQ text; the block is written to
  * block[0, block_cap); b200fqz_block_bound(n) bytes always suffice. */
 size_t b200fqz_block_bound(uint32_t n);

@@ -27,6 +27,9 @@ for k, v in d.get("per_config", {}).items():
 b = d.get("per_config", {}).get("fastq_blocks_m3") or (d if "variants" in d else None)
 if b:
     for vn, v in b["variants"].items():
+        if "picked" in v:
+            print("blocks %-20s value %.2f enc %.2f dec %.2f GB/s text | picked %s" % (vn, v["value"], v["enc_gbs"], v["dec_gbs"], v["picked"]))
+            continue
         print("blocks %-12s value %.2f enc %.2f dec %.2f GB/s text | blocks %d x %.2f GB -> ratio %.3f | wins %s | phases %s" % (
             vn, v["value"], v["enc_gbs"], v["dec_gbs"], v["blocks"], v["block_bytes"] / 1e9, v["ratio"], v["wins"],
             {k: round(x, 1) for k, x in v.get("encode_phase_ms_per_block", {}).items()}))

@@ -102,3 +102,65 @@ def test_tok3_tables_in_c():
     import pytest
     with pytest.raises(codec.B200RansError):
         codec.tok3_methods(3, 13, 4)
+
+
+def test_method_learner_follows_metrics_method():
+    """b200fqz_learner_* (host logic, no device) against a restatement of metrics_method / metrics_update
+    (fqzcomp5.c:1899-1958): METRICS_TRIAL = 3 blocks with every method, the best (csize + 1) / usize alone for
+    METRICS_REVIEW = 100 blocks, then the next trial; a skipped RANSXN1 leaves a hole in the report's sizes."""
+    import numpy as np
+    from fqzcomp5_b200 import codec
+    rng = np.random.default_rng(5)
+    allo = codec.block_opts(slice_bytes=262144, x32=True)
+    lists = [[5], [4, 5, 133, 197], [4, 5, 133, 197, codec.RANSXN1]]
+
+    class Ref:                                          # the reference's per-section state machine
+        def __init__(self, n):
+            self.n, self.review, self.trial, self.used = n, 0, -99999, 0
+            self.us, self.cs = [0] * n, [0] * n
+
+        def methods(self):
+            if self.n <= 1:
+                return list(range(self.n)), False
+            if self.review <= 0:
+                self.review, self.trial = 100, 3
+                self.us, self.cs = [0] * self.n, [0] * self.n
+            if self.trial > 0:
+                return list(range(self.n)), True
+            if self.trial > -99999:
+                best, bsz = 0, 1e30
+                for m in range(self.n):
+                    if self.us[m] and bsz > (self.cs[m] + 1.0) / self.us[m]:
+                        bsz, best = (self.cs[m] + 1.0) / self.us[m], m
+                self.used, self.trial = best, -99999
+            else:
+                self.review -= 1
+            return [self.used], False
+
+    L = codec.Learner()
+    refs = [Ref(len(l)) for l in lists]
+    for blk in range(230):
+        o = L.methods(allo)
+        fixed = 150 if blk % 7 else 0                   # every seventh block has reads of different lengths
+        rep = codec.BlockReport()
+        rep.status, rep.fixed_len = 0, fixed
+        got = [[o.name_methods[i] for i in range(o.n_name_methods)], [o.seq_methods[i] for i in range(o.n_seq_methods)],
+               [o.qual_methods[i] for i in range(o.n_qual_methods)]]
+        for s in range(3):
+            idx, trial = refs[s].methods()
+            want = [lists[s][i] | (0 if lists[s][i] < 0 else 0) for i in idx]
+            assert got[s] == want, (blk, s, got[s], want)
+            rep.ulen[s] = 1000 + s
+            k = 0
+            for i in idx:
+                if lists[s][i] == codec.RANSXN1 and fixed <= 0:
+                    continue                            # skipped by the block call: no size in the report
+                c = int(rng.integers(100, 900))
+                rep.csize[s][k] = c
+                k += 1
+                if trial:
+                    refs[s].us[i] += 1000 + s
+                    refs[s].cs[i] += c
+            if trial:
+                refs[s].trial -= 1
+        L.update(o, rep)
