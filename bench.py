@@ -100,18 +100,29 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def pcie_ceiling(world):
+def pcie_ceiling(world, ratio):
     """Round-trip ceiling of the host-buffer path at `world` GPUs from the committed probe of this pool's boxes
-    (scripts/pcie_probe.py -> profiles/pcie_probe.jsonl): a step moves the block in (encode) and out again
-    (decode), so GB/s <= 1 / (1 / H2D_total + 1 / D2H_total).  None when no probe is committed."""
+    (scripts/pcie_probe.py -> profiles/pcie_probe.jsonl: all GPUs copying at once).  Encode moves U in and C out
+    at the same time, decode C in and U out; each direction is limited by the aggregate rate the probe reached in
+    that direction, so per unit of U
+        t >= max(1 / H2D, ratio / D2H)     (encode; decode with H2D and D2H swapped)
+    and the round trip by the sum of the two.  (With both directions busy the probe reaches less per direction;
+    that figure is carried along, it is not a bound for unequal traffic.)  None when no probe is committed for
+    this GPU count."""
     try:
         rows = [json.loads(l) for l in open(os.path.join(ROOT, "profiles", "pcie_probe.jsonl")) if l.strip().startswith("{")]
         r = [x for x in rows if x["gpus"] == world]
         if not r:
             return None
-        h, d = r[0]["h2d_gbs_total"], r[0]["d2h_gbs_total"]
-        return {"h2d_gbs_total": h, "d2h_gbs_total": d, "round_trip_ceiling_gbs": 1.0 / (1.0 / h + 1.0 / d),
-                "source": "profiles/pcie_probe.jsonl"}
+        h, d, b = r[0]["h2d_gbs_total"], r[0]["d2h_gbs_total"], r[0]["both_gbs_each_direction_total"]
+        t_enc = max(1.0 / h, ratio / d)
+        t_dec = max(ratio / h, 1.0 / d)
+        lim = lambda t, a, c: "H2D" if t == a else "D2H"
+        return {"h2d_gbs_total": h, "d2h_gbs_total": d, "both_gbs_each_direction_total": b,
+                "enc_ceiling_gbs": 1.0 / t_enc, "dec_ceiling_gbs": 1.0 / t_dec,
+                "round_trip_ceiling_gbs": 1.0 / (t_enc + t_dec),
+                "limit": {"enc": lim(t_enc, 1.0 / h, ratio / d), "dec": lim(t_dec, ratio / h, 1.0 / d)},
+                "source": "profiles/pcie_probe.jsonl (scripts/pcie_probe.py on this pool's 8-GPU box)"}
     except Exception:
         return None
 
@@ -495,7 +506,7 @@ def codec_entry(name, r, world, ms_enc, ms_dec, e2e_ms):
         "roofline": r["roofline"], "roofline_enc": r["roofline_enc"], "roofline_dec": r["roofline_dec"],
         "roofline_step": r["roofline_step"], "clocks": r["clocks"], "wall_s_timed_region": r["wall_s_timed_region"],
     }
-    pc = pcie_ceiling(world)
+    pc = pcie_ceiling(world, Cc / U)
     if pc:
         out["e2e"]["pcie"] = pc
         out["e2e"]["frac_of_pcie_ceiling"] = out["e2e"]["value"] / pc["round_trip_ceiling_gbs"]
