@@ -642,33 +642,37 @@ def run_blocks(args, env, seq, qual, ngpu):
         # fqzcomp5.c:1899-1958) tries every method on METRICS_TRIAL = 3 blocks, then uses the best one alone for
         # the next METRICS_REVIEW = 100
         tl, tdl, picked = [], [], None
+        nbl = args.blocks_total                      # the named config: 64 blocks, whatever the number of GPUs
+        tlist_l = [texts[b % ndist].array for b in range(nbl)]
+        olist_l = [outs[slot(b)].array for b in range(nbl)]
+        blist_l = [backs[slot(b)].array for b in range(nbl)]
         for it in range(1 + max(1, min(args.steps, 2))):
             L = bc.Learner()
             t0 = time.perf_counter()
-            ntr = min(3, nb)
+            ntr = min(3, nbl)
             o_tr = [L.methods(opts) for _ in range(ntr)]
-            reps_a = bc.encode_blocks_multi(ngpu, tlist[:ntr], o_tr[0], olist[:ntr])
+            reps_a = bc.encode_blocks_multi(ngpu, tlist_l[:ntr], o_tr[0], olist_l[:ntr])
             for o, r in zip(o_tr, reps_a):
                 L.update(o, r)
-            o_st = [L.methods(opts) for _ in range(nb - ntr)]
-            reps_b = bc.encode_blocks_multi(ngpu, tlist[ntr:], o_st[0], olist[:nb - ntr]) if nb > ntr else []
+            o_st = [L.methods(opts) for _ in range(nbl - ntr)]
+            reps_b = bc.encode_blocks_multi(ngpu, tlist_l[ntr:], o_st[0], olist_l[:nbl - ntr]) if nbl > ntr else []
             t1 = time.perf_counter()
             assert all(r.status == 0 for r in list(reps_a) + list(reps_b)), "a block failed to encode"
-            m = nb - ntr
+            m = nbl - ntr
             last = {}
             for b in range(m):
                 last[slot(b)] = b
             live = sorted(last.values())
             t2 = time.perf_counter()
-            dr = bc.decode_blocks_multi(ngpu, [olist[b] for b in live], [reps_b[b].block_len for b in live],
-                                        [blist[b] for b in live]) if m else []
+            dr = bc.decode_blocks_multi(ngpu, [olist_l[b] for b in live], [reps_b[b].block_len for b in live],
+                                        [blist_l[b] for b in live]) if m else []
             t3 = time.perf_counter()
             assert all(r.status == 0 for r in dr), "a block failed to decode"
             for j, b in enumerate(live):
-                assert dr[j].block_len == n and np.array_equal(blist[b][:n], tlist[ntr + b]), "block round trip mismatch"
+                assert dr[j].block_len == n and np.array_equal(blist_l[b][:n], tlist_l[ntr + b]), "block round trip mismatch"
             if it:
                 tl.append(t1 - t0)
-                tdl.append((t3 - t2) * nb / max(len(live), 1))
+                tdl.append((t3 - t2) * nbl / max(len(live), 1))
             if m:
                 picked = {"seq": int(o_st[0].seq_methods[0]), "qual": int(o_st[0].qual_methods[0]),
                           "n_seq": int(o_st[0].n_seq_methods), "n_qual": int(o_st[0].n_qual_methods),
@@ -678,15 +682,16 @@ def run_blocks(args, env, seq, qual, ngpu):
                                                                    "frame_crc_copy_out"))}}
         tl_m, tdl_m = float(np.mean(tl)), float(np.mean(tdl))
         variants[vname + "_learner"] = {
-            "value": nb * n / (tl_m + tdl_m) / 1e9, "unit": "GB/s of FASTQ text, round trip, host buffers",
-            "enc_gbs": nb * n / tl_m / 1e9, "dec_gbs": nb * n / tdl_m / 1e9, "enc_s": tl_m, "dec_s_scaled": tdl_m,
-            "blocks": nb, "trial_blocks": min(3, nb), "block_bytes": n, "picked": picked,
+            "value": nbl * n / (tl_m + tdl_m) / 1e9, "unit": "GB/s of FASTQ text, round trip, host buffers",
+            "enc_gbs": nbl * n / tl_m / 1e9, "dec_gbs": nbl * n / tdl_m / 1e9, "enc_s": tl_m, "dec_s_scaled": tdl_m,
+            "blocks": nbl, "trial_blocks": min(3, nbl), "block_bytes": n, "picked": picked, "scaling": "strong",
             "note": "fqzcomp5's learner: METRICS_TRIAL = 3 blocks try every method, the rest use the best one alone"}
     # ---- parity on the timed data + CPU codec-only baseline: the same serial trial loop on the host
     cores = os.cpu_count() or 1
     res = {"metric": "fqzcomp5 -3 block pipeline GB/s of FASTQ text (split + method trials + framing + CRC; "
                      "CRC check + decode + join), configs[4]",
-           "config": {"workload": BLOCKS, "blocks": nb, "blocks_per_gpu": args.blocks_per_gpu, "n_gpus": ngpu,
+           "config": {"workload": BLOCKS, "blocks": args.blocks_total, "blocks_all_on_trial_variants": nb,
+                      "blocks_per_gpu_all_on_trial_variants": args.blocks_per_gpu, "n_gpus": ngpu,
                       "block_bytes": n, "distinct_blocks": ndist, "records_per_block": BLOCK_RECORDS,
                       "slice_bytes": S, "dispatch": "one process, %d persistent workers per device, block b on "
                       "device b %% ngpu, results in dispatch order" % W,
@@ -745,18 +750,20 @@ def run_blocks(args, env, seq, qual, ngpu):
     res["variants"] = variants
     res["value"] = variants["x32_learner"]["value"]
     res["value_is"] = "x32_learner"
-    vx = variants["x32"]
-    res["e2e"] = {"value": variants["x32_learner"]["value"], "unit": "GB/s", "all_methods_every_block": vx["value"],
-                  "h2d_bytes_per_step": nb * n + int(vx["block_out_bytes"]) * vx["blocks_decoded_per_pass"],
-                  "d2h_bytes_per_step": nb * int(vx["block_out_bytes"]) + n * vx["blocks_decoded_per_pass"],
-                  "note": "the block calls take and return host buffers: this IS the end-to-end number"}
+    vx, vl = variants["x32"], variants["x32_learner"]
+    ob = int((vl["picked"] or {}).get("steady_block_out_bytes", vx["block_out_bytes"]))
+    res["e2e"] = {"value": vl["value"], "unit": "GB/s", "all_methods_every_block": vx["value"],
+                  "h2d_bytes_per_step": vl["blocks"] * n, "d2h_bytes_per_step": vl["blocks"] * ob,
+                  "note": "the block calls take and return host buffers: this IS the end-to-end number (bytes: "
+                          "the encode pass over all blocks; the decode pass moves the same the other way)"}
     peak, peak_src = load_peaks()
-    a = nb * (n + variants["x32"]["block_out_bytes"]) / variants["x32"]["enc_s"] / 1e9 / max(ngpu, 1)
+    a = vl["blocks"] * (n + ob) / vl["enc_s"] / 1e9 / max(ngpu, 1)
     res["roofline"] = {"kernel": "whole encode chain per GPU (host buffers in and out)", "bound": "hbm",
                        "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "traffic": None,
                        "peak_source": peak_src,
-                       "note": "text in + block out per second and GPU; the chain is bound by PCIe and by its "
-                               "slowest trial candidates (PACK/RLE order-1 streams), see per_config.illumina_seq_c5"}
+                       "note": "text in + block out per second and GPU; steady-state blocks are bound by the PCIe "
+                               "copy of the text (see encode_phase_ms), trial blocks by the STRIPE candidate's "
+                               "300 sub-streams per slice"}
     for t in texts + outs + backs:
         t.free()
     return res
@@ -976,7 +983,10 @@ def main():
     ap.add_argument("--workload", default="all", choices=["all", BLOCKS] + sorted(WORKLOADS) + sorted(EXTRA))
     ap.add_argument("--bytes", type=int, default=0, help="block size per GPU (default: the config's 1 GB)")
     ap.add_argument("--slice", type=int, default=256 << 10, help="bytes per rans_compress_to_4x16 call")
-    ap.add_argument("--blocks-per-gpu", type=int, default=8, help="fastq_blocks_m3: blocks per GPU (8 x 8 GPUs = 64)")
+    ap.add_argument("--blocks-per-gpu", type=int, default=8,
+                    help="fastq_blocks_m3, every block on trial: blocks per GPU (8 x 8 GPUs = 64)")
+    ap.add_argument("--blocks-total", type=int, default=64,
+                    help="fastq_blocks_m3 with fqzcomp5's learner: blocks in all, at any number of GPUs (configs[4]: 64)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     args = ap.parse_args()
     if args.workload in EXTRA:
