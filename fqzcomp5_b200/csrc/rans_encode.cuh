@@ -421,12 +421,13 @@ __device__ __noinline__ int enc_o0(const uint8_t *in, uint32_t n, uint8_t *out, 
         R = enc_step(R, act, e2, w, lane);
         R = enc_step(R, act, e3, w, lane);
     };
-    if (N == 32 && i >= 4 * 512) {
-        // 32 lanes: the symbols of 16 steps are 512 consecutive bytes.  The warp brings them in
-        // with one coalesced 16-byte load per lane, a whole chunk ahead of their use, and parks them
-        // in shared memory (the histogram is dead by now: S.F holds two chunks); a step then takes
-        // its byte from there.  One global load per 16 steps instead of one per step, and no
-        // state-chain instruction ever waits on global memory.
+    if (i >= 4 * 512) {
+        // The symbols of 512 / N steps are 512 consecutive bytes.  The warp brings them in with one coalesced
+        // 16-byte load per lane, a whole chunk ahead of their use, and parks them in shared memory (the histogram
+        // is dead by now: S.F holds two chunks); a step then takes its byte from there.  One global load per
+        // 512 / N steps instead of one per step, and no state-chain instruction ever waits on global memory
+        // (with 4 lanes a chunk is 128 steps: the table and token streams the 4-lane coder gets are read from
+        // DRAM-cold buffers, and a byte load per step stalled every step on it).
         const uint32_t st_s = (uint32_t)__cvta_generic_to_shared(S.F);
         while (i & 511) {                                    // steps above the highest chunk boundary
             w.maybe_flush(lane);
@@ -445,13 +446,13 @@ __device__ __noinline__ int enc_o0(const uint8_t *in, uint32_t n, uint8_t *out, 
                          "r"(nxt.y), "r"(nxt.z), "r"(nxt.w) : "memory");
             __syncwarp();
             if (i >= 1024) nxt = load16(i - 1024);
-            const uint32_t b = st_s + buf * 512 + lane;
-#pragma unroll
-            for (int gi = 3; gi >= 0; gi--) {
+            const uint32_t b = st_s + buf * 512 + (act ? lane : 0);
+#pragma unroll 4
+            for (int gi = 512 / (4 * N) - 1; gi >= 0; gi--) {        // groups of four steps, from the chunk's end
                 uint32_t s4[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++)
-                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(s4[u]) : "r"(b + 32 * (4 * gi + 3 - u)));
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(s4[u]) : "r"(b + N * (4 * gi + 3 - u)));
                 group(s4);
             }
             i -= 512;
