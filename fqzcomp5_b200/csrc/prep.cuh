@@ -47,8 +47,8 @@ __host__ __device__ inline PrepPlan prep_plan(uint32_t isz) {
     p.o_bkt = (uint32_t)((sizeof(Prep) + 255) & ~255u);                     // pairs dealt by context: isz + 32 bytes
     p.o_rows = p.o_bkt + ((isz + 64 + 255) & ~255u);                        // serialised rows before they are packed
     p.o_sym = p.o_rows + ((m * PREP_ROW_STRIDE + 255) & ~255u);             // encoder symbols (rank(ctx), rank(sym))
-    p.o_E = p.o_sym + ((hw + 255) & ~255u);                                 // encoder symbol of every position
-    p.o_tbl = p.o_E + ((4 * (isz + 64) + 255) & ~255u);                     // the table, uncompressed
+    p.o_E = p.o_sym + ((hw + 255) & ~255u);                                 // encoder symbol of every position (8 bytes)
+    p.o_tbl = p.o_E + ((8 * (isz + 64) + 255) & ~255u);                     // the table, uncompressed
     p.o_tmp = p.o_tbl + ((tbl + 255) & ~255u);                              // scratch of the table's order-0 coder
     p.total = p.o_tmp + ((compress_bound(tbl, 0) + 64 + 255) & ~255u);
     return p;
@@ -492,7 +492,7 @@ __device__ __forceinline__ uint32_t row_emit(const uint32_t (&f)[8], uint32_t ns
 // The whole order-1 model of `in`: counts in S.T on entry (symbol space, cta_hist8).  Leaves the uncompressed
 // table (first byte = shift << 4) at tbl, the encoder symbols at symtab, the rank map in P.  N = lanes of the coder.
 __device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint8_t *bucket, uint8_t *rowstage,
-                                    uint32_t *symtab, uint32_t *E, uint8_t *tbl, Prep &P, PrepSmem &S) {
+                                    uint32_t *symtab, uint2 *E, uint8_t *tbl, Prep &P, PrepSmem &S) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // ---- alphabet = symbols present, plus 0 (:357-361)
     const bool pres = S.T[tid] != 0 || tid == 0;
@@ -676,7 +676,10 @@ __device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint8_
     __syncthreads();
     if (stream_syms) {
         // E[p] = symbol of in[p] in the context of in[p-1] (E[0]: context 0); E[n + z] = first symbol of lane z in
-        // context 0.  16 positions per thread and trip: one 16-byte load of the data, 16 look-ups, four 16-byte stores.
+        // context 0: the packed 4-byte symbol and, beside it, the reciprocal of its frequency, so that a chain step
+        // needs no table at all.  16 positions per thread and trip: one 16-byte load of the data, 16 look-ups
+        // (+ 16 in the 16 KiB reciprocal table, L1-resident here), eight 16-byte stores.
+        auto with_rcp = [](uint32_t c) { return make_uint2(c, rcp_of_freq((c >> 13) & 0x1fff)); };
         const uint8_t *rank = S.rank;
         const uint32_t r0 = rank[0], seg = n / N;
         uint32_t done = 0;
@@ -694,14 +697,17 @@ __device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint8_
                     rp = rc;
                 }
                 uint4 *d = (uint4 *)(E + 16 * (size_t)i);
-                d[0] = make_uint4(e[0], e[1], e[2], e[3]); d[1] = make_uint4(e[4], e[5], e[6], e[7]);
-                d[2] = make_uint4(e[8], e[9], e[10], e[11]); d[3] = make_uint4(e[12], e[13], e[14], e[15]);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint2 a = with_rcp(e[2 * k]), b2 = with_rcp(e[2 * k + 1]);
+                    d[k] = make_uint4(a.x, a.y, b2.x, b2.y);
+                }
             }
             done = nv << 4;
         }
         for (uint32_t p2 = done + tid; p2 < n; p2 += PREP_THREADS)
-            E[p2] = symtab[(p2 ? rank[in[p2 - 1]] : r0) * nsym + rank[in[p2]]];
-        if (tid >= 1 && tid < N) E[n + tid] = symtab[r0 * nsym + rank[in[(size_t)tid * seg]]];
+            E[p2] = with_rcp(symtab[(p2 ? rank[in[p2 - 1]] : r0) * nsym + rank[in[p2]]]);
+        if (tid >= 1 && tid < N) E[n + tid] = with_rcp(symtab[r0 * nsym + rank[in[(size_t)tid * seg]]]);
         __syncthreads();
     }
     if (tid == 0) { P.nsym = nsym; P.shift = shift; P.tl = S.bc[1]; P.stream_syms = stream_syms ? 1u : 0u; }
@@ -718,9 +724,19 @@ struct __align__(16) EncPrepSmem {
 };
 // The order-1 state chains over a stream of per-position encoder symbols: E[p] codes in[p] in the context of
 // in[p-1] (E[0]: context 0), E[n + z] codes the first symbol of lane z >= 1 in context 0 (rANS_static32x16pr.c:
-// 457-525).  Lane z owns [z*seg, (z+1)*seg), lane N-1 also the tail; everything runs backwards.
+// 457-525).  An entry is the packed 4-byte symbol (enc_sym_make4) and the reciprocal of its frequency.  Lane z owns
+// [z*seg, (z+1)*seg), lane N-1 also the tail; everything runs backwards.
+__device__ __forceinline__ uint4 enc_sym_unpack2(uint2 c, uint32_t bits) {
+    const uint32_t f = (c.x >> 13) & 0x1fff;
+    uint4 s;
+    s.x = (f << (31 - bits)) - 1;
+    s.y = c.y;
+    s.z = c.x & 0x1fff;
+    s.w = (((1u << bits) - f) & 0xffff) | ((c.x >> 26) << 16);
+    return s;
+}
 template <int N>
-__device__ __forceinline__ void enc_o1_payload_stream(const uint32_t *E, uint32_t n, uint8_t *out, uint8_t *out_end,
+__device__ __forceinline__ void enc_o1_payload_stream(const uint2 *E, uint32_t n, uint8_t *out, uint8_t *out_end,
                                                       uint8_t **ptr_out, uint8_t *ring, uint32_t shift, int lane) {
     const uint32_t seg = n / N;
     const bool act = lane < N;
@@ -731,44 +747,44 @@ __device__ __forceinline__ void enc_o1_payload_stream(const uint32_t *E, uint32_
         const bool lastl = lane == N - 1;
         for (uint32_t p = n - 1; p >= N * seg && p > 0; p--) {
             uint4 e = make_uint4(0, 0, 0, 0);
-            if (lastl) e = enc_sym_unpack(E[p], shift);
+            if (lastl) e = enc_sym_unpack2(E[p], shift);
             w.maybe_flush(lane);
             R = enc_step(R, lastl, e, w, lane);
         }
     }
-    const uint32_t *q = E + (size_t)(act ? lane : 0) * seg;
+    const uint2 *q = E + (size_t)(act ? lane : 0) * seg;
     uint32_t k = seg;                                        // positions q[1 .. k) are still to be coded
     __syncwarp();
     if (N == 32 && seg >= 8 && (seg & 3) == 0) {
-        // whole 16-byte groups per lane, one group ahead of the chain
+        // groups of four entries (two 16-byte loads per lane), one group ahead of the chain
         const uint4 *v = (const uint4 *)q;
         uint32_t j = seg >> 2;
-        uint4 cur = v[j - 1];
+        uint4 c0 = v[2 * j - 2], c1 = v[2 * j - 1];
         while (j > 1) {
-            const uint4 nxt = v[j - 2];
+            const uint4 n0 = v[2 * j - 4], n1 = v[2 * j - 3];
             w.maybe_flush(lane);
-            R = enc_step(R, true, enc_sym_unpack(cur.w, shift), w, lane);
-            R = enc_step(R, true, enc_sym_unpack(cur.z, shift), w, lane);
-            R = enc_step(R, true, enc_sym_unpack(cur.y, shift), w, lane);
-            R = enc_step(R, true, enc_sym_unpack(cur.x, shift), w, lane);
-            cur = nxt;
+            R = enc_step(R, true, enc_sym_unpack2(make_uint2(c1.z, c1.w), shift), w, lane);
+            R = enc_step(R, true, enc_sym_unpack2(make_uint2(c1.x, c1.y), shift), w, lane);
+            R = enc_step(R, true, enc_sym_unpack2(make_uint2(c0.z, c0.w), shift), w, lane);
+            R = enc_step(R, true, enc_sym_unpack2(make_uint2(c0.x, c0.y), shift), w, lane);
+            c0 = n0; c1 = n1;
             j--;
         }
         w.maybe_flush(lane);                                 // group 0: its first entry is the lane's first symbol
-        R = enc_step(R, true, enc_sym_unpack(cur.w, shift), w, lane);
-        R = enc_step(R, true, enc_sym_unpack(cur.z, shift), w, lane);
-        R = enc_step(R, true, enc_sym_unpack(cur.y, shift), w, lane);
+        R = enc_step(R, true, enc_sym_unpack2(make_uint2(c1.z, c1.w), shift), w, lane);
+        R = enc_step(R, true, enc_sym_unpack2(make_uint2(c1.x, c1.y), shift), w, lane);
+        R = enc_step(R, true, enc_sym_unpack2(make_uint2(c0.z, c0.w), shift), w, lane);
         k = 1;
     }
     for (; k > 1; k--) {
         uint4 e = make_uint4(0, 0, 0, 0);
-        if (act) e = enc_sym_unpack(q[k - 1], shift);
+        if (act) e = enc_sym_unpack2(q[k - 1], shift);
         w.maybe_flush(lane);
         R = enc_step(R, act, e, w, lane);
     }
     if (seg) {                                               // every lane's first symbol: context 0
         uint4 e = make_uint4(0, 0, 0, 0);
-        if (act) e = enc_sym_unpack(lane ? E[n + lane] : E[0], shift);
+        if (act) e = enc_sym_unpack2(lane ? E[n + lane] : E[0], shift);
         w.maybe_flush(lane);
         R = enc_step(R, act, e, w, lane);
     }
@@ -822,7 +838,7 @@ __device__ int enc_o1_prepped(const uint8_t *in, uint32_t n, uint8_t *out, uint8
     ((uint2 *)S.rank)[lane] = ((const uint2 *)P.rank)[lane];
     if (P.stream_syms) {
         __syncwarp();
-        enc_o1_payload_stream<N>((const uint32_t *)(prep_base + pl.o_E), n, out, out_end, ptr_out, S.ring, shift, lane);
+        enc_o1_payload_stream<N>((const uint2 *)(prep_base + pl.o_E), n, out, out_end, ptr_out, S.ring, shift, lane);
         return 0;
     }
     const uint32_t hw = nsym * nsym;
@@ -885,7 +901,7 @@ __device__ inline void prep_stream(EncJob &J, PrepSmem &S) {
             const PrepPlan pl = prep_plan(J.in_size);
             uint8_t *base = (uint8_t *)Pp;
             cta_o1_model(in, in_size, N, base + pl.o_bkt, base + pl.o_rows, (uint32_t *)(base + pl.o_sym),
-                         (uint32_t *)(base + pl.o_E), base + pl.o_tbl, P, S);
+                         (uint2 *)(base + pl.o_E), base + pl.o_tbl, P, S);
             model = 2;
         }
     }
