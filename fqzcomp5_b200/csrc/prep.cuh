@@ -760,7 +760,12 @@ __device__ __forceinline__ void enc_o1_payload_stream(const uint2 *E, uint32_t n
         const uint4 *v = (const uint4 *)q;
         uint32_t j = seg >> 2;
         uint4 c0 = v[2 * j - 2], c1 = v[2 * j - 1];
+        // every lane walks its own segment, 32 bytes per group: the next group is in registers, the lines further
+        // down are asked into L2 sixteen groups (four lines) ahead -- a DRAM round trip is several groups long
+        for (uint32_t a = 2; a <= 16 && a < j; a++)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(__cvta_generic_to_global(v + 2 * (j - a) - 2)));
         while (j > 1) {
+            if (j > 17) asm volatile("prefetch.global.L2 [%0];" ::"l"(__cvta_generic_to_global(v + 2 * (j - 17) - 2)));
             const uint4 n0 = v[2 * j - 4], n1 = v[2 * j - 3];
             w.maybe_flush(lane);
             R = enc_step(R, true, enc_sym_unpack2(make_uint2(c1.z, c1.w), shift), w, lane);
