@@ -586,27 +586,6 @@ prep_kernel(EncJob *jobs, uint32_t njobs) {
     prep_stream(jobs[j], S);
 }
 
-size_t prep_area_bytes(uint32_t in_size) { return prep_plan(in_size).total; }
-
-cudaError_t launch_prep(EncJob *d_jobs, uint32_t n, cudaStream_t st) {
-    if (!n) return cudaSuccess;
-    // tuning knob: unused dynamic shared memory per CTA, i.e. fewer streams in flight per SM (their tables share L2)
-    static const char *e = getenv("B200RANS_PREP_PAD_KB");
-    const size_t pad = e ? (size_t)atoi(e) << 10 : 0;
-    if (pad) cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
-    prep_kernel<<<n, PREP_THREADS, pad, st>>>(d_jobs, n);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_hist(EncJob *d_jobs, uint32_t n, cudaStream_t st) {
-    if (!n) return cudaSuccess;
-    hist_kernel<<<n, HIST_THREADS, 0, st>>>(d_jobs, n);
-    return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------ launchers
-static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
-
 // the shared reciprocal table of the order-1 encoder, filled once per device
 static cudaError_t ensure_rcp_table(cudaStream_t st) {
     static std::atomic<bool> done[64];
@@ -624,6 +603,29 @@ static cudaError_t ensure_rcp_table(cudaStream_t st) {
     }
     return cudaSuccess;
 }
+
+size_t prep_area_bytes(uint32_t in_size) { return prep_plan(in_size).total; }
+
+cudaError_t launch_prep(EncJob *d_jobs, uint32_t n, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    // the CTA stores reciprocals beside the per-position encoder symbols (cta_o1_model): the table must be there
+    { cudaError_t e = ensure_rcp_table(st); if (e != cudaSuccess) return e; }
+    // tuning knob: unused dynamic shared memory per CTA, i.e. fewer streams in flight per SM (their tables share L2)
+    static const char *e = getenv("B200RANS_PREP_PAD_KB");
+    const size_t pad = e ? (size_t)atoi(e) << 10 : 0;
+    if (pad) cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+    prep_kernel<<<n, PREP_THREADS, pad, st>>>(d_jobs, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hist(EncJob *d_jobs, uint32_t n, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    hist_kernel<<<n, HIST_THREADS, 0, st>>>(d_jobs, n);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------ launchers
+static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
 cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, uint32_t route, Pool pool, cudaStream_t st, bool inslot) {
     if (!n) return cudaSuccess;
