@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200rans.so")
-SOURCES = ["kernels.cu", "stripe.cu", "fastq.cu", "crc32.cu", "api.cu", "block.cu"]
+SOURCES = ["kernels.cu", "dec_staged.cu", "stripe.cu", "fastq.cu", "crc32.cu", "api.cu", "block.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",                      # keep double arithmetic as the reference's

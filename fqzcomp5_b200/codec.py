@@ -30,7 +30,7 @@ EXPORTS = [
     "b200rans_compress_batch_dev_bound", "b200rans_compress_batch_dev",
     "b200rans_uncompress_batch_dev", "b200rans_compress_batch_multi",
     "b200rans_uncompress_batch_multi", "b200rans_launch_count", "b200rans_version",
-    "b200rans_set_profiling", "b200rans_last_kernel_ms",
+    "b200rans_set_profiling", "b200rans_last_kernel_ms", "b200rans_dec_staged_stats",
     "b200rans_compress_methods_batch", "b200rans_compress_methods", "b200rans_compress_trials",
     "b200fq_split", "b200fq_join", "b200fq_split_dev", "b200fq_join_dev",
     "b200fq_split_scratch_bytes", "b200fq_join_scratch_bytes",
@@ -127,6 +127,7 @@ def lib():
         L.b200rans_set_profiling.argtypes = [i32]
         L.b200rans_last_kernel_ms.argtypes = [i32]
         L.b200rans_last_kernel_ms.restype = C.c_float
+        L.b200rans_dec_staged_stats.argtypes = [C.POINTER(C.c_ulonglong), i32]
         _lib = L
     return _lib
 
@@ -478,6 +479,13 @@ def launch_count():
 
 def set_profiling(on):
     _check(lib().b200rans_set_profiling(1 if on else 0), "b200rans_set_profiling")
+
+
+def dec_staged_stats(reset=False):
+    """Counters of the staged decode's head stage: [taken, failed after taken, handed back by reason ...]."""
+    out = (C.c_ulonglong * 16)()
+    _check(lib().b200rans_dec_staged_stats(out, 1 if reset else 0), "b200rans_dec_staged_stats")
+    return [int(x) for x in out]
 
 
 def last_kernel_ms(which):

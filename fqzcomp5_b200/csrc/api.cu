@@ -285,8 +285,9 @@ int dec_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
     size_t o_jobs = L.take((size_t)n * sizeof(DecJob));
     size_t o_ctr = L.take(256);
     std::vector<DecJob> jobs(n);
-    uint32_t n_o0 = 0, n_o1 = 0;
+    uint32_t n_o0 = 0, n_o1 = 0, n_st = 0;
     size_t pool_bytes = 0;
+    const bool staged = use_dec_staged();
     for (int k = 0; k < n; k++) {
         DecJob &J = jobs[k];
         memset(&J, 0, sizeof(J));
@@ -296,8 +297,17 @@ int dec_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
         // (order-1) kernel, which also decodes order-0 and raw streams
         const bool known = flags != nullptr;
         const int f = known ? flags[k] : (X_PACK | X_RLE | 1);
-        if (f & (X_PACK | X_RLE)) J.tmp = (uint8_t *)L.take((size_t)out_cap[k] * 2 + 4096, 256);
-        if (!known || ((f & 1) && !(f & X_CAT))) {
+        const bool o1 = !known || ((f & 1) && !(f & X_CAT));
+        // order-1 behind PACK / RLE with a known flag byte: staged decode (the head stage hands small alphabets back
+        // to the general kernel); its post stage keeps a bitmap of the run-length bytes behind the usual scratch
+        const bool st2 = staged && known && o1 && (f & (X_PACK | X_RLE)) && !(f & X_STRIPE);
+        if (f & (X_PACK | X_RLE))
+            J.tmp = (uint8_t *)L.take((size_t)out_cap[k] * 2 + 4096 + (st2 ? (size_t)out_cap[k] / 4 + 4096 : 0), 256);
+        if (st2) {
+            J.route = 2; n_st++;
+            J.prep = (uint8_t *)L.take(dec_prep_bytes(), 256);
+            pool_bytes += 257 * 257 * 3 + 257 * 256 * 4 + 256 * 2048 + 16 * 1024;
+        } else if (o1) {
             J.route = 1; n_o1++;
             pool_bytes += 257 * 257 * 3 + 257 * 256 * 4 + 256 * 2048 + 16 * 1024;   // table text + DecO1Big
         } else n_o0++;
@@ -308,7 +318,10 @@ int dec_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
     int r = Ln.work.ensure(L.off + 256);
     if (r) return r;
     uint8_t *W = Ln.work.p;
-    for (auto &J : jobs) if (J.tmp) J.tmp = W + (size_t)J.tmp;
+    for (auto &J : jobs) {
+        if (J.tmp) J.tmp = W + (size_t)J.tmp;
+        if (J.route == 2) J.prep = W + (size_t)J.prep;
+    }
     Stage *S;
     if ((r = Ln.get_stage((size_t)n * sizeof(DecJob), &S))) return r;
     memcpy(S->h.p, jobs.data(), (size_t)n * sizeof(DecJob));
@@ -317,18 +330,29 @@ int dec_core(Ctx &C, Lane &Ln, cudaStream_t st, int n, const uint8_t *d_in, cons
     CK(cudaMemsetAsync(W + o_ctr, 0, 256, st));
     Pool pool{W + o_pool, pool_bytes, (unsigned long long *)(W + o_ctr)};
     if (C.prof) CK(cudaEventRecord(C.pe[2], st));
-    if (n_o0 && n_o1) {           // independent streams: the two launches run side by side
+    // independent streams: the launches run side by side -- order-0 on a side stream from the start, the
+    // general order-1 kernel on another one behind the head stage (which may route streams to it), the
+    // staged launches on `st`
+    int njoin = 0;
+    if (n_o0 && (n_o1 || n_st)) {
         CK(cudaEventRecord(Ln.fork, st));
         CK(cudaStreamWaitEvent(Ln.aux[0], Ln.fork, 0));
-        CK(launch_dec(d_jobs, (uint32_t)n, true, pool, st));
         CK(launch_dec(d_jobs, (uint32_t)n, false, pool, Ln.aux[0]));
-        CK(cudaEventRecord(Ln.join[0], Ln.aux[0]));
-        CK(cudaStreamWaitEvent(st, Ln.join[0], 0));
-        C.launches += 2;
-    } else {
-        if (n_o0) { CK(launch_dec(d_jobs, (uint32_t)n, false, pool, st)); C.launches++; }
-        if (n_o1) { CK(launch_dec(d_jobs, (uint32_t)n, true, pool, st)); C.launches++; }
-    }
+        CK(cudaEventRecord(Ln.join[njoin], Ln.aux[0]));
+        njoin++;
+        C.launches++;
+    } else if (n_o0) { CK(launch_dec(d_jobs, (uint32_t)n, false, pool, st)); C.launches++; }
+    if (n_st) {
+        CK(launch_dec_head(d_jobs, (uint32_t)n, pool, st));
+        CK(cudaEventRecord(Ln.fork2, st));
+        CK(cudaStreamWaitEvent(Ln.aux[1], Ln.fork2, 0));
+        CK(launch_dec(d_jobs, (uint32_t)n, true, pool, Ln.aux[1]));
+        CK(cudaEventRecord(Ln.join[njoin], Ln.aux[1]));
+        njoin++;
+        CK(launch_dec_staged_rest(d_jobs, (uint32_t)n, st));
+        C.launches += 5;
+    } else if (n_o1) { CK(launch_dec(d_jobs, (uint32_t)n, true, pool, st)); C.launches++; }
+    for (int q = 0; q < njoin; q++) CK(cudaStreamWaitEvent(st, Ln.join[q], 0));
     if (C.prof) { CK(cudaEventRecord(C.pe[3], st)); C.pe_valid[1] = true; }
     CK(cudaEventRecord(S->ev, st)); S->busy = true;
     CK(launch_dec_results(d_jobs, (uint32_t)n, d_osz, d_status, st));
@@ -1121,5 +1145,14 @@ API float b200rans_last_kernel_ms(int which) {
     if (cudaEventSynchronize(C->pe[2 * which + 1]) != cudaSuccess) return -1.f;
     if (cudaEventElapsedTime(&ms, C->pe[2 * which], C->pe[2 * which + 1]) != cudaSuccess) return -1.f;
     return ms;
+}
+API int b200rans_dec_staged_stats(unsigned long long out16[16], int reset) {
+    int e = 0;
+    Ctx *C = get_ctx(&e);
+    if (!C) return e;
+    if (!out16) return B200RANS_EINVAL;
+    CK(cudaDeviceSynchronize());
+    CK(dec_staged_stats(out16, reset != 0));
+    return 0;
 }
 API const char *b200rans_version(void) { return "b200rans 0.1 (sm_100a)"; }

@@ -62,8 +62,9 @@ struct DecJob {
     uint32_t out_cap;       // capacity; exact length for NOSZ streams
     uint32_t out_size;      // result
     int32_t  status;        // result: 0 ok
-    uint32_t route;         // 0: order-0 kernel, 1: order-1 kernel
+    uint32_t route;         // 0: order-0 kernel, 1: order-1 (general) kernel, 2: staged decode (dec_staged.cuh)
     uint32_t pad_;
+    uint8_t *prep;          // route 2: the stream's DecPrep record
 };
 
 enum : int32_t {

@@ -28,6 +28,12 @@ cudaError_t launch_prep(EncJob *d_jobs, uint32_t n, cudaStream_t st);
 size_t prep_area_bytes(uint32_t in_size);
 cudaError_t launch_enc(EncJob *d_jobs, uint32_t n, uint32_t route, Pool pool, cudaStream_t st, bool inslot = false);
 cudaError_t launch_dec(DecJob *d_jobs, uint32_t n, bool o1, Pool pool, cudaStream_t st);
+// staged decode of order-1 streams behind PACK / RLE (dec_staged.cu): the head stage first -- it hands streams it
+// does not take back to route 1, so launch_dec(o1) for this batch must be ordered behind it -- then table, chain, post
+size_t dec_prep_bytes();
+cudaError_t dec_staged_stats(unsigned long long *out16, bool reset);   // diagnostics: see g_dec_stats
+cudaError_t launch_dec_head(DecJob *d_jobs, uint32_t n, Pool pool, cudaStream_t st);
+cudaError_t launch_dec_staged_rest(DecJob *d_jobs, uint32_t n, cudaStream_t st);
 // method trial: items first[k]..first[k+1]-1 are the candidates of input k -> sizes of all, first smallest kept
 cudaError_t launch_trial_select(EncJob *d_jobs, uint32_t njobs, uint32_t ninputs, const uint32_t *d_first,
                                 uint32_t *d_csize, uint32_t *d_jobidx, int32_t *d_best, cudaStream_t st);

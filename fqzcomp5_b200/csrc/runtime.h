@@ -83,6 +83,8 @@ inline uint32_t hist_min_bytes(bool o1) {
 // PACK / RLE streams: transforms, counts and order-1 model by one CTA per stream (prep_kernel) in front of the
 // coder warp; 0 = the coder warp does everything itself (kept for measurement)
 inline bool use_prep() { static int v = env_int("B200RANS_PREP", 1, 0, 1); return v != 0; }
+// order-1 streams behind PACK / RLE: staged decode (dec_staged.cu); 0 = the general kernel alone (kept for measurement)
+inline bool use_dec_staged() { static int v = env_int("B200RANS_DEC_STAGED", 1, 0, 1); return v != 0; }
 inline size_t chunk_bytes() { static size_t v = (size_t)env_int("B200RANS_CHUNK_MB", 48, 1, 1024) << 20; return v; }
 inline int chunk_min_streams() { static int v = env_int("B200RANS_CHUNK_STREAMS", 256, 1, 16384); return v; }
 
@@ -92,7 +94,7 @@ inline int chunk_min_streams() { static int v = env_int("B200RANS_CHUNK_STREAMS"
 struct Lane {
     cudaStream_t st = nullptr;
     cudaStream_t aux[3] = {nullptr, nullptr, nullptr};   // side streams: coder launches of different routes run side by side
-    cudaEvent_t fork = nullptr, join[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t fork = nullptr, fork2 = nullptr, join[3] = {nullptr, nullptr, nullptr};
     Arena work;                 // device: jobs, slots, scratch, pool
     Arena io;                   // device: staged inputs / outputs of the host-buffer API
     Arena crc;                  // device: CRC-32 tables and tile values (kept apart from `work`, which an
@@ -105,6 +107,7 @@ struct Lane {
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         for (auto &a : aux) CK(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&fork2, cudaEventDisableTiming));
         for (auto &j : join) CK(cudaEventCreateWithFlags(&j, cudaEventDisableTiming));
         hio.pinned = true;
         for (auto &s : stage) { s.h.pinned = true; CK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming)); }
@@ -126,6 +129,7 @@ struct Lane {
         for (auto &s : stage) { s.h.release(); if (s.ev) cudaEventDestroy(s.ev); }
         for (auto &a : aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); a = nullptr; }
         if (fork) cudaEventDestroy(fork);
+        if (fork2) cudaEventDestroy(fork2);
         for (auto &j : join) if (j) cudaEventDestroy(j);
         if (st) cudaStreamDestroy(st);
         st = nullptr;

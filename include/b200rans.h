@@ -458,6 +458,11 @@ uint64_t b200rans_launch_count(void);
  * or a negative value if none was recorded. */
 int   b200rans_set_profiling(int on);
 float b200rans_last_kernel_ms(int which);
+/* Diagnostics of the staged order-1 decode (streams behind PACK / RLE with a known flag byte): what became
+ * of the streams its head stage looked at on the current device since the last reset -- out16[0] taken,
+ * [1] taken and then failed, [2..9] handed back to the general kernel (header, pack meta-data, run-length
+ * header, no payload, order-1 header, table peek, alphabet, alphabet of <= 64 symbols).  Synchronises. */
+int   b200rans_dec_staged_stats(unsigned long long out16[16], int reset);
 const char *b200rans_version(void);
 
 #ifdef __cplusplus

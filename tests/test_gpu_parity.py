@@ -497,3 +497,61 @@ def test_tok3_stream_trials(gpu_codec, checker):
             assert cs[k] == wsizes, (level, k, lists[k], cs[k], wsizes)
             assert best[k] == wb
             assert out[int(ooff[k]):int(ooff[k]) + int(osz[k])].tobytes() == wout
+
+
+def test_staged_decode_large_alphabets(gpu_codec, checker):
+    """Order-1 streams behind PACK / RLE whose (packed) alphabet has more than 64 symbols take the staged decode
+    (head / table / chain / post launches, dec_staged.cu); smaller ones are handed back to the general kernel.
+    Reference-coded streams must decode to the input, 4 and 32 lanes, every transform combination."""
+    rng = np.random.default_rng(77)
+    def sticky(n, k, stay=0.75):                     # k symbols, each repeating its predecessor with p = stay: the
+        v = rng.integers(0, k, n).astype(np.uint8)    # packed bytes use all 256 values and stay compressible
+        keep = rng.random(n) < stay
+        keep[0] = False
+        idx = np.where(~keep, np.arange(n), 0)
+        np.maximum.accumulate(idx, out=idx)
+        return (v[idx] * 3 + 65).astype(np.uint8).tobytes()
+    def walk(n, k=200):                               # a random walk over 200 symbols in short runs: RLE alone, large alphabet
+        m = n // 3 + 2
+        q = np.cumsum(rng.integers(-2, 3, m)) % k
+        return np.repeat(q.astype(np.uint8), rng.integers(1, 7, m))[:n].tobytes().ljust(n, b"\1")
+    cases = []
+    for n in (1500, 4096, 30000, 70001, 262144, 300007):
+        cases += [(sticky(n, 4), o) for o in (0xc5, 0xc1, 0x85, 0x81, 0xd5)]
+        cases += [(sticky(n, 16), o) for o in (0xc5, 0x81)]
+        cases += [(sticky(n, 2), 0xc5), (sticky(n, 5), 0xc1), (sticky(n, 4, 0.97), 0xc5), (sticky(n, 16, 0.97), 0xc1)]
+        cases += [(walk(n), o) for o in (0x45, 0x41)]
+    cases += [(corpus.make("illumina_seq", 1 << 20, 3), 0xc5), (corpus.make("wide", 200000, 3), 0x45)]
+    bad = []
+    gpu_codec.dec_staged_stats(reset=True)
+    for data, order in cases:
+        want = checker.compress(data, order)
+        assert want is not None
+        if _gpu_decode(gpu_codec, want, len(data)) != data:
+            bad.append(("dec", len(data), hex(order), hex(want[0])))
+        if gpu_codec.rans_compress_to_4x16(data, order) != want:
+            bad.append(("enc", len(data), hex(order)))
+    assert not bad, bad[:10]
+    stats = gpu_codec.dec_staged_stats()
+    assert stats[0] >= len(cases) // 3 and stats[1] == 0, stats     # the staged route really took them
+    # a batch: many staged streams next to plain ones in one call
+    parts = [np.frombuffer(d, np.uint8) for d, _ in cases[:24]]
+    orders = [o for _, o in cases[:24]]
+    sizes = [p.size for p in parts]
+    offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64)
+    buf = np.concatenate(parts)
+    out, ooff, osz = gpu_codec.compress_batch(buf, offs, sizes, orders)
+    back = np.zeros(buf.size, np.uint8)
+    dsz, st = gpu_codec.uncompress_batch(out, ooff, osz, back, offs, sizes)
+    assert all(int(x) == 0 for x in st) and [int(x) for x in dsz] == sizes
+    assert np.array_equal(back, buf)
+    # damaged staged streams: a result or a clean failure, and the library stays healthy
+    data, order = cases[0]
+    c = checker.compress(sticky(50000, 4, 0.97), 0xc5)
+    for _ in range(40):
+        d = bytearray(c)
+        pos = int(rng.integers(1, len(d)))
+        d[pos] ^= 1 << int(rng.integers(0, 8))
+        r = gpu_codec.rans_uncompress_4x16(bytes(d[:int(rng.integers(pos, len(d) + 1))]))
+        assert r is None or isinstance(r, bytes)
+    assert gpu_codec.rans_uncompress_4x16(checker.compress(data, order)) == data
