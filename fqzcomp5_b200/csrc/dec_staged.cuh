@@ -15,6 +15,7 @@
 // (state chains), rle.c:142-189, pack.c:161-344.
 #pragma once
 #include <stddef.h>
+#include <type_traits>
 #include "common.cuh"
 #include "rans_decode.cuh"
 #include "transforms.cuh"
@@ -253,19 +254,23 @@ __device__ inline int cta_parse_o1_rows(const uint8_t *cp, const uint8_t *tend, 
         auto byte_at = [&](int k) { return (v[k >> 2] >> (8 * (k & 3))) & 0xffu; };
         // ---- walk 1: exit state and slots for each entry state
         uint32_t s0 = 0, s1 = 1, s2 = 2, c0 = 0, c1 = 0, c2 = 0;
+        const bool whole = (uint64_t)i0 + DT_SPAN + 8 <= avail;     // the span and its look-ahead lie inside the text
+        auto walk1 = [&](auto all) {
 #pragma unroll
-        for (int k = 0; k < (int)DT_SPAN; k++) {
-            const uint32_t b = byte_at(k);
-            if (i0 + k < avail) {
-                const uint32_t from0 = b == 0 ? 2u : (b < 128 ? 0u : 1u), from1 = b < 128 ? 0u : 1u;
-                c0 += s0 == 0 ? 1u : s0 == 2 ? b : 0u;
-                c1 += s1 == 0 ? 1u : s1 == 2 ? b : 0u;
-                c2 += s2 == 0 ? 1u : s2 == 2 ? b : 0u;
-                s0 = s0 == 0 ? from0 : s0 == 1 ? from1 : 0u;
-                s1 = s1 == 0 ? from0 : s1 == 1 ? from1 : 0u;
-                s2 = s2 == 0 ? from0 : s2 == 1 ? from1 : 0u;
+            for (int k = 0; k < (int)DT_SPAN; k++) {
+                const uint32_t b = byte_at(k);
+                if (decltype(all)::value || i0 + k < avail) {
+                    const uint32_t from0 = b == 0 ? 2u : (b < 128 ? 0u : 1u), from1 = b < 128 ? 0u : 1u;
+                    c0 += s0 == 0 ? 1u : s0 == 2 ? b : 0u;
+                    c1 += s1 == 0 ? 1u : s1 == 2 ? b : 0u;
+                    c2 += s2 == 0 ? 1u : s2 == 2 ? b : 0u;
+                    s0 = s0 == 0 ? from0 : s0 == 1 ? from1 : 0u;
+                    s1 = s1 == 0 ? from0 : s1 == 1 ? from1 : 0u;
+                    s2 = s2 == 0 ? from0 : s2 == 1 ? from1 : 0u;
+                }
             }
-        }
+        };
+        if (whole) walk1(std::true_type{}); else walk1(std::false_type{});
         uint32_t F = s0 | (s1 << 2) | (s2 << 4);
         // ---- inclusive scan over the warp: (earlier) then (this)
 #pragma unroll
@@ -298,38 +303,42 @@ __device__ inline int cta_parse_o1_rows(const uint8_t *cp, const uint8_t *tend, 
         // ---- walk 2: tokens that start in this span
         bool rc_valid = false;
         uint32_t row = 0, col = 0;
+        auto walk2 = [&](auto all) {
+            constexpr bool ALL = decltype(all)::value;
 #pragma unroll
-        for (int k = 0; k < (int)DT_SPAN; k++) {
-            const uint32_t i = i0 + k;
-            if (i >= avail) continue;
-            const uint32_t b = byte_at(k);
-            if (x == 1) { x = b < 128 ? 0u : 1u; continue; }
-            if (x == 2) { sl += b; x = 0; continue; }
-            uint32_t val = 0, slots = 1, len = 1;
-            bool terr = false;
-            if (b == 0) {
-                if (i + 1 >= avail) terr = true;
-                else { slots = 1 + byte_at(k + 1); len = 2; }
-                x = 2;
-            } else {
-                uint32_t c = b;
-                val = c & 0x7f;
+            for (int k = 0; k < (int)DT_SPAN; k++) {
+                const uint32_t i = i0 + k;
+                if (!ALL && i >= avail) continue;
+                const uint32_t b = byte_at(k);
+                if (x == 1) { x = b < 128 ? 0u : 1u; continue; }
+                if (x == 2) { sl += b; x = 0; continue; }
+                uint32_t val = 0, slots = 1, len = 1;
+                bool terr = false;
+                if (b == 0) {
+                    if (!ALL && i + 1 >= avail) terr = true;
+                    else { slots = 1 + byte_at(k + 1); len = 2; }
+                    x = 2;
+                } else {
+                    uint32_t c = b;
+                    val = c & 0x7f;
 #pragma unroll
-                for (int q = 1; q < 6; q++)
-                    if ((c & 0x80) && len == (uint32_t)q && i + q < avail) { c = byte_at(k + q); val = (val << 7) | (c & 0x7f); len = q + 1; }
-                terr = (c & 0x80) || val == 0 || val > tot;
-                x = b < 128 ? 0u : 1u;
+                    for (int q = 1; q < 6; q++)
+                        if ((c & 0x80) && len == (uint32_t)q && (ALL || i + q < avail)) { c = byte_at(k + q); val = (val << 7) | (c & 0x7f); len = q + 1; }
+                    terr = (c & 0x80) || val == 0 || val > tot;
+                    x = b < 128 ? 0u : 1u;
+                }
+                if (sl < total) {
+                    if (!rc_valid) { row = sl / nsym; col = sl - row * nsym; rc_valid = true; }
+                    if (terr || col + slots > nsym) err = 1;                // a zero run never crosses a row
+                    else if (val) raw[row * stride + col + 1] = (uint16_t)val;
+                    if (sl + slots >= total) my_end = i + len;              // the token that completes the last row
+                    col += slots;
+                    if (col >= nsym) { col -= nsym; row++; }
+                }
+                sl += 1;
             }
-            if (sl < total) {
-                if (!rc_valid) { row = sl / nsym; col = sl - row * nsym; rc_valid = true; }
-                if (terr || col + slots > nsym) err = 1;                // a zero run never crosses a row
-                else if (val) raw[row * stride + col + 1] = (uint16_t)val;
-                if (sl + slots >= total) my_end = i + len;              // the token that completes the last row
-                col += slots;
-                if (col >= nsym) { col -= nsym; row++; }
-            }
-            sl += 1;
-        }
+        };
+        if (whole) walk2(std::true_type{}); else walk2(std::false_type{});
         if (__syncthreads_or(err)) return 1;
     }
     if (my_end) S.end_off = my_end;                         // exactly one thread saw the closing token
@@ -504,13 +513,15 @@ __device__ inline int dec_chain_big(const DecPrep &P, DecChainSmem &S, int lane)
 
 // ------------------------------------------------------------------------ post (one CTA of 256 threads)
 constexpr int DP_THREADS = 256, DP_WARPS = 8;
-constexpr uint32_t DP_PER = 16, DP_TILE = DP_THREADS * DP_PER;
+constexpr uint32_t DP_PER = 16, DP_TILE = DP_THREADS * DP_PER, DP_STAGE = 8192;
 struct __align__(16) DecPostSmem {
     uint32_t lut[256];          // unpack: byte -> symbols
     uint8_t  isr[256];          // RLE: symbol is run-length coded
     uint32_t wsum[DP_WARPS], wsum2[DP_WARPS];
     uint32_t carry[4];
     uint32_t bad;
+    uint32_t pad_[3];
+    uint8_t  stage[DP_STAGE + 16];      // RLE: the output of one round of literals (16-byte aligned)
 };
 
 // exclusive scan of one value per thread over the CTA; returns the thread's offset, *total the sum
@@ -587,23 +598,33 @@ __device__ inline bool cta_rle_decode(const uint8_t *lit, uint32_t lit_len, cons
     }
     const bool partial = last_end < run_len;
     // ---- pass 2
+    const bool lit_al = (((uintptr_t)lit) & 15) == 0;
     uint32_t K = 0, op = 0;                                     // varints consumed / bytes written before this round
     for (uint32_t base = 0; base < lit_len; base += DP_TILE) {
         const uint32_t i0 = base + DP_PER * (uint32_t)tid;
+        const uint32_t nlit = i0 >= lit_len ? 0u : (lit_len - i0 < DP_PER ? lit_len - i0 : DP_PER);
         uint32_t c[DP_PER];
+        if (lit_al && nlit == DP_PER) {
+            const uint4 q = *(const uint4 *)(lit + i0);         // (written by the chain launch: plain load)
+            const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < (int)DP_PER; k++) c[k] = (w4[k >> 2] >> (8 * (k & 3))) & 0xff;
+        } else {
+#pragma unroll
+            for (int k = 0; k < (int)DP_PER; k++) c[k] = (uint32_t)k < nlit ? lit[i0 + k] : 0;
+        }
         uint32_t rm = 0;                                        // bit k: literal k carries a run
 #pragma unroll
-        for (int k = 0; k < (int)DP_PER; k++) {
-            c[k] = i0 + k < lit_len ? lit[i0 + k] : 0;
-            if (i0 + k < lit_len && S.isr[c[k]]) rm |= 1u << k;
-        }
+        for (int k = 0; k < (int)DP_PER; k++) if ((uint32_t)k < nlit && S.isr[c[k]]) rm |= 1u << k;
         uint32_t nrun_tot;
         const uint32_t kfirst = K + cta_excl_scan(__popc(rm), S.wsum, &nrun_tot);
         // the thread's varints: kfirst, kfirst + 1, ... ; values
         uint32_t val[DP_PER];
-        uint32_t lensum = 0;
+        uint32_t lensum = nlit;
         int tbad = 0;
-        {
+#pragma unroll
+        for (int k = 0; k < (int)DP_PER; k++) val[k] = 0;
+        if (rm) {
             uint32_t pos = 0;                                   // next byte of the run stream for this thread
             bool located = false;
             uint32_t kk = kfirst;
@@ -619,9 +640,9 @@ __device__ inline bool cta_rle_decode(const uint8_t *lit, uint32_t lit_len, cons
                             uint32_t lo = 0, hi = G;            // invariant: gp[lo] <= kk < gp[hi]
                             while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (gp[mid] <= kk) lo = mid; else hi = mid; }
                             const uint32_t e = 32 * lo + __fns(bm[lo], 0, kk - gp[lo] + 1);
-                            uint32_t s = e;
-                            while (s > 0 && e - s < 4 && (run[s - 1] & 0x80)) s--;
-                            pos = s;
+                            uint32_t s2 = e;
+                            while (s2 > 0 && e - s2 < 4 && (run[s2 - 1] & 0x80)) s2--;
+                            pos = s2;
                             located = true;
                         }
                         uint32_t b;
@@ -630,41 +651,76 @@ __device__ inline bool cta_rle_decode(const uint8_t *lit, uint32_t lit_len, cons
                     }
                 }
                 val[k] = v;
-                if (i0 + k < lit_len) lensum += v + 1;
+                lensum += v;
             }
         }
         uint32_t round_out;
-        uint32_t o = op + cta_excl_scan(lensum, S.wsum2, &round_out);
+        const uint32_t o0 = op + cta_excl_scan(lensum, S.wsum2, &round_out);
         // the reference's checks: outp >= out_end before each literal, outp + rlen >= out_end for runs
+        if (nlit) {
+            if (!rm) { if ((uint64_t)o0 + nlit > cap) tbad = 1; }
+            else {
+                uint32_t o = o0;
 #pragma unroll
-        for (int k = 0; k < (int)DP_PER; k++) {
-            if (i0 + k < lit_len) {
-                const uint32_t len = val[k] + 1;
-                if (o >= cap || (val[k] && (uint64_t)o + val[k] >= cap)) tbad = 1;
-                else if (len <= 32) for (uint32_t q = 0; q < len; q++) out[o + q] = (uint8_t)c[k];
-                o += len;
+                for (int k = 0; k < (int)DP_PER; k++)
+                    if ((uint32_t)k < nlit) {
+                        if (o >= cap || (val[k] && (uint64_t)o + val[k] >= cap)) tbad = 1;
+                        o += val[k] + 1;
+                    }
             }
         }
         if (__syncthreads_or(tbad)) return false;
+        // A round that expands to at most DP_STAGE bytes is put together in shared memory and leaves as 16-byte
+        // stores; a larger one (long runs) is written in place.
+        const bool staged = round_out <= DP_STAGE;
+        const uint32_t sa = (uint32_t)((uintptr_t)(out + op) & 15);   // the stage keeps the output's alignment mod 16
+        uint8_t *dst = staged ? S.stage + sa - op : out;        // byte x of the output goes to dst[x]
+        if (nlit) {
+            if (!rm) {
+#pragma unroll
+                for (int k = 0; k < (int)DP_PER; k++) if ((uint32_t)k < nlit) dst[o0 + k] = (uint8_t)c[k];
+            } else {
+                uint32_t o = o0;
+#pragma unroll
+                for (int k = 0; k < (int)DP_PER; k++)
+                    if ((uint32_t)k < nlit) {
+                        const uint32_t len = val[k] + 1;
+                        dst[o] = (uint8_t)c[k];
+                        if (len <= 32) for (uint32_t q = 1; q < len; q++) dst[o + q] = (uint8_t)c[k];
+                        o += len;
+                    }
+            }
+        }
         // long runs: the warp writes them together
-        {
-            uint32_t o2 = o - lensum;
+        if (__any_sync(FULL, rm != 0)) {
+            uint32_t o2 = o0;
 #pragma unroll
             for (int k = 0; k < (int)DP_PER; k++) {
-                const uint32_t len = i0 + k < lit_len ? val[k] + 1 : 0;
+                const uint32_t len = (uint32_t)k < nlit ? val[k] + 1 : 0;
                 uint32_t big = __ballot_sync(FULL, len > 32);
                 while (big) {
                     const int l = __ffs(big) - 1;
                     big &= big - 1;
                     const uint32_t oo = __shfl_sync(FULL, o2, l), ll = __shfl_sync(FULL, len, l), cc = __shfl_sync(FULL, c[k], l);
-                    for (uint32_t q = lane; q < ll; q += 32) out[oo + q] = (uint8_t)cc;
+                    for (uint32_t q = 1 + lane; q < ll; q += 32) dst[oo + q] = (uint8_t)cc;
                 }
                 o2 += len;
             }
         }
+        if (staged) {
+            __syncthreads();
+            uint8_t *g = out + op;
+            const uint8_t *sp = S.stage + sa;
+            uint32_t head = (16 - sa) & 15;
+            if (head > round_out) head = round_out;
+            if ((uint32_t)tid < head) g[tid] = sp[tid];
+            const uint32_t nv = (round_out - head) >> 4;
+            for (uint32_t i = tid; i < nv; i += DP_THREADS) *(uint4 *)(g + head + 16 * i) = *(const uint4 *)(sp + head + 16 * i);
+            for (uint32_t i = head + (nv << 4) + tid; i < round_out; i += DP_THREADS) g[i] = sp[i];
+            __syncthreads();
+        }
         K += nrun_tot;
         op += round_out;
-        (void)lt;
     }
     *out_len = op;
     __threadfence_block();
@@ -699,10 +755,16 @@ __device__ inline bool cta_unpack(const uint8_t *src, uint32_t len, uint8_t *dst
             const uint32_t *s4 = (const uint32_t *)src;
             uint4 *d16 = (uint4 *)dst;
             const uint32_t nq = whole >> 2;
-            for (uint32_t i = tid; i < nq; i += DP_THREADS) {
-                const uint32_t w = s4[i];
-                d16[i] = make_uint4(lut[w & 0xff], lut[(w >> 8) & 0xff], lut[(w >> 16) & 0xff], lut[w >> 24]);
+            auto expand = [&](uint32_t w) {
+                return make_uint4(lut[w & 0xff], lut[(w >> 8) & 0xff], lut[(w >> 16) & 0xff], lut[w >> 24]);
+            };
+            uint32_t i = tid;
+            for (; i + 3 * DP_THREADS < nq; i += 4 * DP_THREADS) {          // four loads in flight per thread
+                const uint32_t w0 = s4[i], w1 = s4[i + DP_THREADS], w2 = s4[i + 2 * DP_THREADS], w3 = s4[i + 3 * DP_THREADS];
+                d16[i] = expand(w0); d16[i + DP_THREADS] = expand(w1);
+                d16[i + 2 * DP_THREADS] = expand(w2); d16[i + 3 * DP_THREADS] = expand(w3);
             }
+            for (; i < nq; i += DP_THREADS) d16[i] = expand(s4[i]);
             j0 = nq << 2;
         }
         for (uint32_t j = j0 + tid; j < whole; j += DP_THREADS) d4[j] = lut[src[j]];

@@ -467,11 +467,13 @@ struct DecO1Big {
     // returns the entry for slot m in context ctx
     __device__ __forceinline__ uint32_t look(uint32_t m, uint32_t ctx) const {
         const uint32_t *r = rec + (((ctx << 6) + (m >> (shift - 6))) << 3);
-        uint4 a, c;
-        asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w)
+        uint4 a, c;                                          // one 32-byte load: one request for the record's sector
+#ifndef B200_LOOK_LD
+#define B200_LOOK_LD "ld.global.v8.u32"
+#endif
+        asm volatile(B200_LOOK_LD " {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w)
                      : "l"(__cvta_generic_to_global(r)));
-        asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w)
-                     : "l"(__cvta_generic_to_global(r + 4)));
         const uint32_t T = (m << 20) | 0xfffff;              // entries with start <= m are <= T
         uint32_t best = a.x;                                 // the bucket's first entry always qualifies
         best = max(best, a.y <= T ? a.y : 0u);

@@ -161,6 +161,10 @@ struct Ctx {
         if (device < 0 || device >= n) return B200RANS_EINVAL;
         dev = device;
         CK(cudaSetDevice(dev));
+        {   // measurement knob: the L2's DRAM fetch granularity (32 / 64 / 128 bytes; device default when unset)
+            static int g = env_int("B200RANS_L2_FETCH", 0, 0, 128);
+            if (g) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
+        }
         for (auto &l : lane) { int r = l.init(); if (r) return r; }
         { int r = dlane.init(); if (r) return r; }
         single.pinned = true;
