@@ -430,7 +430,7 @@ int compress_batch_impl(int n, const unsigned char *const *in, const unsigned in
         const size_t no = M ? mfirst[n] : (size_t)n;
         for (size_t i = 0; i < no && !slow; i++) slow = (o[i] & (X_PACK | X_RLE)) != 0;
     }
-    const int min_streams = slow ? CHUNK_MIN_STREAMS_SLOW : chunk_min_streams();
+    const int min_streams = slow ? chunk_min_streams_slow(false) : chunk_min_streams();
     std::vector<EncChunk> ch;
     for (int k = 0; k < n;) {
         EncChunk c;
@@ -615,7 +615,7 @@ int uncompress_batch_impl(int n, const unsigned char *const *in, const unsigned 
             }
             it.njobs = (uint32_t)jin.size() - it.first_job;
             acc += ocap[k];
-            if (it.njobs && (jflag.back() & (X_PACK | X_RLE))) dec_min_streams = CHUNK_MIN_STREAMS_SLOW;
+            if (it.njobs && (jflag.back() & (X_PACK | X_RLE))) dec_min_streams = chunk_min_streams_slow(true);
             if ((acc >= chunk_bytes() && k - c.k0 + 1 >= dec_min_streams) || k - c.k0 + 1 >= CHUNK_MAX_STREAMS || k == n - 1) {
                 c.k1 = k + 1; c.j1 = (int)jin.size();
                 ch.push_back(c);

@@ -86,6 +86,11 @@ inline bool use_prep() { static int v = env_int("B200RANS_PREP", 1, 0, 1); retur
 // order-1 streams behind PACK / RLE: staged decode (dec_staged.cu); 0 = the general kernel alone (kept for measurement)
 inline bool use_dec_staged() { static int v = env_int("B200RANS_DEC_STAGED", 1, 0, 1); return v != 0; }
 inline size_t chunk_bytes() { static size_t v = (size_t)env_int("B200RANS_CHUNK_MB", 48, 1, 1024) << 20; return v; }
+inline int chunk_min_streams_slow(bool dec) {
+    static int ve = env_int("B200RANS_CHUNK_STREAMS_SLOW", CHUNK_MIN_STREAMS_SLOW, 1, 16384);
+    static int vd = env_int("B200RANS_CHUNK_STREAMS_SLOW_DEC", CHUNK_MIN_STREAMS_SLOW, 1, 16384);
+    return dec ? vd : ve;
+}
 inline int chunk_min_streams() { static int v = env_int("B200RANS_CHUNK_STREAMS", 256, 1, 16384); return v; }
 
 // One pipeline lane: a stream plus the arenas a chunk of work needs.  Chunks of a
@@ -161,10 +166,6 @@ struct Ctx {
         if (device < 0 || device >= n) return B200RANS_EINVAL;
         dev = device;
         CK(cudaSetDevice(dev));
-        {   // measurement knob: the L2's DRAM fetch granularity (32 / 64 / 128 bytes; device default when unset)
-            static int g = env_int("B200RANS_L2_FETCH", 0, 0, 128);
-            if (g) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
-        }
         for (auto &l : lane) { int r = l.init(); if (r) return r; }
         { int r = dlane.init(); if (r) return r; }
         single.pinned = true;
