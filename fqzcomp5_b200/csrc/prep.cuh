@@ -755,31 +755,40 @@ __device__ __forceinline__ void enc_o1_payload_stream(const uint2 *E, uint32_t n
     const uint2 *q = E + (size_t)(act ? lane : 0) * seg;
     uint32_t k = seg;                                        // positions q[1 .. k) are still to be coded
     __syncwarp();
-    if (N == 32 && seg >= 8 && (seg & 3) == 0) {
-        // groups of four entries (two 16-byte loads per lane), one group ahead of the chain
-        const uint4 *v = (const uint4 *)q;
+    if (N == 32 && seg >= 8) {
+        // Groups of four entries counted from the END of the lane's segment, one group ahead of the chain in registers
+        // (a segment has any length -- the payload behind RLE -- so the groups are 8-byte aligned only); the seg % 4
+        // entries in front of the first group go through the loop below.  Every lane walks its own segment: the
+        // lines further down are asked into L2 sixteen groups (four lines) ahead.
+        const uint32_t lead = seg & 3;
+        const uint2 *qq = q + lead;                          // qq[4 g .. 4 g + 3] = group g
+        auto ld4 = [&](uint32_t g, uint2 (&c)[4]) {
+            const uint2 *p = qq + 4 * (size_t)g;
+            c[0] = p[0]; c[1] = p[1]; c[2] = p[2]; c[3] = p[3];
+        };
         uint32_t j = seg >> 2;
-        uint4 c0 = v[2 * j - 2], c1 = v[2 * j - 1];
-        // every lane walks its own segment, 32 bytes per group: the next group is in registers, the lines further
-        // down are asked into L2 sixteen groups (four lines) ahead -- a DRAM round trip is several groups long
+        uint2 c[4];
+        ld4(j - 1, c);
         for (uint32_t a = 2; a <= 16 && a < j; a++)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(__cvta_generic_to_global(v + 2 * (j - a) - 2)));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(__cvta_generic_to_global(qq + 4 * (size_t)(j - a))));
         while (j > 1) {
-            if (j > 17) asm volatile("prefetch.global.L2 [%0];" ::"l"(__cvta_generic_to_global(v + 2 * (j - 17) - 2)));
-            const uint4 n0 = v[2 * j - 4], n1 = v[2 * j - 3];
+            if (j > 17) asm volatile("prefetch.global.L2 [%0];" ::"l"(__cvta_generic_to_global(qq + 4 * (size_t)(j - 18))));
+            uint2 nx[4];
+            ld4(j - 2, nx);
             w.maybe_flush(lane);
-            R = enc_step(R, true, enc_sym_unpack2(make_uint2(c1.z, c1.w), shift), w, lane);
-            R = enc_step(R, true, enc_sym_unpack2(make_uint2(c1.x, c1.y), shift), w, lane);
-            R = enc_step(R, true, enc_sym_unpack2(make_uint2(c0.z, c0.w), shift), w, lane);
-            R = enc_step(R, true, enc_sym_unpack2(make_uint2(c0.x, c0.y), shift), w, lane);
-            c0 = n0; c1 = n1;
+            R = enc_step(R, true, enc_sym_unpack2(c[3], shift), w, lane);
+            R = enc_step(R, true, enc_sym_unpack2(c[2], shift), w, lane);
+            R = enc_step(R, true, enc_sym_unpack2(c[1], shift), w, lane);
+            R = enc_step(R, true, enc_sym_unpack2(c[0], shift), w, lane);
+            c[0] = nx[0]; c[1] = nx[1]; c[2] = nx[2]; c[3] = nx[3];
             j--;
         }
-        w.maybe_flush(lane);                                 // group 0: its first entry is the lane's first symbol
-        R = enc_step(R, true, enc_sym_unpack2(make_uint2(c1.z, c1.w), shift), w, lane);
-        R = enc_step(R, true, enc_sym_unpack2(make_uint2(c1.x, c1.y), shift), w, lane);
-        R = enc_step(R, true, enc_sym_unpack2(make_uint2(c0.z, c0.w), shift), w, lane);
-        k = 1;
+        w.maybe_flush(lane);                                 // group 0
+        R = enc_step(R, true, enc_sym_unpack2(c[3], shift), w, lane);
+        R = enc_step(R, true, enc_sym_unpack2(c[2], shift), w, lane);
+        R = enc_step(R, true, enc_sym_unpack2(c[1], shift), w, lane);
+        if (lead) R = enc_step(R, true, enc_sym_unpack2(c[0], shift), w, lane);    // else it is the lane's first symbol
+        k = lead ? lead : 1;
     }
     for (; k > 1; k--) {
         uint4 e = make_uint4(0, 0, 0, 0);
