@@ -604,6 +604,12 @@ static cudaError_t ensure_rcp_table(cudaStream_t st) {
     return cudaSuccess;
 }
 
+#ifdef B200_PREP_PROF
+extern "C" __attribute__((visibility("default"))) int b200rans_prep_prof(unsigned long long *out16) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out16, g_prep_prof, sizeof(g_prep_prof));
+}
+#endif
 size_t prep_area_bytes(uint32_t in_size) { return prep_plan(in_size).total; }
 
 cudaError_t launch_prep(EncJob *d_jobs, uint32_t n, cudaStream_t st) {

@@ -15,6 +15,15 @@
 
 namespace b200 {
 
+#ifdef B200_PREP_PROF
+__device__ unsigned long long g_prep_prof[16];
+#define PREP_T0() long long t_prof = clock64()
+#define PREP_T(i) do { __syncthreads(); if (threadIdx.x == 0) { long long t2 = clock64(); atomicAdd(&g_prep_prof[i], (unsigned long long)(t2 - t_prof)); t_prof = t2; } } while (0)
+#else
+#define PREP_T0() do {} while (0)
+#define PREP_T(i) do {} while (0)
+#endif
+
 constexpr int PREP_THREADS = 256, PREP_WARPS = 8;
 
 // What the CTA leaves for the coder warp, at the head of the job's prep area (J.prep).
@@ -494,6 +503,7 @@ __device__ __forceinline__ uint32_t row_emit(const uint32_t (&f)[8], uint32_t ns
 __device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint8_t *bucket, uint8_t *rowstage,
                                     uint32_t *symtab, uint2 *E, uint8_t *tbl, Prep &P, PrepSmem &S) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    PREP_T0();
     // ---- alphabet = symbols present, plus 0 (:357-361)
     const bool pres = S.T[tid] != 0 || tid == 0;
     {
@@ -509,6 +519,7 @@ __device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint8_
     // ---- pairs dealt into their contexts' buckets (the lane starts of :325-327 included)
     const bool stream_syms = nsym > PREP_SYM_MAX;       // encoder symbols per position instead of a table
     cta_pair_buckets(in, n, N, nsym, bucket, S);
+    PREP_T(4);
     S.bstart[tid] = S.rowlen[tid];
     if (tid == 0) S.bstart[256] = n + (uint32_t)N - 1;
     __syncthreads();
@@ -561,6 +572,7 @@ __device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint8_
     }
     if (lane == 0) { S.red[0][wid] = e10; S.red[1][wid] = e12; S.redu[wid] = max_tot; }
     __syncthreads();
+    PREP_T(5);
     e10 = 0; e12 = 0; max_tot = 0;
 #pragma unroll
     for (int w = 0; w < PREP_WARPS; w++) { e10 += S.red[0][w]; e12 += S.red[1][w]; max_tot = max(max_tot, S.redu[w]); }
@@ -637,6 +649,7 @@ __device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint8_
     }
     err = __any_sync(FULL, err);
     if (err && lane == 0) P.err = 1;
+    PREP_T(6);
     // ---- the alphabet of the contexts, 0 forced in (:357-361), then the rows' offsets
     if (tid == 0) {
         uint8_t *cp = tbl;
@@ -674,6 +687,7 @@ __device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint8_
         warp_copy(tbl + S.bstart[i], rowstage + (size_t)i * PREP_ROW_STRIDE, S.rowlen[i], lane);
     __threadfence_block();
     __syncthreads();
+    PREP_T(7);
     if (stream_syms) {
         // E[p] = symbol of in[p] in the context of in[p-1] (E[0]: context 0); E[n + z] = first symbol of lane z in
         // context 0: the packed 4-byte symbol and, beside it, the reciprocal of its frequency, so that a chain step
@@ -710,6 +724,7 @@ __device__ inline void cta_o1_model(const uint8_t *in, uint32_t n, int N, uint8_
         if (tid >= 1 && tid < N) E[n + tid] = with_rcp(symtab[r0 * nsym + rank[in[(size_t)tid * seg]]]);
         __syncthreads();
     }
+    PREP_T(8);
     if (tid == 0) { P.nsym = nsym; P.shift = shift; P.tl = S.bc[1]; P.stream_syms = stream_syms ? 1u : 0u; }
 }
 
@@ -888,6 +903,7 @@ __device__ inline void prep_stream(EncJob &J, PrepSmem &S) {
     const uint32_t meta = 1 + (no_size ? 0 : var_size_u32(in_size));
     uint8_t *work = J.work;
     uint32_t packed = 0, pmeta = 0, plen = 0, rle_len = 0, rmeta_len = 0;
+    PREP_T0();
     if (do_pack) {                                                        // rANS_static4x16pr.c:1429-1459
         packed = cta_pack(in, in_size, J.slot + meta, &pmeta, work, &plen, S) ? 1u : 0u;
         if (packed) {
@@ -896,6 +912,7 @@ __device__ inline void prep_stream(EncJob &J, PrepSmem &S) {
             if (do_simd && in_size < 32) do_simd = 0;
         }
     }
+    PREP_T(0);
     if (do_rle && in_size) {                                              // :1464-1533
         uint8_t *lits = work, *rmeta = work + ((in_size + 15) & ~15u);
         cta_rle_encode(in, in_size, lits, &rle_len, rmeta, &rmeta_len, S);
@@ -904,10 +921,12 @@ __device__ inline void prep_stream(EncJob &J, PrepSmem &S) {
             in = lits; in_size = rle_len;
         }
     }
+    PREP_T(1);
     if (o1 && in_size < 8) o1 = 0;                                        // :1547
     uint32_t model = 0;
     if (in_size) {
         cta_hist8(in, in_size, S);
+        PREP_T(2);
         P.F[tid] = S.T[tid];
         model = 1;
         const int N = do_simd ? 32 : 4;
