@@ -430,7 +430,17 @@ int compress_batch_impl(int n, const unsigned char *const *in, const unsigned in
         const size_t no = M ? mfirst[n] : (size_t)n;
         for (size_t i = 0; i < no && !slow; i++) slow = (o[i] & (X_PACK | X_RLE)) != 0;
     }
-    const int min_streams = slow ? chunk_min_streams_slow(false) : chunk_min_streams();
+    // large 4-lane streams: a 256 KiB stream is 65 536 dependent steps per lane (several ms) whatever the size of the
+    // launch, so a chunk should hold as many of them as the GPU has warp slots
+    bool lanes4 = false;
+    for (int k = 0; k < n && !lanes4; k++) {
+        if (in_size[k] < 32768) continue;
+        const uint32_t c0 = M ? mfirst[k] : (uint32_t)k, c1 = M ? mfirst[k + 1] : (uint32_t)k + 1;
+        const int *o = M ? methods : order;
+        for (uint32_t c2 = c0; c2 < c1 && !lanes4; c2++)
+            lanes4 = !(o[c2] & X_32) && !((o[c2] & ORDER_SIMD_AUTO) && in_size[k] >= 50000) && !(o[c2] & (X_STRIPE | X_CAT));
+    }
+    const int min_streams = lanes4 ? chunk_min_streams_4lane() : slow ? chunk_min_streams_slow(false) : chunk_min_streams();
     std::vector<EncChunk> ch;
     for (int k = 0; k < n;) {
         EncChunk c;
@@ -615,7 +625,9 @@ int uncompress_batch_impl(int n, const unsigned char *const *in, const unsigned 
             }
             it.njobs = (uint32_t)jin.size() - it.first_job;
             acc += ocap[k];
-            if (it.njobs && (jflag.back() & (X_PACK | X_RLE))) dec_min_streams = chunk_min_streams_slow(true);
+            if (it.njobs && (jflag.back() & (X_PACK | X_RLE))) dec_min_streams = std::max(dec_min_streams, chunk_min_streams_slow(true));
+            if (it.njobs && !(jflag.back() & (X_32 | X_CAT)) && ocap[k] >= 32768)       // large 4-lane stream (see the encoder)
+                dec_min_streams = std::max(dec_min_streams, chunk_min_streams_4lane());
             if ((acc >= chunk_bytes() && k - c.k0 + 1 >= dec_min_streams) || k - c.k0 + 1 >= CHUNK_MAX_STREAMS || k == n - 1) {
                 c.k1 = k + 1; c.j1 = (int)jin.size();
                 ch.push_back(c);

@@ -770,7 +770,7 @@ __device__ __forceinline__ void enc_o1_payload_stream(const uint2 *E, uint32_t n
     const uint2 *q = E + (size_t)(act ? lane : 0) * seg;
     uint32_t k = seg;                                        // positions q[1 .. k) are still to be coded
     __syncwarp();
-    if (N == 32 && seg >= 8) {
+    if (seg >= 8) {
         // Groups of four entries counted from the END of the lane's segment, one group ahead of the chain in registers
         // (a segment has any length -- the payload behind RLE -- so the groups are 8-byte aligned only); the seg % 4
         // entries in front of the first group go through the loop below.  Every lane walks its own segment: the
@@ -791,18 +791,18 @@ __device__ __forceinline__ void enc_o1_payload_stream(const uint2 *E, uint32_t n
             uint2 nx[4];
             ld4(j - 2, nx);
             w.maybe_flush(lane);
-            R = enc_step(R, true, enc_sym_unpack2(c[3], shift), w, lane);
-            R = enc_step(R, true, enc_sym_unpack2(c[2], shift), w, lane);
-            R = enc_step(R, true, enc_sym_unpack2(c[1], shift), w, lane);
-            R = enc_step(R, true, enc_sym_unpack2(c[0], shift), w, lane);
+            R = enc_step(R, act, enc_sym_unpack2(c[3], shift), w, lane);
+            R = enc_step(R, act, enc_sym_unpack2(c[2], shift), w, lane);
+            R = enc_step(R, act, enc_sym_unpack2(c[1], shift), w, lane);
+            R = enc_step(R, act, enc_sym_unpack2(c[0], shift), w, lane);
             c[0] = nx[0]; c[1] = nx[1]; c[2] = nx[2]; c[3] = nx[3];
             j--;
         }
         w.maybe_flush(lane);                                 // group 0
-        R = enc_step(R, true, enc_sym_unpack2(c[3], shift), w, lane);
-        R = enc_step(R, true, enc_sym_unpack2(c[2], shift), w, lane);
-        R = enc_step(R, true, enc_sym_unpack2(c[1], shift), w, lane);
-        if (lead) R = enc_step(R, true, enc_sym_unpack2(c[0], shift), w, lane);    // else it is the lane's first symbol
+        R = enc_step(R, act, enc_sym_unpack2(c[3], shift), w, lane);
+        R = enc_step(R, act, enc_sym_unpack2(c[2], shift), w, lane);
+        R = enc_step(R, act, enc_sym_unpack2(c[1], shift), w, lane);
+        if (lead) R = enc_step(R, act, enc_sym_unpack2(c[0], shift), w, lane);    // else it is the lane's first symbol
         k = lead ? lead : 1;
     }
     for (; k > 1; k--) {

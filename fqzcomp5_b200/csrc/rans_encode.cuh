@@ -948,11 +948,12 @@ __device__ __forceinline__ void enc_o1_payload(const uint8_t *in, uint32_t n, ui
             rc = rn;
         }
         kstart = 1;
-    } else if (N == 32 && seg >= 32) {
-        // Encoder symbols in global memory (large alphabets): the 16 symbols of a group are
-        // requested together before the group's 16 steps run, so one L2/DRAM round trip is paid
-        // per group instead of per step.  Groups are counted from the END of the lane's segment
-        // (any alignment, any length); the seg % 16 bytes at its start go through the loop below.
+    } else if (seg >= 32) {
+        // Any lane count, any alignment, encoder symbols in shared or global memory: the 16 input bytes
+        // and the 16 symbols of a group are requested together before the group's 16 steps run, so one
+        // round trip to memory is paid per group instead of per step (a 4-lane stream of 256 KiB is
+        // 65 536 steps per lane: with one exposed global load each it took ~35 ms).  Groups are counted
+        // from the END of the lane's segment; the seg % 16 bytes at its start go through the loop below.
         const uint32_t rank_s = (uint32_t)__cvta_generic_to_shared(rank);
         const uint32_t J = seg >> 4, lead = seg & 15;
         const uint8_t *g0 = q + lead;                          // group j = bytes g0[16j .. 16j+15]
@@ -977,7 +978,7 @@ __device__ __forceinline__ void enc_o1_payload(const uint8_t *in, uint32_t n, ui
             for (int b = 15; b >= 0; b--) {
                 if (b == 0 && j == 0 && !lead) break;        // the lane's first symbol is coded below
                 if ((b & 3) == 3) w.maybe_flush(lane);
-                R = enc_step(R, true, enc_sym_unpack(ev[b], shift), w, lane);
+                R = enc_step(R, act, enc_sym_unpack(ev[b], shift), w, lane);
             }
             rs = lead ? rk[0] : rk[1];                       // rank of the next symbol to code
             cur = prv;

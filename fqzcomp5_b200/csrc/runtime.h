@@ -91,6 +91,7 @@ inline int chunk_min_streams_slow(bool dec) {
     static int vd = env_int("B200RANS_CHUNK_STREAMS_SLOW_DEC", CHUNK_MIN_STREAMS_SLOW, 1, 16384);
     return dec ? vd : ve;
 }
+inline int chunk_min_streams_4lane() { static int v = env_int("B200RANS_CHUNK_STREAMS_4LANE", 4096, 1, 16384); return v; }
 inline int chunk_min_streams() { static int v = env_int("B200RANS_CHUNK_STREAMS", 256, 1, 16384); return v; }
 
 // One pipeline lane: a stream plus the arenas a chunk of work needs.  Chunks of a
