@@ -131,7 +131,9 @@ def codec_config(workload, order, U, S, n, world, ratio):
     """`config` of a codec workload: the same dict in the b200 and the reference arm."""
     return {"workload": workload, "description": WORKLOADS[workload][3], "order": hex(order), "block_bytes": U,
             "slice_bytes": S, "streams": n, "blocks": world,
-            "l2": "inputs (%.2f GB per step) exceed the 126 MB L2" % (U / 1e9), "ratio": ratio}
+            "l2": "inputs (%.2f GB per step) exceed the 126 MB L2" % (U / 1e9), "ratio": ratio,
+            "output": "one rans_compress_bound_4x16-sized buffer per call (in-slot), as the reference's callers "
+                      "provide; decode flags (first byte of each stream) are host-known"}
 
 
 def synth_seed(gen):
@@ -494,9 +496,7 @@ def codec_entry(name, r, world, ms_enc, ms_dec, e2e_ms):
     ms_step = ms_enc + ms_dec
     out = {
         "metric": METRIC, "value": world * U / (ms_step * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_step,
-        "config": dict(codec_config(name, r["order"], U, r["S"], r["n"], world, Cc / U),
-                       output="in-slot: one rans_compress_bound_4x16-sized buffer per call, as the reference's "
-                              "callers provide; decode flags (first byte of each stream) are host-known"),
+        "config": codec_config(name, r["order"], U, r["S"], r["n"], world, Cc / U),
         "enc_gbs": world * U / (ms_enc * 1e-3) / 1e9, "dec_gbs": world * U / (ms_dec * 1e-3) / 1e9,
         "enc_packed_gbs": (world * U / (r["packed_enc_ms"] * 1e-3) / 1e9) if r.get("packed_enc_ms") else None,
         "e2e": {"value": world * U / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s",
