@@ -586,7 +586,8 @@ def run_blocks(args, env, seq, qual, ngpu):
         pb.array[:] = t
         texts.append(pb)
     n = int(texts[0].array.size)
-    W = 2                                   # B200RANS_WORKERS_PER_DEVICE: block b runs on worker (b % ngpu, (b // ngpu) % W)
+    # workers per device the library's block calls use: block b runs on worker (b % ngpu, (b // ngpu) % W)
+    W = max(1, min(4, int(os.environ.get("B200RANS_BLOCK_WORKERS", "2"))))
     out_cap = n // 2 + (64 << 20)
     outs = [bc.PinnedBuffer(out_cap) for _ in range(ngpu * W)]
     backs = [bc.PinnedBuffer(n + 4096) for _ in range(ngpu * W)]

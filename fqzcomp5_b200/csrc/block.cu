@@ -110,6 +110,12 @@ int run_on_workers(int ngpu, int slots, const std::function<int(int, int)> &fn) 
     return rc;
 }
 
+// workers per device the block calls use (each holds the arenas of a block in flight)
+inline int block_workers() {
+    static int v = env_int("B200RANS_BLOCK_WORKERS", 2, 1, B200RANS_WORKERS_PER_DEVICE);
+    return v;
+}
+
 inline double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -829,7 +835,7 @@ API int b200fqz_encode_blocks_multi(int ngpu, int nblocks, const unsigned char *
                                     const b200fqz_block_opts *opts, unsigned char *const *block,
                                     const size_t *block_cap, b200fqz_block_report *rep) {
     if (nblocks < 0 || ngpu <= 0 || !opts || (nblocks && (!text || !n || !block || !block_cap || !rep))) return B200RANS_EINVAL;
-    const int W = B200RANS_WORKERS_PER_DEVICE;
+    const int W = block_workers();
     return run_on_workers(ngpu, W, [&](int g, int s) {
         for (int b = g + s * ngpu; b < nblocks; b += ngpu * W) {   // block b on device b % ngpu
             int r = encode_block_impl(text[b], n[b], opts, block[b], block_cap[b], &rep[b]);
@@ -843,7 +849,7 @@ API int b200fqz_decode_blocks_multi(int ngpu, int nblocks, const unsigned char *
                                     const uint32_t *block_len, int plus_name, unsigned char *const *text,
                                     const size_t *text_cap, b200fqz_block_report *rep) {
     if (nblocks < 0 || ngpu <= 0 || (nblocks && (!block || !block_len || !text || !text_cap || !rep))) return B200RANS_EINVAL;
-    const int W = B200RANS_WORKERS_PER_DEVICE;
+    const int W = block_workers();
     return run_on_workers(ngpu, W, [&](int g, int s) {
         for (int b = g + s * ngpu; b < nblocks; b += ngpu * W) {
             int r = decode_block_impl(block[b], block_len[b], plus_name, text[b], text_cap[b], &rep[b]);

@@ -222,10 +222,12 @@ int b200rans_tok3_methods(int level, int token_type, unsigned int in_len, int *o
 /* Multi-GPU block partitioning: streams are dealt round-robin by
  * `block_of[k]` >= 0 (or by k when NULL) over the first `ngpu` devices, results
  * gathered in call order (the hts_tpool contract, thread_pool.c:113-164).  The
- * worker threads -- B200RANS_WORKERS_PER_DEVICE per device, each with its own
+ * worker threads -- up to B200RANS_WORKERS_PER_DEVICE per device, each with its own
  * context, streams and arenas -- are created on first use and kept for the life
- * of the process.  No collective is involved. */
-#define B200RANS_WORKERS_PER_DEVICE 2
+ * of the process.  The block calls keep B200RANS_BLOCK_WORKERS of them busy per device
+ * (environment, default 2: one block copying in while another is being coded).
+ * No collective is involved. */
+#define B200RANS_WORKERS_PER_DEVICE 4
 int b200rans_compress_batch_multi(int ngpu, int n,
                                   const unsigned char *const *in, const unsigned int *in_size,
                                   const int *order, const int *block_of,
