@@ -39,6 +39,8 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
     const uint8_t *in = J.in;
     uint32_t in_size = J.in_size;
     uint8_t *out = J.slot;
+    // the order-0 kernel gives every warp a multiple of 1 KiB of shared memory: its output ring is aligned (OutRingT)
+    constexpr bool AL = !O1;
     // PACK / RLE streams: transforms, counts and the order-1 model may have been done by prep_kernel (prep.cuh)
     const Prep *P = (J.prep && ((const Prep *)J.prep)->state == 1) ? (const Prep *)J.prep : nullptr;
     CapCheck cc{J.cap, 1, J.cap != 0};            // (out && *out_size == 0) -> NULL (:1227)
@@ -116,8 +118,8 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
                 uint8_t *tmp = rmeta + ((rmeta_len + 15) & ~15u);        // scratch for the coded meta
                 uint32_t cb = (compress_bound(rmeta_len, 0) - 20) & ~1u, ctab = 0;
                 uint8_t *cptr = nullptr;
-                int e = do_simd ? enc_o0<32>(rmeta, rmeta_len, tmp, tmp + cb, &ctab, &cptr, *(EncO0Smem *)smem, lane)
-                                : enc_o0<4>(rmeta, rmeta_len, tmp, tmp + cb, &ctab, &cptr, *(EncO0Smem *)smem, lane);
+                int e = do_simd ? enc_o0<32, AL>(rmeta, rmeta_len, tmp, tmp + cb, &ctab, &cptr, *(EncO0Smem *)smem, lane)
+                                : enc_o0<4, AL>(rmeta, rmeta_len, tmp, tmp + cb, &ctab, &cptr, *(EncO0Smem *)smem, lane);
                 if (e) status = ST_FAIL;
                 uint32_t pay = (uint32_t)(tmp + cb - cptr), c_rmeta = ctab + pay, sz2 = 0;
                 if (!e && c_rmeta < rmeta_len) {
@@ -169,8 +171,8 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
                 e = 3;      // order-1 stream routed to the order-0-only kernel: host bug
             } else {
                 EncO0Smem &S = *(EncO0Smem *)smem;
-                e = do_simd ? enc_o0<32>(in, in_size, out + meta, oend, &tab, &ptr, S, lane, model)
-                            : enc_o0<4>(in, in_size, out + meta, oend, &tab, &ptr, S, lane, model);
+                e = do_simd ? enc_o0<32, AL>(in, in_size, out + meta, oend, &tab, &ptr, S, lane, model)
+                            : enc_o0<4, AL>(in, in_size, out + meta, oend, &tab, &ptr, S, lane, model);
             }
             if (e) status = (e == 2 || e == 3) ? ST_UNSUPPORTED : ST_FAIL;
         }
@@ -213,7 +215,9 @@ __device__ void enc_stream(EncJob &J, uint8_t *smem, uint32_t smem_bytes, const 
 template <bool O1, bool PREPPED>
 __global__ void __launch_bounds__((O1 ? ENC_WARPS_O1 : ENC_WARPS) * 32, PREPPED ? 14 : O1 ? 11 : 7)
 enc_kernel(EncJob *jobs, uint32_t njobs, uint32_t warp_smem, Pool pool, uint32_t route, uint32_t inslot) {
-    extern __shared__ __align__(16) uint8_t smem_all[];
+    extern __shared__ __align__(1024) uint8_t smem_all[];
+    static_assert(ENC_SMEM_O0 % ORING == 0, "the order-0 kernel's output rings are aligned to their size");
+    if (!O1 && ((warp_smem | (uint32_t)__cvta_generic_to_shared(smem_all)) & (ORING - 1))) __trap();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t j = blockIdx.x * (O1 ? ENC_WARPS_O1 : ENC_WARPS) + wid;
     if (j >= njobs || jobs[j].route != route) return;   // another launch's stream, or a STRIPE parent
@@ -474,14 +478,29 @@ cudaError_t launch_inslot_results(EncJob *d_jobs, uint32_t njobs, const uint32_t
 }
 
 // ------------------------------------------------------------------------
-// Histograms at full occupancy: one CTA of 8 warps per stream counts its bytes
-// into warp-private shared-memory bins (order 0) and, for order-1 streams, its
-// (previous, current) pairs into a rank-space matrix, merging equal neighbours
-// before touching shared memory.  The coder kernels then start from the counts
-// instead of reading the stream a second time with one warp.
+// Histograms at full occupancy: one CTA of 8 warps per stream.  Order 0: a table of 256 symbols x 32
+// columns in shared memory, lane l of every warp counting into column l -- the 32 shared-memory
+// atomics of a warp instruction fall into 32 different banks whatever the bytes are, so a byte costs
+// three instructions (shift, mask + base, ATOMS.POPC.INC) and the pass runs at the speed the stream
+// arrives from DRAM (0.19 ms per GB against 0.43 ms for warp-private bins with equal neighbours
+// merged, which is bound by its 13 instructions per byte: scripts/microbench/hist_variants.cu).
+// Order-1 streams then count their (previous, current) pairs into a rank-space matrix, merging
+// equal neighbours before touching shared memory.  The coder kernels start from the counts instead
+// of reading the stream a second time with one warp.
 // ------------------------------------------------------------------------
 constexpr int HIST_THREADS = 256;
-constexpr uint32_t HIST_SMEM_PAIRS = 6400;          // words: rank-space matrices up to 80x80 stay in shared memory
+constexpr uint32_t HIST_COLS = 32;                  // one column per lane
+constexpr uint32_t HIST_SMEM_PAIRS = 256 * HIST_COLS;   // words: the pair matrix reuses the order-0 table (up to 90 x 90 symbols)
+
+// the four bytes of w, each into its row of the lane's column; base = table + 4 * lane (shared space)
+__device__ __forceinline__ void hist_word_cols(uint32_t w, uint32_t base) {
+    const uint32_t a0 = ((w << 7) & 0x7f80u) + base, a1 = ((w >> 1) & 0x7f80u) + base,
+                   a2 = ((w >> 9) & 0x7f80u) + base, a3 = ((w >> 17) & 0x7f80u) + base;
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a0) : "memory");
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a1) : "memory");
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a2) : "memory");
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a3) : "memory");
+}
 
 __global__ void __launch_bounds__(HIST_THREADS)
 hist_kernel(EncJob *jobs, uint32_t njobs) {
@@ -490,14 +509,13 @@ hist_kernel(EncJob *jobs, uint32_t njobs) {
     EncJob &J = jobs[jn];
     uint32_t *model = J.model;
     if (!model) return;
-    __shared__ uint32_t Fw[8][256];
+    __shared__ __align__(16) uint32_t Hs[HIST_SMEM_PAIRS];       // order 0: [symbol][column]; then the pair matrix
     __shared__ uint8_t rank[256];
     __shared__ uint32_t wtot[8];
-    __shared__ uint32_t Hs[HIST_SMEM_PAIRS];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint8_t *in = J.in;
     const uint32_t n = J.in_size;
-    for (int j = tid; j < 8 * 256; j += HIST_THREADS) (&Fw[0][0])[j] = 0;
+    for (int j = tid; j < (int)(HIST_SMEM_PAIRS / 4); j += HIST_THREADS) ((uint4 *)Hs)[j] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     uint32_t head = (uint32_t)((16 - ((uintptr_t)in & 15)) & 15);
     if (head > n) head = n;
@@ -505,21 +523,29 @@ hist_kernel(EncJob *jobs, uint32_t njobs) {
     const uint32_t rest = n - head, nv = rest >> 4;
     const uint4 *v = (const uint4 *)p;
     {
-        uint32_t *F = Fw[wid];
-        if ((uint32_t)tid < head) atomicAdd(&F[in[tid]], 1u);
+        const uint32_t base = (uint32_t)__cvta_generic_to_shared(Hs) + 4 * lane;
+        if ((uint32_t)tid < head) atomicAdd(&Hs[in[tid] * HIST_COLS + lane], 1u);
         uint32_t i = tid;
-        for (; i + 3 * HIST_THREADS < nv; i += 4 * HIST_THREADS) {
-            uint4 q0 = ldg_u128(v + i), q1 = ldg_u128(v + i + HIST_THREADS),
-                  q2 = ldg_u128(v + i + 2 * HIST_THREADS), q3 = ldg_u128(v + i + 3 * HIST_THREADS);
-            hist16(q0, F); hist16(q1, F); hist16(q2, F); hist16(q3, F);
+        for (; i + 7 * HIST_THREADS < nv; i += 8 * HIST_THREADS) {
+            uint4 q[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) q[u] = ldg_u128(v + i + u * HIST_THREADS);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                hist_word_cols(q[u].x, base); hist_word_cols(q[u].y, base);
+                hist_word_cols(q[u].z, base); hist_word_cols(q[u].w, base);
+            }
         }
-        for (; i < nv; i += HIST_THREADS) hist16(ldg_u128(v + i), F);
-        for (uint32_t t = (nv << 4) + tid; t < rest; t += HIST_THREADS) atomicAdd(&F[p[t]], 1u);
+        for (; i < nv; i += HIST_THREADS) {
+            const uint4 q = ldg_u128(v + i);
+            hist_word_cols(q.x, base); hist_word_cols(q.y, base); hist_word_cols(q.z, base); hist_word_cols(q.w, base);
+        }
+        for (uint32_t t = (nv << 4) + tid; t < rest; t += HIST_THREADS) atomicAdd(&Hs[p[t] * HIST_COLS + lane], 1u);
     }
     __syncthreads();
-    uint32_t f = 0;
-#pragma unroll
-    for (int w = 0; w < 8; w++) f += Fw[w][tid];
+    uint32_t f = 0;                                   // row tid, columns rotated so that a warp reads 32 banks
+#pragma unroll 8
+    for (int k = 0; k < (int)HIST_COLS; k++) f += Hs[tid * HIST_COLS + ((k + tid) & (HIST_COLS - 1))];
     model[tid] = f;
     const bool o1 = (J.order & 1) && n >= 8;
     if (!o1) return;                                  // uniform per CTA

@@ -747,7 +747,7 @@ __device__ __forceinline__ uint4 enc_sym_unpack2(uint2 c, uint32_t bits) {
     s.x = (f << (31 - bits)) - 1;
     s.y = c.y;
     s.z = c.x & 0x1fff;
-    s.w = (((1u << bits) - f) & 0xffff) | ((c.x >> 26) << 16);
+    s.w = (((1u << bits) - f) << 16) | (c.x >> 26);
     return s;
 }
 template <int N>
@@ -791,31 +791,31 @@ __device__ __forceinline__ void enc_o1_payload_stream(const uint2 *E, uint32_t n
             uint2 nx[4];
             ld4(j - 2, nx);
             w.maybe_flush(lane);
-            R = enc_step(R, act, enc_sym_unpack2(c[3], shift), w, lane);
-            R = enc_step(R, act, enc_sym_unpack2(c[2], shift), w, lane);
-            R = enc_step(R, act, enc_sym_unpack2(c[1], shift), w, lane);
-            R = enc_step(R, act, enc_sym_unpack2(c[0], shift), w, lane);
+            R = enc_step<N == 32>(R, act, enc_sym_unpack2(c[3], shift), w, lane);
+            R = enc_step<N == 32>(R, act, enc_sym_unpack2(c[2], shift), w, lane);
+            R = enc_step<N == 32>(R, act, enc_sym_unpack2(c[1], shift), w, lane);
+            R = enc_step<N == 32>(R, act, enc_sym_unpack2(c[0], shift), w, lane);
             c[0] = nx[0]; c[1] = nx[1]; c[2] = nx[2]; c[3] = nx[3];
             j--;
         }
         w.maybe_flush(lane);                                 // group 0
-        R = enc_step(R, act, enc_sym_unpack2(c[3], shift), w, lane);
-        R = enc_step(R, act, enc_sym_unpack2(c[2], shift), w, lane);
-        R = enc_step(R, act, enc_sym_unpack2(c[1], shift), w, lane);
-        if (lead) R = enc_step(R, act, enc_sym_unpack2(c[0], shift), w, lane);    // else it is the lane's first symbol
+        R = enc_step<N == 32>(R, act, enc_sym_unpack2(c[3], shift), w, lane);
+        R = enc_step<N == 32>(R, act, enc_sym_unpack2(c[2], shift), w, lane);
+        R = enc_step<N == 32>(R, act, enc_sym_unpack2(c[1], shift), w, lane);
+        if (lead) R = enc_step<N == 32>(R, act, enc_sym_unpack2(c[0], shift), w, lane);    // else it is the lane's first symbol
         k = lead ? lead : 1;
     }
     for (; k > 1; k--) {
         uint4 e = make_uint4(0, 0, 0, 0);
         if (act) e = enc_sym_unpack2(q[k - 1], shift);
         w.maybe_flush(lane);
-        R = enc_step(R, act, e, w, lane);
+        R = enc_step<N == 32>(R, act, e, w, lane);
     }
     if (seg) {                                               // every lane's first symbol: context 0
         uint4 e = make_uint4(0, 0, 0, 0);
         if (act) e = enc_sym_unpack2(lane ? E[n + lane] : E[0], shift);
         w.maybe_flush(lane);
-        R = enc_step(R, act, e, w, lane);
+        R = enc_step<N == 32>(R, act, e, w, lane);
     }
     enc_flush(R, act, N, w, lane);
     *ptr_out = w.slot + w.off;

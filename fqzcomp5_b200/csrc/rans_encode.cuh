@@ -202,7 +202,9 @@ __device__ inline int put_alphabet(uint8_t *cp, const uint32_t *F) {
 }
 
 // Encoder symbol (rANS_word.h:171-179,201-272) packed into 16 bytes:
-//   x = x_max, y = rcp_freq, z = bias, w = cmpl_freq | (rcp_shift-32)<<16
+//   x = x_max, y = rcp_freq, z = bias, w = cmpl_freq << 16 | (rcp_shift - 32)
+// (the shift in the low bits: a wrapping funnel shift takes its count from the low five bits of a
+// register, so a step needs no instruction to extract it)
 __device__ __forceinline__ uint4 enc_sym_init(uint32_t start, uint32_t freq, uint32_t bits) {
     uint4 s;
     s.x = ((RANS_L >> bits) << 16) * freq - 1;
@@ -210,12 +212,12 @@ __device__ __forceinline__ uint4 enc_sym_init(uint32_t start, uint32_t freq, uin
     if (freq < 2) {
         s.y = ~0u;
         s.z = start + (1u << bits) - 1;
-        s.w = cmpl;
+        s.w = cmpl << 16;
     } else {
         uint32_t sh = 32 - __clz(freq - 1);                 // smallest sh with freq <= 1<<sh
         s.y = (uint32_t)(((1ull << (sh + 31)) + freq - 1) / freq);
         s.z = start;
-        s.w = cmpl | ((sh - 1) << 16);
+        s.w = (cmpl << 16) | (sh - 1);
     }
     return s;
 }
@@ -228,7 +230,7 @@ __device__ __forceinline__ uint4 enc_sym_init(uint32_t start, uint32_t freq, uin
 // 16-byte symbols and the order-1 kernels keep twice the warps resident.
 __device__ uint32_t g_rcp_freq[4097];
 __device__ __forceinline__ uint32_t enc_sym_pack(uint4 s, uint32_t freq) {
-    return s.z | (freq << 13) | ((s.w >> 16) << 26);
+    return s.z | (freq << 13) | ((s.w & 31) << 26);
 }
 __device__ __forceinline__ uint32_t rcp_of_freq(uint32_t f) {
     uint32_t v;
@@ -241,7 +243,7 @@ __device__ __forceinline__ uint4 enc_sym_unpack(uint32_t c, uint32_t bits) {
     s.x = (f << (31 - bits)) - 1;
     s.y = rcp_of_freq(f);
     s.z = c & 0x1fff;
-    s.w = (((1u << bits) - f) & 0xffff) | ((c >> 26) << 16);
+    s.w = (((1u << bits) - f) << 16) | (c >> 26);
     return s;
 }
 
@@ -253,12 +255,18 @@ __device__ __forceinline__ uint4 enc_sym_unpack(uint32_t c, uint32_t bits) {
 // 512 bytes at a time, instead of millions of scattered 2-byte stores.
 // ------------------------------------------------------------------------
 constexpr uint32_t ORING = 1024;
-struct OutRing {
+// AL: the ring starts at a multiple of its size in the shared window, so that "base + (offset mod size)" is one
+// LOP3 (and, or) instead of a mask and an add.
+template <bool AL>
+struct OutRingT {
     uint8_t *slot;       // slot base (global, 256-byte aligned)
     uint32_t ring_s;     // shared-space address of the ring (16-byte aligned)
     uint32_t off;        // next byte to write is off-1 (downward), offset from slot
     uint32_t hi;         // bytes [off, hi) are still in the ring; hi is a multiple of 16
 
+    __device__ __forceinline__ uint32_t at(uint32_t o) const {
+        return AL ? (ring_s | (o & (ORING - 1))) : (ring_s + (o & (ORING - 1)));
+    }
     // lo: any address at or below everything that will be written; out_end: even address
     // where writing starts (downward).  Up to 15 bytes above out_end may be overwritten
     // when out_end is not 16-byte aligned (callers leave that slack).
@@ -277,7 +285,7 @@ struct OutRing {
             if (o < hi) {
                 uint4 v;
                 asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ring_s + (o & (ORING - 1))));
+                             : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(at(o)));
                 asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(__cvta_generic_to_global(slot + o)),
                              "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
             }
@@ -292,13 +300,13 @@ struct OutRing {
         if (a > hi) a = hi;
         for (uint32_t o = off + 2 * lane; o < a; o += 64) {          // leading 2-byte pieces (off is even)
             uint32_t v;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(ring_s + (o & (ORING - 1))));
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(at(o)));
             *(uint16_t *)(slot + o) = (uint16_t)v;
         }
         for (uint32_t o = a + 16 * lane; o < hi; o += 512) {
             uint4 v;
             asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(ring_s + (o & (ORING - 1))));
+                         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(at(o)));
             asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(__cvta_generic_to_global(slot + o)),
                          "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
         }
@@ -306,35 +314,63 @@ struct OutRing {
         __syncwarp();
     }
 };
+using OutRing = OutRingT<false>;
 
 // One encode step for the warp (rANS_word.h:287-336 + the lane order of
 // rANS_static32x16pr.c:187-231): lanes whose state exceeds x_max emit their low
 // 16 bits; lane 31's word lands at the highest address.  At most 4 steps may
 // pass between two maybe_flush() calls.
-__device__ __forceinline__ uint32_t enc_step(uint32_t R, bool on, uint4 e, OutRing &w, int lane) {
-    bool emit = on && R > e.x;
-    uint32_t mask = __ballot_sync(FULL, emit);
-    if (emit) {
-        uint32_t k = __popc(mask >> lane);
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(w.ring_s + ((w.off - 2 * k) & (ORING - 1))), "r"(R) : "memory");
-        R >>= 16;
+// The renormalisation is written out in PTX so that one predicate serves the ballot, the store and the
+// shift (compiled from C++ the comparison was made twice and the shifted state went through a second
+// register), and the reciprocal's shift is taken straight from the symbol's last word.
+// ALL: every lane is on (the main loops of the 32-lane coders).
+#define B200_ENC_RENORM(PRED, ADDR)                                                              \
+    "{\n\t.reg .pred p, q;\n\t.reg .b32 m, t, k, a;\n\t" PRED                                   \
+    "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"                                                \
+    "shr.b32 t, m, %3;\n\t"                                                                     \
+    "popc.b32 k, t;\n\t"                                                                        \
+    "popc.b32 t, m;\n\t"                                                                        \
+    "sub.u32 a, %1, k;\n\t"                                                                     \
+    "sub.u32 a, a, k;\n\t"                                                                      \
+    "sub.u32 %1, %1, t;\n\t"                                                                    \
+    "sub.u32 %1, %1, t;\n\t"                                                                    \
+    "and.b32 a, a, 1023;\n\t" ADDR                                                              \
+    "@p st.shared.u16 [a], %0;\n\t"                                                             \
+    "@p shr.u32 %0, %0, 16;\n\t}"
+template <bool ALL = false, bool AL>
+__device__ __forceinline__ uint32_t enc_step(uint32_t R, bool on, uint4 e, OutRingT<AL> &w, int lane) {
+    static_assert(ORING == 1024, "the mask in B200_ENC_RENORM");
+    uint32_t off = w.off;
+    if (ALL) {
+        if (AL) asm volatile(B200_ENC_RENORM("setp.gt.u32 p, %0, %2;\n\t", "or.b32 a, a, %4;\n\t")
+                             : "+r"(R), "+r"(off) : "r"(e.x), "r"(lane), "r"(w.ring_s) : "memory");
+        else asm volatile(B200_ENC_RENORM("setp.gt.u32 p, %0, %2;\n\t", "add.u32 a, a, %4;\n\t")
+                          : "+r"(R), "+r"(off) : "r"(e.x), "r"(lane), "r"(w.ring_s) : "memory");
+    } else {
+        const uint32_t on32 = on;
+        if (AL) asm volatile(B200_ENC_RENORM("setp.ne.u32 q, %5, 0;\n\tsetp.gt.u32.and p, %0, %2, q;\n\t", "or.b32 a, a, %4;\n\t")
+                             : "+r"(R), "+r"(off) : "r"(e.x), "r"(lane), "r"(w.ring_s), "r"(on32) : "memory");
+        else asm volatile(B200_ENC_RENORM("setp.ne.u32 q, %5, 0;\n\tsetp.gt.u32.and p, %0, %2, q;\n\t", "add.u32 a, a, %4;\n\t")
+                          : "+r"(R), "+r"(off) : "r"(e.x), "r"(lane), "r"(w.ring_s), "r"(on32) : "memory");
     }
-    w.off -= 2 * __popc(mask);
-    if (on) {
-        uint32_t q = __umulhi(R, e.y) >> (e.w >> 16);
-        R = R + e.z + q * (e.w & 0xffff);
+    w.off = off;
+    if (ALL || on) {
+        uint32_t q;
+        asm("shf.r.wrap.b32 %0, %1, %2, %3;" : "=r"(q) : "r"(__umulhi(R, e.y)), "r"(0), "r"(e.w));
+        R = R + e.z + q * (e.w >> 16);
     }
     return R;
 }
 
 // final states, lane 0 lowest (rANS_word.h:105-117); then everything leaves the ring
-__device__ __forceinline__ void enc_flush(uint32_t R, bool act, int N, OutRing &w, int lane) {
+template <bool AL>
+__device__ __forceinline__ void enc_flush(uint32_t R, bool act, int N, OutRingT<AL> &w, int lane) {
     w.maybe_flush(lane);
     w.off -= 4 * N;
     if (act) {
         uint32_t a = w.off + 4 * lane;       // off is 2-byte aligned only
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(w.ring_s + (a & (ORING - 1))), "r"(R) : "memory");
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(w.ring_s + ((a + 2) & (ORING - 1))), "r"(R >> 16) : "memory");
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(w.at(a)), "r"(R) : "memory");
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(w.at(a + 2)), "r"(R >> 16) : "memory");
     }
     w.final_flush(lane);
 }
@@ -351,7 +387,8 @@ struct __align__(16) EncO0Smem {
 // Not inlined: it is called from three places (payload, RLE meta-data, self-compressed order-1
 // tables), and as a function of its own its hot loop gets a register allocation that does not
 // depend on what surrounds the call.
-template <int N>
+// AL: S.ring sits at a multiple of ORING in the shared window (the order-0 kernel's streams)
+template <int N, bool AL = false>
 __device__ __noinline__ int enc_o0(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_end,
                       uint32_t *tab_len, uint8_t **ptr_out, EncO0Smem &S, int lane,
                       const uint32_t *model = nullptr) {
@@ -393,7 +430,7 @@ __device__ __noinline__ int enc_o0(const uint8_t *in, uint32_t n, uint8_t *out, 
 
     // NB every lane runs the same ballots: lanes >= N (N == 4) are predicated off.
     const bool act = (N == 32) ? true : lane < N;
-    OutRing w;
+    OutRingT<AL> w;
     w.init(out, out_end, S.ring);
     uint32_t R = RANS_L;
     const uint32_t rem = n % N;
@@ -416,10 +453,10 @@ __device__ __noinline__ int enc_o0(const uint8_t *in, uint32_t n, uint8_t *out, 
     auto group = [&](const uint32_t (&s4)[4]) {
         w.maybe_flush(lane);
         uint4 e0 = S.sym[s4[0]], e1 = S.sym[s4[1]], e2 = S.sym[s4[2]], e3 = S.sym[s4[3]];
-        R = enc_step(R, act, e0, w, lane);
-        R = enc_step(R, act, e1, w, lane);
-        R = enc_step(R, act, e2, w, lane);
-        R = enc_step(R, act, e3, w, lane);
+        R = enc_step<N == 32>(R, act, e0, w, lane);
+        R = enc_step<N == 32>(R, act, e1, w, lane);
+        R = enc_step<N == 32>(R, act, e2, w, lane);
+        R = enc_step<N == 32>(R, act, e3, w, lane);
     };
     if (i >= 4 * 512) {
         // The symbols of 512 / N steps are 512 consecutive bytes.  The warp brings them in with one coalesced
@@ -431,7 +468,7 @@ __device__ __noinline__ int enc_o0(const uint8_t *in, uint32_t n, uint8_t *out, 
         const uint32_t st_s = (uint32_t)__cvta_generic_to_shared(S.F);
         while (i & 511) {                                    // steps above the highest chunk boundary
             w.maybe_flush(lane);
-            R = enc_step(R, act, S.sym[q[i - N]], w, lane);
+            R = enc_step<N == 32>(R, act, S.sym[q[i - N]], w, lane);
             i -= N;
         }
         const bool al16 = (((uintptr_t)in) & 15) == 0;
@@ -472,7 +509,7 @@ __device__ __noinline__ int enc_o0(const uint8_t *in, uint32_t n, uint8_t *out, 
     for (; i >= 4 * N; i -= 4 * N) { fetch(sA, i); group(sA); }
     for (; i > 0; i -= N) {
         w.maybe_flush(lane);
-        R = enc_step(R, act, S.sym[q[i - N]], w, lane);
+        R = enc_step<N == 32>(R, act, S.sym[q[i - N]], w, lane);
     }
     enc_flush(R, act, N, w, lane);
     *ptr_out = w.slot + w.off;
@@ -929,7 +966,7 @@ __device__ __forceinline__ void enc_o1_payload(const uint8_t *in, uint32_t n, ui
                 uint32_t rn = rank_of(nb);
                 uint4 en = lds_sym(sym_s + (rn * nsym + rc) * 4);
                 if ((b & 3) == 3) w.maybe_flush(lane);
-                R = enc_step(R, true, e, w, lane);
+                R = enc_step<true>(R, true, e, w, lane);
                 e = en;
                 rs = rc;
                 rc = rn;
@@ -942,7 +979,7 @@ __device__ __forceinline__ void enc_o1_payload(const uint8_t *in, uint32_t n, ui
             uint32_t rn = b >= 2 ? rank_of(byte_of(cur, b - 2)) : 0;
             uint4 en = b >= 2 ? lds_sym(sym_s + (rn * nsym + rc) * 4) : e;
             if ((b & 3) == 3) w.maybe_flush(lane);
-            R = enc_step(R, true, e, w, lane);
+            R = enc_step<true>(R, true, e, w, lane);
             e = en;
             rs = rc;
             rc = rn;
@@ -978,7 +1015,7 @@ __device__ __forceinline__ void enc_o1_payload(const uint8_t *in, uint32_t n, ui
             for (int b = 15; b >= 0; b--) {
                 if (b == 0 && j == 0 && !lead) break;        // the lane's first symbol is coded below
                 if ((b & 3) == 3) w.maybe_flush(lane);
-                R = enc_step(R, act, enc_sym_unpack(ev[b], shift), w, lane);
+                R = enc_step<N == 32>(R, act, enc_sym_unpack(ev[b], shift), w, lane);
             }
             rs = lead ? rk[0] : rk[1];                       // rank of the next symbol to code
             cur = prv;
@@ -994,7 +1031,7 @@ __device__ __forceinline__ void enc_o1_payload(const uint8_t *in, uint32_t n, ui
             const uint32_t rc = rank[(w4[(k - 1) >> 2] >> (8 * ((k - 1) & 3))) & 0xff];
             uint4 e = enc_sym_unpack(symtab[rc * nsym + rs], shift);
             w.maybe_flush(lane);
-            R = enc_step(R, act, e, w, lane);
+            R = enc_step<N == 32>(R, act, e, w, lane);
             rs = rc;
         }
         kstart = 1;
@@ -1003,13 +1040,13 @@ __device__ __forceinline__ void enc_o1_payload(const uint8_t *in, uint32_t n, ui
         uint32_t rc = rank[q[k - 1]];
         uint4 e = enc_sym_unpack(symtab[rc * nsym + rs], shift);
         w.maybe_flush(lane);
-        R = enc_step(R, act, e, w, lane);
+        R = enc_step<N == 32>(R, act, e, w, lane);
         rs = rc;
     }
     if (seg) {
         uint4 e = enc_sym_unpack(symtab[rank[0] * nsym + rs], shift);
         w.maybe_flush(lane);
-        R = enc_step(R, act, e, w, lane);
+        R = enc_step<N == 32>(R, act, e, w, lane);
     }
     enc_flush(R, act, N, w, lane);
     *ptr_out = w.slot + w.off;
