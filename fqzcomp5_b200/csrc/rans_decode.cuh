@@ -200,7 +200,10 @@ struct __align__(16) DecO0Smem {
 };
 static_assert(sizeof(DecO0Smem) == 8192, "DecO0Smem layout");
 
-template <int N, bool ODD, bool AL>
+// WIDE (N == 32, `out` 16-byte aligned): the 8 x 32 symbols of a group are collected in shared memory (the
+// parse scratch is free by now) and leave as sixteen 16-byte stores.  A template parameter, not a flag: as a
+// flag both stores were issued (one of them predicated off) on every step.
+template <int N, bool ODD, bool AL, bool WIDE>
 __device__ __forceinline__ void dec_o0_fast(uint32_t &R_, uint32_t &i_, uint32_t full, uint8_t *out,
                                             WordRing0 &w, DecO0Smem &S, int lane, uint32_t lt) {
     const bool act = (N == 32) ? true : lane < N;
@@ -208,10 +211,7 @@ __device__ __forceinline__ void dec_o0_fast(uint32_t &R_, uint32_t &i_, uint32_t
     const uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(S.lut);
     const uint32_t f_s = (uint32_t)__cvta_generic_to_shared(S.f16);
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(w.ring);
-    // N == 32: the 8 x 32 symbols of a group are collected in shared memory (the parse scratch
-    // is free by now) and leave as sixteen 16-byte stores when `out` allows it
     const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(S.tab);
-    const bool wide = N == 32 && ((uintptr_t)out & 15) == 0;
     uint8_t *o = out + i + (act ? lane : 0);
     while (i + 8 * N <= full && pos + 8 * 64 <= w.end) {
         w.pos = pos;
@@ -223,20 +223,55 @@ __device__ __forceinline__ void dec_o0_fast(uint32_t &R_, uint32_t &i_, uint32_t
             uint32_t fa = f_s + 2 * s;
             uint32_t f = lds_u16a(fa), b = lds_u16a(fa + 512);
             R = f * (R >> 12) + m - b;
-            if (wide) asm volatile("st.shared.u8 [%0], %1;" ::"r"(tile_s + u * 32 + lane), "r"(s) : "memory");
+            if (WIDE) asm volatile("st.shared.u8 [%0], %1;" ::"r"(tile_s + u * 32 + lane), "r"(s) : "memory");
             else if (act) stg_u8(o + u * N, s);
-            bool need = act && R < RANS_L;
-            uint32_t mask = __ballot_sync(FULL, need);
-            // branch-free refill: every lane reads a word (lanes that do not need one read a
-            // valid but unused position), then selects
-            uint32_t p = pos + 2 * __popc(mask & lt);
-            uint32_t wv;
-            if (ODD) wv = lds_u8a(ring_s + (p & (RING0 - 1))) | (lds_u8a(ring_s + ((p + 1) & (RING0 - 1))) << 8);
-            else wv = lds_u16a(AL ? (ring_s | (p & (RING0 - 1))) : (ring_s + (p & (RING0 - 1))));
-            R = need ? ((R << 16) | wv) : R;
-            pos += 2 * __popc(mask);
+            if (N == 32 && !ODD) {
+                // branch-free refill (rANS_word.h:414-476): every lane reads a word (lanes that do not need one
+                // read a valid but unused position), the lanes below 2^15 take theirs.  In PTX so that the
+                // position advances by one three-input add per step and one predicate serves ballot and refill.
+                static_assert(RING0 == 2048, "the mask below");
+                if (AL) asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 m, t, a, v;\n\t"
+                                     "setp.lt.u32 p, %0, 0x8000;\n\t"
+                                     "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+                                     "and.b32 t, m, %2;\n\t"
+                                     "popc.b32 t, t;\n\t"
+                                     "add.u32 a, %1, t;\n\t"
+                                     "add.u32 a, a, t;\n\t"
+                                     "and.b32 a, a, 2046;\n\t"
+                                     "or.b32 a, a, %3;\n\t"
+                                     "ld.shared.u16 v, [a];\n\t"
+                                     "@p mad.lo.u32 %0, %0, 65536, v;\n\t"
+                                     "popc.b32 t, m;\n\t"
+                                     "add.u32 %1, %1, t;\n\t"
+                                     "add.u32 %1, %1, t;\n\t}"
+                                     : "+r"(R), "+r"(pos) : "r"(lt), "r"(ring_s) : "memory");
+                else asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 m, t, a, v;\n\t"
+                                  "setp.lt.u32 p, %0, 0x8000;\n\t"
+                                  "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+                                  "and.b32 t, m, %2;\n\t"
+                                  "popc.b32 t, t;\n\t"
+                                  "add.u32 a, %1, t;\n\t"
+                                  "add.u32 a, a, t;\n\t"
+                                  "and.b32 a, a, 2046;\n\t"
+                                  "add.u32 a, a, %3;\n\t"
+                                  "ld.shared.u16 v, [a];\n\t"
+                                  "@p mad.lo.u32 %0, %0, 65536, v;\n\t"
+                                  "popc.b32 t, m;\n\t"
+                                  "add.u32 %1, %1, t;\n\t"
+                                  "add.u32 %1, %1, t;\n\t}"
+                                  : "+r"(R), "+r"(pos) : "r"(lt), "r"(ring_s) : "memory");
+            } else {
+                bool need = act && R < RANS_L;
+                uint32_t mask = __ballot_sync(FULL, need);
+                uint32_t p = pos + 2 * __popc(mask & lt);
+                uint32_t wv;
+                if (ODD) wv = lds_u8a(ring_s + (p & (RING0 - 1))) | (lds_u8a(ring_s + ((p + 1) & (RING0 - 1))) << 8);
+                else wv = lds_u16a(AL ? (ring_s | (p & (RING0 - 1))) : (ring_s + (p & (RING0 - 1))));
+                R = need ? ((R << 16) | wv) : R;
+                pos += 2 * __popc(mask);
+            }
         }
-        if (wide) {
+        if (WIDE) {
             __syncwarp();
             if (lane < 16) {
                 uint4 v;
@@ -332,12 +367,16 @@ __device__ int dec_o0(const uint8_t *in, uint32_t in_size, uint8_t *out, uint32_
     // Hot loop: groups of 8 steps while 8*64 bytes of words are certainly left, so no
     // end-of-stream bookkeeping and one ring check per group.
     const bool al = (((uint32_t)__cvta_generic_to_shared(S.lut)) & 8191) == 0;
-    if (al) {
-        if (w.pos & 1) dec_o0_fast<N, true, true>(R, i, full, out, w, S, lane, lt);
-        else dec_o0_fast<N, false, true>(R, i, full, out, w, S, lane, lt);
+    const bool wide = N == 32 && ((uintptr_t)out & 15) == 0;
+    if (al && wide) {                                                   // the common case
+        if (w.pos & 1) dec_o0_fast<N, true, true, N == 32>(R, i, full, out, w, S, lane, lt);
+        else dec_o0_fast<N, false, true, N == 32>(R, i, full, out, w, S, lane, lt);
+    } else if (al) {
+        if (w.pos & 1) dec_o0_fast<N, true, true, false>(R, i, full, out, w, S, lane, lt);
+        else dec_o0_fast<N, false, true, false>(R, i, full, out, w, S, lane, lt);
     } else {
-        if (w.pos & 1) dec_o0_fast<N, true, false>(R, i, full, out, w, S, lane, lt);
-        else dec_o0_fast<N, false, false>(R, i, full, out, w, S, lane, lt);
+        if (w.pos & 1) dec_o0_fast<N, true, false, false>(R, i, full, out, w, S, lane, lt);
+        else dec_o0_fast<N, false, false, false>(R, i, full, out, w, S, lane, lt);
     }
     for (; i < full; i += N) {
         uint32_t m = R & 4095;
