@@ -741,13 +741,14 @@ struct __align__(16) EncPrepSmem {
 // in[p-1] (E[0]: context 0), E[n + z] codes the first symbol of lane z >= 1 in context 0 (rANS_static32x16pr.c:
 // 457-525).  An entry is the packed 4-byte symbol (enc_sym_make4) and the reciprocal of its frequency.  Lane z owns
 // [z*seg, (z+1)*seg), lane N-1 also the tail; everything runs backwards.
-__device__ __forceinline__ uint4 enc_sym_unpack2(uint2 c, uint32_t bits) {
+__device__ __forceinline__ EncSym enc_sym_unpack2(uint2 c, uint32_t bits) {
     const uint32_t f = (c.x >> 13) & 0x1fff;
-    uint4 s;
-    s.x = (f << (31 - bits)) - 1;
-    s.y = c.y;
-    s.z = c.x & 0x1fff;
-    s.w = (((1u << bits) - f) << 16) | (c.x >> 26);
+    EncSym s;
+    s.xlim = f << (31 - bits);
+    s.rcp = c.y;
+    s.bias = c.x & 0x1fff;
+    s.cmpl = (1u << bits) - f;
+    s.shw = c.x >> 26;
     return s;
 }
 template <int N>
@@ -761,7 +762,7 @@ __device__ __forceinline__ void enc_o1_payload_stream(const uint2 *E, uint32_t n
     {   // tail on lane N-1, from the end down to N*seg
         const bool lastl = lane == N - 1;
         for (uint32_t p = n - 1; p >= N * seg && p > 0; p--) {
-            uint4 e = make_uint4(0, 0, 0, 0);
+            EncSym e = make_uint4(0, 0, 0, 0);
             if (lastl) e = enc_sym_unpack2(E[p], shift);
             w.maybe_flush(lane);
             R = enc_step(R, lastl, e, w, lane);
@@ -806,13 +807,13 @@ __device__ __forceinline__ void enc_o1_payload_stream(const uint2 *E, uint32_t n
         k = lead ? lead : 1;
     }
     for (; k > 1; k--) {
-        uint4 e = make_uint4(0, 0, 0, 0);
+        EncSym e = make_uint4(0, 0, 0, 0);
         if (act) e = enc_sym_unpack2(q[k - 1], shift);
         w.maybe_flush(lane);
         R = enc_step<N == 32>(R, act, e, w, lane);
     }
     if (seg) {                                               // every lane's first symbol: context 0
-        uint4 e = make_uint4(0, 0, 0, 0);
+        EncSym e = make_uint4(0, 0, 0, 0);
         if (act) e = enc_sym_unpack2(lane ? E[n + lane] : E[0], shift);
         w.maybe_flush(lane);
         R = enc_step<N == 32>(R, act, e, w, lane);

@@ -202,12 +202,12 @@ __device__ inline int put_alphabet(uint8_t *cp, const uint32_t *F) {
 }
 
 // Encoder symbol (rANS_word.h:171-179,201-272) packed into 16 bytes:
-//   x = x_max, y = rcp_freq, z = bias, w = cmpl_freq << 16 | (rcp_shift - 32)
+//   x = x_max + 1, y = rcp_freq, z = bias, w = cmpl_freq << 16 | (rcp_shift - 32)
 // (the shift in the low bits: a wrapping funnel shift takes its count from the low five bits of a
 // register, so a step needs no instruction to extract it)
 __device__ __forceinline__ uint4 enc_sym_init(uint32_t start, uint32_t freq, uint32_t bits) {
     uint4 s;
-    s.x = ((RANS_L >> bits) << 16) * freq - 1;
+    s.x = ((RANS_L >> bits) << 16) * freq;           // a state renormalises when it is >= this (at most 2^31)
     uint32_t cmpl = ((1u << bits) - freq) & 0xffff;
     if (freq < 2) {
         s.y = ~0u;
@@ -237,13 +237,22 @@ __device__ __forceinline__ uint32_t rcp_of_freq(uint32_t f) {
     asm("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(__cvta_generic_to_global(g_rcp_freq + f)));
     return v;
 }
-__device__ __forceinline__ uint4 enc_sym_unpack(uint32_t c, uint32_t bits) {
-    uint32_t f = (c >> 13) & 0x1fff;
-    uint4 s;
-    s.x = (f << (31 - bits)) - 1;
-    s.y = rcp_of_freq(f);
-    s.z = c & 0x1fff;
-    s.w = (((1u << bits) - f) << 16) | (c >> 26);
+// What a step needs, as separate values: a symbol fetched from the 16-byte table pays one shift for cmpl, one
+// unpacked from the 4-byte form is used as it is unpacked (packing it into the uint4 layout and taking it apart
+// again cost three instructions per order-1 step).  shw: the shift is its low five bits.
+struct EncSym {
+    uint32_t xlim, rcp, bias, cmpl, shw;
+    __device__ __forceinline__ EncSym() {}
+    __device__ __forceinline__ EncSym(uint4 s) : xlim(s.x), rcp(s.y), bias(s.z), cmpl(s.w >> 16), shw(s.w) {}
+};
+__device__ __forceinline__ EncSym enc_sym_unpack(uint32_t c, uint32_t bits) {
+    const uint32_t f = (c >> 13) & 0x1fff;
+    EncSym s;
+    s.xlim = f << (31 - bits);
+    s.rcp = rcp_of_freq(f);
+    s.bias = c & 0x1fff;
+    s.cmpl = (1u << bits) - f;
+    s.shw = c >> 26;
     return s;
 }
 
@@ -338,26 +347,26 @@ using OutRing = OutRingT<false>;
     "@p st.shared.u16 [a], %0;\n\t"                                                             \
     "@p shr.u32 %0, %0, 16;\n\t}"
 template <bool ALL = false, bool AL>
-__device__ __forceinline__ uint32_t enc_step(uint32_t R, bool on, uint4 e, OutRingT<AL> &w, int lane) {
+__device__ __forceinline__ uint32_t enc_step(uint32_t R, bool on, EncSym e, OutRingT<AL> &w, int lane) {
     static_assert(ORING == 1024, "the mask in B200_ENC_RENORM");
     uint32_t off = w.off;
     if (ALL) {
-        if (AL) asm volatile(B200_ENC_RENORM("setp.gt.u32 p, %0, %2;\n\t", "or.b32 a, a, %4;\n\t")
-                             : "+r"(R), "+r"(off) : "r"(e.x), "r"(lane), "r"(w.ring_s) : "memory");
-        else asm volatile(B200_ENC_RENORM("setp.gt.u32 p, %0, %2;\n\t", "add.u32 a, a, %4;\n\t")
-                          : "+r"(R), "+r"(off) : "r"(e.x), "r"(lane), "r"(w.ring_s) : "memory");
+        if (AL) asm volatile(B200_ENC_RENORM("setp.ge.u32 p, %0, %2;\n\t", "or.b32 a, a, %4;\n\t")
+                             : "+r"(R), "+r"(off) : "r"(e.xlim), "r"(lane), "r"(w.ring_s) : "memory");
+        else asm volatile(B200_ENC_RENORM("setp.ge.u32 p, %0, %2;\n\t", "add.u32 a, a, %4;\n\t")
+                          : "+r"(R), "+r"(off) : "r"(e.xlim), "r"(lane), "r"(w.ring_s) : "memory");
     } else {
         const uint32_t on32 = on;
-        if (AL) asm volatile(B200_ENC_RENORM("setp.ne.u32 q, %5, 0;\n\tsetp.gt.u32.and p, %0, %2, q;\n\t", "or.b32 a, a, %4;\n\t")
-                             : "+r"(R), "+r"(off) : "r"(e.x), "r"(lane), "r"(w.ring_s), "r"(on32) : "memory");
-        else asm volatile(B200_ENC_RENORM("setp.ne.u32 q, %5, 0;\n\tsetp.gt.u32.and p, %0, %2, q;\n\t", "add.u32 a, a, %4;\n\t")
-                          : "+r"(R), "+r"(off) : "r"(e.x), "r"(lane), "r"(w.ring_s), "r"(on32) : "memory");
+        if (AL) asm volatile(B200_ENC_RENORM("setp.ne.u32 q, %5, 0;\n\tsetp.ge.u32.and p, %0, %2, q;\n\t", "or.b32 a, a, %4;\n\t")
+                             : "+r"(R), "+r"(off) : "r"(e.xlim), "r"(lane), "r"(w.ring_s), "r"(on32) : "memory");
+        else asm volatile(B200_ENC_RENORM("setp.ne.u32 q, %5, 0;\n\tsetp.ge.u32.and p, %0, %2, q;\n\t", "add.u32 a, a, %4;\n\t")
+                          : "+r"(R), "+r"(off) : "r"(e.xlim), "r"(lane), "r"(w.ring_s), "r"(on32) : "memory");
     }
     w.off = off;
     if (ALL || on) {
         uint32_t q;
-        asm("shf.r.wrap.b32 %0, %1, %2, %3;" : "=r"(q) : "r"(__umulhi(R, e.y)), "r"(0), "r"(e.w));
-        R = R + e.z + q * (e.w >> 16);
+        asm("shf.r.wrap.b32 %0, %1, %2, %3;" : "=r"(q) : "r"(__umulhi(R, e.rcp)), "r"(0), "r"(e.shw));
+        R = R + e.bias + q * e.cmpl;
     }
     return R;
 }
@@ -921,7 +930,7 @@ __device__ __forceinline__ void enc_o1_payload(const uint8_t *in, uint32_t n, ui
     {   // tail on lane N-1, from the end down to N*seg
         const bool lastl = lane == N - 1;
         for (uint32_t p = n - 1; p >= N * seg && p > 0; p--) {
-            uint4 e = make_uint4(0, 0, 0, 0);
+            EncSym e = make_uint4(0, 0, 0, 0);
             if (lastl) e = enc_sym_unpack(symtab[rank[in[p - 1]] * nsym + rank[in[p]]], shift);
             w.maybe_flush(lane);
             R = enc_step(R, lastl, e, w, lane);
@@ -956,7 +965,7 @@ __device__ __forceinline__ void enc_o1_payload(const uint8_t *in, uint32_t n, ui
         // the encoder symbol of the NEXT step is fetched (rank look-up, table look-up, unpack)
         // while the current step runs: none of it depends on the state
         uint32_t rc = rank_of(byte_of(cur, 14));
-        uint4 e = lds_sym(sym_s + (rc * nsym + rs) * 4);
+        EncSym e = lds_sym(sym_s + (rc * nsym + rs) * 4);
         for (uint32_t j = J - 1; j >= 1; j--) {
             uint4 nn = j >= 2 ? ldg_u128(v + j - 2) : make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -964,7 +973,7 @@ __device__ __forceinline__ void enc_o1_payload(const uint8_t *in, uint32_t n, ui
                 // next step codes byte b-1 in the context of byte b-2 (crossing into nxt at the low end)
                 uint32_t nb = b >= 2 ? byte_of(cur, b - 2) : byte_of(nxt, 14 + b);
                 uint32_t rn = rank_of(nb);
-                uint4 en = lds_sym(sym_s + (rn * nsym + rc) * 4);
+                EncSym en = lds_sym(sym_s + (rn * nsym + rc) * 4);
                 if ((b & 3) == 3) w.maybe_flush(lane);
                 R = enc_step<true>(R, true, e, w, lane);
                 e = en;
@@ -977,7 +986,7 @@ __device__ __forceinline__ void enc_o1_payload(const uint8_t *in, uint32_t n, ui
 #pragma unroll
         for (int b = 15; b >= 1; b--) {                      // group 0: its byte 0 is the lane's first symbol
             uint32_t rn = b >= 2 ? rank_of(byte_of(cur, b - 2)) : 0;
-            uint4 en = b >= 2 ? lds_sym(sym_s + (rn * nsym + rc) * 4) : e;
+            EncSym en = b >= 2 ? lds_sym(sym_s + (rn * nsym + rc) * 4) : e;
             if ((b & 3) == 3) w.maybe_flush(lane);
             R = enc_step<true>(R, true, e, w, lane);
             e = en;
@@ -1029,7 +1038,7 @@ __device__ __forceinline__ void enc_o1_payload(const uint8_t *in, uint32_t n, ui
         const uint32_t w4[4] = {h16.x, h16.y, h16.z, h16.w};
         for (uint32_t k = kstart; k-- > 1;) {
             const uint32_t rc = rank[(w4[(k - 1) >> 2] >> (8 * ((k - 1) & 3))) & 0xff];
-            uint4 e = enc_sym_unpack(symtab[rc * nsym + rs], shift);
+            EncSym e = enc_sym_unpack(symtab[rc * nsym + rs], shift);
             w.maybe_flush(lane);
             R = enc_step<N == 32>(R, act, e, w, lane);
             rs = rc;
@@ -1038,13 +1047,13 @@ __device__ __forceinline__ void enc_o1_payload(const uint8_t *in, uint32_t n, ui
     }
     for (uint32_t k = kstart; k-- > 1;) {
         uint32_t rc = rank[q[k - 1]];
-        uint4 e = enc_sym_unpack(symtab[rc * nsym + rs], shift);
+        EncSym e = enc_sym_unpack(symtab[rc * nsym + rs], shift);
         w.maybe_flush(lane);
         R = enc_step<N == 32>(R, act, e, w, lane);
         rs = rc;
     }
     if (seg) {
-        uint4 e = enc_sym_unpack(symtab[rank[0] * nsym + rs], shift);
+        EncSym e = enc_sym_unpack(symtab[rank[0] * nsym + rs], shift);
         w.maybe_flush(lane);
         R = enc_step<N == 32>(R, act, e, w, lane);
     }
