@@ -1174,6 +1174,18 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
     else { symtab = (uint32_t *)pool_alloc(pool, hw * 4, lane); if (!symtab) return 2; }
     uint32_t shift = 12, tl = 0;
     const bool wide = nsym > 64;              // large alphabets: row-at-a-time, lanes across columns
+    // Pair counts from hist_kernel, small alphabet: the passes below walk a row per lane, element by element, and on
+    // the matrix in global memory every element was an L2 round trip of its own (8 % of the kernel's samples sat on
+    // those loads).  The matrix is brought into the shared-memory area of the encoder symbols, worked on there, and
+    // turned into the symbols in place; the table coder's scratch aliases that area, so around it the normalised
+    // rows go back to their global home for a moment.
+    uint32_t *const Hg = H;
+    const bool staged = h_global && sym_smem && !wide;
+    if (staged) {
+        for (uint32_t j = lane; j < hw; j += 32) symtab[j] = Hg[j];
+        __syncwarp();
+        H = symtab;
+    }
     if (wide) {
         uint32_t hdr = 0;
         if (lane == 0) {                      // alphabet of the contexts, 0 forced in (:357-361)
@@ -1332,7 +1344,12 @@ __device__ int enc_o1(const uint8_t *in, uint32_t n, uint8_t *out, uint8_t *out_
         }
         __syncwarp();
     };
-    if (h_global || wide) compress_table();       // its scratch aliases the symbol area
+    if (h_global || wide) {                       // its scratch aliases the symbol area
+        const bool park = staged && tl > 1000;    // (the table coder does nothing for shorter tables)
+        if (park) { for (uint32_t j = lane; j < hw; j += 32) Hg[j] = H[j]; __syncwarp(); }
+        compress_table();
+        if (park) { for (uint32_t j = lane; j < hw; j += 32) H[j] = Hg[j]; __syncwarp(); }
+    }
     if (!wide)
     for (uint32_t i0 = 0; i0 < nsym; i0 += 32) { const uint32_t i = i0 + lane; if (i >= nsym) continue;
         uint32_t *row = H + i * nsym;

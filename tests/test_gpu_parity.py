@@ -342,6 +342,53 @@ def test_in_slot_output(gpu_codec, checker):
         assert np.array_equal(back[int(offs[k]):int(offs[k]) + int(sizes[k])], parts[k]), k
 
 
+def test_histogram_pass_alignments_and_ranges(gpu_codec, checker):
+    """hist_kernel (counts and pair counts in front of the coders): inputs at odd device addresses, sizes around
+    its loop boundaries, and symbol ranges either side of the limit of its byte-indexed pair matrix (a span of 90
+    symbols fits, 91 goes through the rank-space form), with and without symbol 0 in the data, sticky and not."""
+    import torch
+    rng = np.random.default_rng(11)
+
+    def sticky(n, lo, hi, keep):
+        draw = rng.random(n) >= keep
+        draw[0] = True
+        vals = rng.integers(lo, hi + 1, n, dtype=np.uint8)
+        idx = np.where(draw, np.arange(n), 0)
+        np.maximum.accumulate(idx, out=idx)
+        return vals[idx]
+
+    items = []
+    for n in (4096, 4097, 4111, 32767, 32768, 32769 + 16, 65536 + 15, 262144 + 7):
+        for lo, hi, keep in ((2, 40, 0.875), (0, 40, 0.875), (10, 99, 0.5), (10, 100, 0.5), (1, 200, 0.9), (0, 255, 0.0),
+                             (7, 7, 0.0), (33, 71, 0.0)):
+            items.append((sticky(n, lo, hi, keep), 5 if (n + hi) % 3 else 1))
+    items += [(sticky(70001, 2, 40, 0.875), 4), (sticky(5000, 2, 40, 0.875), 0), (np.repeat(np.arange(2, 41, dtype=np.uint8), 997), 5)]
+    sizes = np.array([d.size for d, _ in items], np.uint32)
+    orders = np.array([o for _, o in items], np.int32)
+    offs, at = [], 0
+    for k, (d, _) in enumerate(items):
+        at += k % 16                       # every alignment of the first byte
+        offs.append(at)
+        at += d.size
+    offs = np.array(offs, np.uint64)
+    buf = np.zeros(at + 64, np.uint8)
+    for (d, _), o in zip(items, offs):
+        buf[int(o):int(o) + d.size] = d
+    d_in = torch.from_numpy(buf).cuda()
+    cap = gpu_codec.compress_slots_bound(sizes, orders)
+    d_out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    d_off = torch.zeros(len(items), dtype=torch.int64, device="cuda")
+    d_sz = torch.zeros(len(items), dtype=torch.int32, device="cuda")
+    st = torch.cuda.Stream()
+    gpu_codec.compress_batch_dev2(st.cuda_stream, d_in.data_ptr(), offs, sizes, orders, d_out.data_ptr(), cap,
+                                  d_off.data_ptr(), d_sz.data_ptr(), flags=gpu_codec.OUT_IN_SLOT)
+    st.synchronize()
+    off, sz, comp = d_off.cpu().numpy(), d_sz.cpu().numpy(), d_out.cpu().numpy()
+    for k, (d, o) in enumerate(items):
+        want = checker.compress(d.tobytes(), int(o))
+        assert comp[off[k]:off[k] + sz[k]].tobytes() == want, (k, d.size, int(d.min()), int(d.max()), int(o))
+
+
 def test_method_trial_device_resident(gpu_codec, checker):
     """b200rans_compress_trials_dev: ragged trial with inputs and winners in HBM, winners packed without
     gaps (pack_align 1) as the block pipeline uses it."""
