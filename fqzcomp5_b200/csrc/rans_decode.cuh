@@ -462,16 +462,34 @@ __device__ __forceinline__ void dec_o1_fast(uint32_t &R_, uint32_t &ctx_, uint32
                 R = (c1 - c0) * (R >> shift) + m - c0;
                 ctx = r;
                 acc[g] |= lds_u8a(sym_s + r) << (8 * u);
-                bool need = R < RANS_L;
-                uint32_t bal = __ballot_sync(FULL, need);
-                if (need) {
-                    uint32_t p = pos + 2 * __popc(bal & lt);
-                    uint32_t wv = ODD ? (lds_u8a(ring_s + (p & (RING - 1))) |
-                                         (lds_u8a(ring_s + ((p + 1) & (RING - 1))) << 8))
-                                      : lds_u16a(ring_s + (p & (RING - 1)));
-                    R = (R << 16) | wv;
+                if (!ODD) {
+                    // branch-free refill, as in dec_o0_fast: every lane reads a word, the lanes below 2^15 take theirs
+                    static_assert(RING == 1024, "the mask below");
+                    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 m, t, a, v;\n\t"
+                                 "setp.lt.u32 p, %0, 0x8000;\n\t"
+                                 "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+                                 "and.b32 t, m, %2;\n\t"
+                                 "popc.b32 t, t;\n\t"
+                                 "add.u32 a, %1, t;\n\t"
+                                 "add.u32 a, a, t;\n\t"
+                                 "and.b32 a, a, 1022;\n\t"
+                                 "add.u32 a, a, %3;\n\t"
+                                 "ld.shared.u16 v, [a];\n\t"
+                                 "@p mad.lo.u32 %0, %0, 65536, v;\n\t"
+                                 "popc.b32 t, m;\n\t"
+                                 "add.u32 %1, %1, t;\n\t"
+                                 "add.u32 %1, %1, t;\n\t}"
+                                 : "+r"(R), "+r"(pos) : "r"(lt), "r"(ring_s) : "memory");
+                } else {
+                    bool need = R < RANS_L;
+                    uint32_t bal = __ballot_sync(FULL, need);
+                    if (need) {
+                        uint32_t p = pos + 2 * __popc(bal & lt);
+                        uint32_t wv = lds_u8a(ring_s + (p & (RING - 1))) | (lds_u8a(ring_s + ((p + 1) & (RING - 1))) << 8);
+                        R = (R << 16) | wv;
+                    }
+                    pos += 2 * __popc(bal);
                 }
-                pos += 2 * __popc(bal);
             }
         }
         stg_u128(o + k, acc[0], acc[1], acc[2], acc[3]);
@@ -554,16 +572,34 @@ __device__ __forceinline__ void dec_o1_fast_big(uint32_t &R_, uint32_t &ctx_, ui
                 R = (((e >> 8) & 0xfff) + 1) * (R >> T.shift) + m - (e >> 20);
                 ctx = r;
                 acc[g] |= lds_u8a(sym_s + r) << (8 * u);
-                bool need = R < RANS_L;
-                uint32_t bal = __ballot_sync(FULL, need);
-                if (need) {
-                    uint32_t p = pos + 2 * __popc(bal & lt);
-                    uint32_t wv = ODD ? (lds_u8a(ring_s + (p & (RING - 1))) |
-                                         (lds_u8a(ring_s + ((p + 1) & (RING - 1))) << 8))
-                                      : lds_u16a(ring_s + (p & (RING - 1)));
-                    R = (R << 16) | wv;
+                if (!ODD) {
+                    // branch-free refill, as in dec_o0_fast: every lane reads a word, the lanes below 2^15 take theirs
+                    static_assert(RING == 1024, "the mask below");
+                    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 m, t, a, v;\n\t"
+                                 "setp.lt.u32 p, %0, 0x8000;\n\t"
+                                 "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+                                 "and.b32 t, m, %2;\n\t"
+                                 "popc.b32 t, t;\n\t"
+                                 "add.u32 a, %1, t;\n\t"
+                                 "add.u32 a, a, t;\n\t"
+                                 "and.b32 a, a, 1022;\n\t"
+                                 "add.u32 a, a, %3;\n\t"
+                                 "ld.shared.u16 v, [a];\n\t"
+                                 "@p mad.lo.u32 %0, %0, 65536, v;\n\t"
+                                 "popc.b32 t, m;\n\t"
+                                 "add.u32 %1, %1, t;\n\t"
+                                 "add.u32 %1, %1, t;\n\t}"
+                                 : "+r"(R), "+r"(pos) : "r"(lt), "r"(ring_s) : "memory");
+                } else {
+                    bool need = R < RANS_L;
+                    uint32_t bal = __ballot_sync(FULL, need);
+                    if (need) {
+                        uint32_t p = pos + 2 * __popc(bal & lt);
+                        uint32_t wv = lds_u8a(ring_s + (p & (RING - 1))) | (lds_u8a(ring_s + ((p + 1) & (RING - 1))) << 8);
+                        R = (R << 16) | wv;
+                    }
+                    pos += 2 * __popc(bal);
                 }
-                pos += 2 * __popc(bal);
             }
         }
         stg_u128(o + k, acc[0], acc[1], acc[2], acc[3]);
