@@ -405,6 +405,9 @@ def measure_codec(args, name, data, env, with_cpu):
         torch.cuda.synchronize()
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    # the steps issued back to back left the same bytes as the checked first pass
+    assert int(d_st.abs().sum()) == 0 and torch.equal(d_back, d_in), "round trip mismatch after the timed steps"
+    assert np.array_equal(d_csz.cpu().numpy().astype(np.uint32), csz), "stream sizes changed during the timed steps"
     ms_enc, ms_dec = float(np.mean(t_enc)), float(np.mean(t_dec))
     # streams of the first slices, as the device left them (for the byte comparison with the CPU below)
     kpar = min(n, 64)
