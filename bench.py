@@ -36,7 +36,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from fqzcomp5_b200 import synth  # noqa: E402
+from fqzcomp5_b200 import partition, synth  # noqa: E402
 
 WORKLOADS = {
     # name: (generator, order, default bytes, description)
@@ -606,7 +606,7 @@ def run_blocks(args, env, seq, qual, ngpu):
     out_cap = n // 2 + (64 << 20)
     outs = [bc.PinnedBuffer(out_cap) for _ in range(ngpu * W)]
     backs = [bc.PinnedBuffer(n + 4096) for _ in range(ngpu * W)]
-    slot = lambda b: (b % ngpu) * W + (b // ngpu) % W
+    slot = lambda b: partition.worker_slot(b, ngpu, W)
     tlist = [texts[b % ndist].array for b in range(nb)]
     olist = [outs[slot(b)].array for b in range(nb)]
     blist = [backs[slot(b)].array for b in range(nb)]

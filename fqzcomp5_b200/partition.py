@@ -16,6 +16,14 @@ def owner(block, world):
     return block % world
 
 
+def worker_slot(block, ngpu, workers):
+    """The library's block calls (csrc/block.cu, b200fqz_*_blocks_multi) run block b on worker
+    (b % ngpu, (b // ngpu) % workers): the index of that worker among ngpu * workers.  A caller that gives
+    every worker its own output buffer (bench.py's config-5 workload) uses this to pick it: two blocks with
+    the same slot are never in flight together."""
+    return owner(block, ngpu) * workers + (block // ngpu) % workers
+
+
 def gather_in_order(per_rank, nblocks, world):
     """per_rank[r] = results of blocks_of_rank(nblocks, r, world), in that order.
     Returns the results in block (dispatch) order, as the reference's ordered

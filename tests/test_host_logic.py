@@ -36,6 +36,18 @@ def test_partition_round_robin():
         assert partition.gather_in_order(per_rank, 64, world) == [("blk", b) for b in range(64)]
 
 
+def test_worker_slots_never_collide_in_flight():
+    """bench.py gives every (device, worker) of the library's block calls its own output buffer: block b runs on
+    worker (b % ngpu, (b // ngpu) % W), so blocks sharing a slot are W * ngpu dispatches apart."""
+    for ngpu in (1, 2, 4, 8):
+        for W in (1, 2, 3):
+            slots = [partition.worker_slot(b, ngpu, W) for b in range(64)]
+            assert set(slots) == set(range(ngpu * W))
+            for b in range(64 - ngpu * W):
+                assert len(set(slots[b:b + ngpu * W])) == ngpu * W
+            assert all(s // W == partition.owner(b, ngpu) for b, s in enumerate(slots))
+
+
 def _worker(rank, world, port, nblocks, q):
     import torch
     import torch.distributed as dist
